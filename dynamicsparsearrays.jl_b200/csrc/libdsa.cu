@@ -1,0 +1,891 @@
+// libdsa — C ABI (include/dsa.h) over the device structures of pma.cuh / pcsr.cuh.
+// Host orchestration only: every data-parallel step is a kernel launched on the handle's stream.
+#include <memory>
+#include <mutex>
+#include "pcsr.cuh"
+
+namespace dsa {
+
+Prof& prof() {
+    static Prof p;
+    return p;
+}
+
+static thread_local std::string g_last_error;
+
+// ---------------------------------------------------------------------------------------------
+// Pcsr::set_batch_d — batched setindex! of one orientation (pcsr.jl:341-347 per op), DESIGN.md §4
+// ---------------------------------------------------------------------------------------------
+struct BatchStats {
+    int64_t missing, minkey, maxkey, maxpart_nz, maxkey_nz, minpart;
+};
+
+static BatchStats lookup_and_stats(Pcsr& P, PcsrWorkspace& ws, const int64_t* d_inkeys, const int64_t* d_partkeys, const double* d_vals,
+                                   int64_t n, cudaStream_t st) {
+    int32_t* op_slot = ws.op_slot.ensure((size_t)n);
+    int64_t* cs = ws.cs.ensure(CS_WORDS);
+    int64_t* hcs = ws.h_cs.ensure(CS_WORDS);
+    DSA_LAUNCH("colstat_init", k_colstat_init, 1, 1, 0, st, cs);
+    DSA_LAUNCH("col_lookup", k_col_lookup, grid_for(n, 256), 256, 0, st, d_partkeys, d_inkeys, d_vals, n, P.d_live_keys.p, P.d_live_slot.p,
+               P.nlive(), op_slot, cs);
+    DSA_CUDA(cudaMemcpyAsync(hcs, cs, CS_WORDS * 8, cudaMemcpyDeviceToHost, st));
+    DSA_CUDA(cudaStreamSynchronize(st));
+    return BatchStats{hcs[CS_MISSING], hcs[CS_MINKEY], hcs[CS_MAXKEY], hcs[CS_MAXPART_NZ], hcs[CS_MAXKEY_NZ], hcs[CS_MINPART]};
+}
+
+void Pcsr::set_batch_d(PcsrWorkspace& ws, const int64_t* d_inkeys, const int64_t* d_partkeys, const double* d_vals, int64_t n,
+                       int64_t* max_part_nz, int64_t* max_key_nz, cudaStream_t st) {
+    if (n <= 0) return;
+    BatchStats bs = lookup_and_stats(*this, ws, d_inkeys, d_partkeys, d_vals, n, st);
+    if (bs.minkey < 1) throw DsaError{DSA_ERR_ARGUMENT, "in-array keys must be >= 1 (key 0 is the semaphore key, pcsr.jl:23)"};
+    if (max_part_nz) *max_part_nz = bs.maxpart_nz;
+    if (max_key_nz) *max_key_nz = bs.maxkey_nz;
+    const unsigned gr = grid_for(n, 256);
+    std::vector<int32_t> new_slots_h;
+    if (bs.missing > 0) {
+        // absent columns: distinct keys in first-arrival order -> addcolumn! plan (pcsr.jl:148-169) on the host mirror
+        int32_t* flag = ws.flag32.ensure((size_t)n);
+        int32_t* idx = ws.idx32.ensure((size_t)n);
+        int64_t* mk = ws.miss_keys.ensure((size_t)bs.missing);
+        DSA_LAUNCH("flag_missing", k_flag_missing, gr, 256, 0, st, ws.op_slot.p, n, flag);
+        exclusive_scan_i32<int32_t>(ws.batch.scan, flag, idx, n, nullptr, st);
+        DSA_LAUNCH("compact_missing", k_compact_missing, gr, 256, 0, st, ws.op_slot.p, d_partkeys, idx, n, mk);
+        ws.h_tmp.resize((size_t)bs.missing);
+        DSA_CUDA(cudaMemcpyAsync(ws.h_tmp.data(), mk, (size_t)bs.missing * 8, cudaMemcpyDeviceToHost, st));
+        DSA_CUDA(cudaStreamSynchronize(st));
+        std::vector<int64_t> distinct;
+        {
+            std::unordered_set<int64_t> seen;
+            seen.reserve(ws.h_tmp.size() * 2);
+            for (int64_t k : ws.h_tmp)
+                if (seen.insert(k).second) distinct.push_back(k);
+        }
+        std::vector<int64_t> out_key, out_old;
+        std::vector<uint8_t> out_live;
+        const int64_t nold = nslots();
+        const int64_t nnew_slots = colmap_plan(slot_key.data(), slot_live.data(), nold, distinct.data(), (int64_t)distinct.size(), out_key,
+                                               out_live, out_old);
+        if (nnew_slots >= (int64_t(1) << 31)) throw DsaError{DSA_ERR_ARGUMENT, "too many partitions"};
+        std::vector<int32_t> old2new((size_t)std::max<int64_t>(nold, 1), -1);
+        for (int64_t t = 0; t < nnew_slots; ++t) {
+            if (out_old[(size_t)t] > 0) old2new[(size_t)out_old[(size_t)t] - 1] = (int32_t)t;
+            else if (out_live[(size_t)t]) new_slots_h.push_back((int32_t)t);
+        }
+        DBuf<int64_t> new_sem;
+        new_sem.ensure((size_t)nnew_slots + 1);
+        DSA_LAUNCH("fill_sem", k_fill_i64, grid_for(nnew_slots, 256), 256, 0, st, new_sem.p, nnew_slots, (int64_t)-1);
+        if (nold > 0) {
+            int32_t* d_o2n = ws.old2new.ensure((size_t)nold);
+            DSA_CUDA(cudaMemcpyAsync(d_o2n, old2new.data(), (size_t)nold * 4, cudaMemcpyHostToDevice, st));
+            DSA_LAUNCH("renumber", k_renumber, grid_for(nold, 256), 256, 0, st, d_sem.p, d_o2n, nold, new_sem.p, pma.vals.p);
+        }
+        DSA_CUDA(cudaStreamSynchronize(st));
+        d_sem.swap(new_sem);
+        slot_key.swap(out_key);
+        slot_live.swap(out_live);
+        nb_partitions += (int64_t)distinct.size();
+        rebuild_live_and_upload(st);
+        next_dirty = true;
+        // slots changed: look every op up again
+        int64_t* cs = ws.cs.ensure(CS_WORDS);
+        DSA_LAUNCH("colstat_init", k_colstat_init, 1, 1, 0, st, cs);
+        DSA_LAUNCH("col_lookup", k_col_lookup, gr, 256, 0, st, d_partkeys, (const int64_t*)nullptr, (const double*)nullptr, n, d_live_keys.p,
+                   d_live_slot.p, nlive(), ws.op_slot.p, cs);
+    }
+    ensure_next(ws, st);
+    const int64_t nnew = (int64_t)new_slots_h.size();
+    const int64_t ntot = n + nnew;
+    int32_t* d_new = ws.new_slots.ensure((size_t)nnew + 1);
+    if (nnew) DSA_CUDA(cudaMemcpyAsync(d_new, new_slots_h.data(), (size_t)nnew * 4, cudaMemcpyHostToDevice, st));
+    const int kb = std::max(1, bits_for((uint64_t)bs.maxkey));
+    const int pb = std::max(1, bits_for((uint64_t)std::max<int64_t>(nslots() - 1, 1)));
+    if (kb + pb > 64) throw DsaError{DSA_ERR_ARGUMENT, "key range too wide: bits(max in-array key) + bits(#partitions) must be <= 64"};
+    uint64_t* sk = ws.sk.ensure((size_t)ntot);
+    uint32_t* perm = ws.perm.ensure((size_t)ntot);
+    const unsigned grt = grid_for(ntot, 256);
+    DSA_LAUNCH("make_sortkeys", k_make_sortkeys, grt, 256, 0, st, ws.op_slot.p, d_inkeys, n, d_new, nnew, kb, sk, perm);
+    radix_sort_pairs(ws.sort, sk, perm, ntot, kb + pb, st);
+    int32_t* flag = ws.flag32.ensure((size_t)ntot);
+    int32_t* uidx = ws.idx32.ensure((size_t)ntot);
+    int64_t* nuniq_dev = ws.nuniq.ensure(4) + 2;
+    DSA_LAUNCH("flag_run_last", k_flag_run_last, grt, 256, 0, st, sk, ntot, flag);
+    exclusive_scan_i32<int32_t>(ws.batch.scan, flag, uidx, ntot, nuniq_dev, st);
+    int32_t* u_pid = ws.u_pid.ensure((size_t)ntot);
+    int64_t* u_key = ws.u_key.ensure((size_t)ntot);
+    double* u_val = ws.u_val.ensure((size_t)ntot);
+    DSA_LAUNCH("gather_unique_ops", k_gather_unique_ops, grt, 256, 0, st, sk, perm, flag, uidx, ntot, n, kb, d_inkeys, d_vals, u_pid, u_key,
+               u_val);
+    if (nnew) DSA_CUDA(cudaStreamSynchronize(st));   // new_slots_h is read by the async copy above
+    pma.apply_sorted_ops(ws.batch, u_pid, u_key, u_val, ntot, d_sem.p, d_next.p, st, false, nuniq_dev);
+    if (bs.maxkey > max_inkey) max_inkey = bs.maxkey;
+    next_dirty = true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// handles
+// ---------------------------------------------------------------------------------------------
+struct StreamHolder {
+    cudaStream_t st = nullptr;
+    bool owned = false;
+    void create() {
+        DSA_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        owned = true;
+    }
+    void set(cudaStream_t s) {
+        if (owned && st) cudaStreamDestroy(st);
+        st = s;
+        owned = false;
+    }
+    ~StreamHolder() {
+        if (owned && st) cudaStreamDestroy(st);
+    }
+};
+
+// staging of host batches
+struct Staging {
+    DBuf<int64_t> a, b;
+    DBuf<double> v, out;
+};
+
+}  // namespace dsa
+
+using namespace dsa;
+
+struct dsa_vec {
+    PmaCore pma;
+    int64_t n = 0;   // vector.jl:2
+    PcsrWorkspace ws;
+    Staging stg;
+    StreamHolder sh;
+};
+
+struct dsa_matrix {
+    Pcsr colmajor, rowmajor;   // matrix.jl:6-7
+    int64_t m = 0, n = 0;      // matrix.jl:2-3
+    PcsrWorkspace ws;
+    Staging stg;
+    StreamHolder sh;
+    DBuf<int32_t> d_slots;
+    DBuf<int64_t> d_ids;
+};
+
+#define DSA_TRY try {
+#define DSA_CATCH                                                              \
+    }                                                                          \
+    catch (const DsaError& e) {                                                \
+        g_last_error = e.msg;                                                  \
+        return e.code;                                                         \
+    }                                                                          \
+    catch (const std::bad_alloc&) {                                            \
+        g_last_error = "host out of memory";                                   \
+        return DSA_ERR_OOM;                                                    \
+    }                                                                          \
+    catch (const std::exception& e) {                                          \
+        g_last_error = e.what();                                               \
+        return DSA_ERR_INTERNAL;                                               \
+    }
+
+static void require_device() {
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess || c == 0) {
+        cudaGetLastError();
+        throw DsaError{DSA_ERR_CUDA, "no CUDA device available: libdsa has no CPU fallback"};
+    }
+}
+
+template <typename T>
+static T* h2d(DBuf<T>& buf, const T* h, int64_t n, cudaStream_t st) {
+    T* d = buf.ensure((size_t)std::max<int64_t>(n, 1));
+    if (n > 0) DSA_CUDA(cudaMemcpyAsync(d, h, (size_t)n * sizeof(T), cudaMemcpyHostToDevice, st));
+    return d;
+}
+
+// ---- vector batch (plain PMA): sort by key, last writer wins, merge -----------------------------------------------
+static void vec_sorted_unique(dsa_vec* v, const int64_t* d_keys, const double* d_vals, int64_t n, bool build, int combine,
+                              int64_t** out_k, double** out_v, int64_t* nuniq_host, int64_t** nuniq_dev, int64_t* maxkey_nz,
+                              int64_t* maxkey) {
+    cudaStream_t st = v->sh.st;
+    PcsrWorkspace& ws = v->ws;
+    int64_t* mm = ws.cs.ensure(CS_WORDS);
+    int64_t* hmm = ws.h_cs.ensure(CS_WORDS);
+    minmax_i64(d_keys, n, mm, st);
+    DSA_CUDA(cudaMemcpyAsync(hmm, mm, 16, cudaMemcpyDeviceToHost, st));
+    DSA_CUDA(cudaStreamSynchronize(st));
+    const int64_t kmin = hmm[0], kmax = hmm[1];
+    if (kmin == GAP_KEY) throw DsaError{DSA_ERR_ARGUMENT, "key typemin(Int64) is reserved"};
+    *maxkey = kmax;
+    const int nbits = std::max(1, bits_for((uint64_t)kmax - (uint64_t)kmin));
+    uint64_t* sk = ws.sk.ensure((size_t)n);
+    uint32_t* perm = ws.perm.ensure((size_t)n);
+    const unsigned gr = grid_for(n, 256);
+    DSA_LAUNCH("make_sortkeys_vec", k_make_sortkeys_vec, gr, 256, 0, st, d_keys, n, kmin, sk, perm);
+    radix_sort_pairs(ws.sort, sk, perm, n, nbits, st);
+    int32_t* flag = ws.flag32.ensure((size_t)n);
+    int32_t* uidx = ws.idx32.ensure((size_t)n);
+    int64_t* tot = ws.nuniq.ensure(4) + 2;
+    int64_t* uk = ws.u_key.ensure((size_t)n);
+    double* uv = ws.u_val.ensure((size_t)n);
+    if (build) {
+        DSA_LAUNCH("flag_run_first", k_flag_run_first, gr, 256, 0, st, sk, n, flag);
+        exclusive_scan_i32<int32_t>(ws.batch.scan, flag, uidx, n, tot, st);
+        DSA_LAUNCH("build_flatten", k_build_flatten, gr, 256, 0, st, sk, perm, flag, uidx, (const int32_t*)nullptr, (const int32_t*)nullptr, n,
+                   d_keys, (const int64_t*)nullptr, d_vals, combine, 0, uk, uv, (int64_t*)nullptr);
+    } else {
+        DSA_LAUNCH("flag_run_last", k_flag_run_last, gr, 256, 0, st, sk, n, flag);
+        exclusive_scan_i32<int32_t>(ws.batch.scan, flag, uidx, n, tot, st);
+        DSA_LAUNCH("gather_unique_ops", k_gather_unique_ops, gr, 256, 0, st, sk, perm, flag, uidx, n, n, 0, d_keys, d_vals, (int32_t*)nullptr, uk,
+                   uv);
+    }
+    *out_k = uk;
+    *out_v = uv;
+    *nuniq_dev = tot;
+    if (nuniq_host) {
+        DSA_CUDA(cudaMemcpyAsync(nuniq_host, tot, 8, cudaMemcpyDeviceToHost, st));
+        DSA_CUDA(cudaStreamSynchronize(st));
+    }
+    (void)maxkey_nz;
+}
+
+__global__ void __launch_bounds__(256) k_max_key_nonzero(const int64_t* __restrict__ keys, const double* __restrict__ vals, int64_t n,
+                                                          int64_t* __restrict__ out) {
+    int64_t hi = INT64_MIN;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (vals[i] != 0.0 && keys[i] > hi) hi = keys[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        int64_t h2 = __shfl_down_sync(0xffffffffu, hi, o);
+        hi = h2 > hi ? h2 : hi;
+    }
+    if ((threadIdx.x & 31) == 0 && hi != INT64_MIN) atomicMax((long long*)out, (long long)hi);
+}
+__global__ void __launch_bounds__(256) k_max_live_key(const int64_t* __restrict__ keys, int64_t n, int64_t* __restrict__ out) {
+    int64_t hi = INT64_MIN;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (keys[i] != GAP_KEY && keys[i] > hi) hi = keys[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        int64_t h2 = __shfl_down_sync(0xffffffffu, hi, o);
+        hi = h2 > hi ? h2 : hi;
+    }
+    if ((threadIdx.x & 31) == 0 && hi != INT64_MIN) atomicMax((long long*)out, (long long)hi);
+}
+__global__ void k_set_i64(int64_t* p, int64_t v) { *p = v; }
+
+static void vec_set_batch_dev(dsa_vec* v, const int64_t* d_keys, const double* d_vals, int64_t n) {
+    if (n <= 0) return;
+    cudaStream_t st = v->sh.st;
+    // n = max(n, key) for non-zero writes (vector.jl:77-79)
+    int64_t* mx = v->ws.cs.ensure(CS_WORDS) + 6;
+    DSA_LAUNCH("set_i64", k_set_i64, 1, 1, 0, st, mx, (int64_t)INT64_MIN);
+    DSA_LAUNCH("max_key_nonzero", k_max_key_nonzero, (unsigned)std::min<int64_t>((n + 255) / 256, 1184), 256, 0, st, d_keys, d_vals, n, mx);
+    int64_t h_mx = INT64_MIN;
+    DSA_CUDA(cudaMemcpyAsync(&h_mx, mx, 8, cudaMemcpyDeviceToHost, st));
+    int64_t *uk, *nu_dev, maxkey;
+    double* uv;
+    vec_sorted_unique(v, d_keys, d_vals, n, false, 0, &uk, &uv, nullptr, &nu_dev, nullptr, &maxkey);   // syncs (h_mx valid after)
+    v->pma.apply_sorted_ops(v->ws.batch, nullptr, uk, uv, n, nullptr, nullptr, st, false, nu_dev);
+    if (h_mx != INT64_MIN && h_mx > v->n) v->n = h_mx;
+}
+
+// ---- matrix helpers -----------------------------------------------------------------------------------------------
+static void matrix_set_batch_dev(dsa_matrix* A, const int64_t* d_rows, const int64_t* d_cols, const double* d_vals, int64_t n) {
+    if (n <= 0) return;
+    cudaStream_t st = A->sh.st;
+    // validate before mutate: both orientations need in-array keys >= 1 (rows for col-major, columns for row-major)
+    {
+        int64_t* mm = A->ws.cs.ensure(CS_WORDS);
+        int64_t* hmm = A->ws.h_cs.ensure(CS_WORDS);
+        minmax_i64(d_rows, n, mm, st);
+        minmax_i64(d_cols, n, mm + 2, st);
+        DSA_CUDA(cudaMemcpyAsync(hmm, mm, 32, cudaMemcpyDeviceToHost, st));
+        DSA_CUDA(cudaStreamSynchronize(st));
+        if (hmm[0] < 1 || hmm[2] < 1)
+            throw DsaError{DSA_ERR_ARGUMENT, "row and column keys must be >= 1 (each is an in-array key of one orientation; key 0 is the semaphore key, pcsr.jl:23)"};
+    }
+    int64_t maxcol_nz = INT64_MIN, maxrow_nz = INT64_MIN;
+    A->colmajor.set_batch_d(A->ws, d_rows, d_cols, d_vals, n, &maxcol_nz, &maxrow_nz, st);   // colmajor[row, col] = v  (matrix.jl:53-55)
+    A->rowmajor.set_batch_d(A->ws, d_cols, d_rows, d_vals, n, nullptr, nullptr, st);         // rowmajor[col, row] = v  (matrix.jl:57-59)
+    if (maxrow_nz != INT64_MIN && maxrow_nz > A->m) A->m = maxrow_nz;                        // matrix.jl:44-47
+    if (maxcol_nz != INT64_MIN && maxcol_nz > A->n) A->n = maxcol_nz;
+}
+
+static void matrix_delete(dsa_matrix* A, bool rows, const int64_t* ids, int64_t n) {
+    if (n <= 0) return;
+    cudaStream_t st = A->sh.st;
+    Pcsr& primary = rows ? A->rowmajor : A->colmajor;
+    Pcsr& twin = rows ? A->colmajor : A->rowmajor;
+    // validate before mutate (pcsr.jl:208)
+    std::vector<int32_t> slots;
+    {
+        std::unordered_set<int32_t> seen;
+        for (int64_t i = 0; i < n; ++i) {
+            int32_t s = primary.host_lookup(ids[i]);
+            if (s < 0) throw DsaError{DSA_ERR_ARGUMENT, (rows ? "row " : "column ") + std::to_string(ids[i]) + " does not exist."};
+            if (!seen.insert(s).second) throw DsaError{DSA_ERR_ARGUMENT, "column listed twice."};
+            slots.push_back(s);
+        }
+    }
+    int32_t* d_slots = A->d_slots.ensure((size_t)n);
+    int64_t* d_ids = A->d_ids.ensure((size_t)n);
+    DSA_CUDA(cudaMemcpyAsync(d_slots, slots.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    DSA_CUDA(cudaMemcpyAsync(d_ids, ids, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    // entries to delete from the twin: for (row, val) in view(matrix, :, col): rowmajor[col, row] = 0  (matrix.jl:97-99)
+    const int64_t tot = primary.gather_spans(A->ws, d_slots, n, d_ids, false, st);
+    if (tot > 0) {
+        // twin partition key = in-array key of the primary cell, twin in-array key = deleted id, value 0.0
+        // copy out of the shared workspace: the twin batch reuses it
+        DBuf<int64_t> pk, ik;
+        DBuf<double> zeros;
+        pk.ensure((size_t)tot);
+        ik.ensure((size_t)tot);
+        zeros.ensure((size_t)tot);
+        DSA_CUDA(cudaMemcpyAsync(pk.p, A->ws.tmp_k.p, (size_t)tot * 8, cudaMemcpyDeviceToDevice, st));
+        DSA_CUDA(cudaMemcpyAsync(ik.p, A->ws.tmp_owner.p, (size_t)tot * 8, cudaMemcpyDeviceToDevice, st));
+        DSA_CUDA(cudaMemsetAsync(zeros.p, 0, (size_t)tot * 8, st));
+        twin.set_batch_d(A->ws, ik.p, pk.p, zeros.p, tot, nullptr, nullptr, st);
+        DSA_CUDA(cudaStreamSynchronize(st));
+    }
+    primary.delete_slots(A->ws, slots, d_slots, st);   // deletecolumn!(colmajor, col)  (matrix.jl:100)
+}
+
+static void matrix_spmv_slots(dsa_matrix* A, int trans, const double* d_x, const uint8_t* d_mask, int64_t nx) {
+    // mat * x sums, per row, over ascending columns (operations.jl:97-103): that is a segmented reduction over the
+    // ROW-major twin; transpose(mat) * x is the same over the column-major structure.
+    Pcsr& P = trans ? A->colmajor : A->rowmajor;
+    P.spmv_slots(A->ws, d_x, d_mask, nx, A->sh.st);
+}
+
+extern "C" {
+
+int dsa_version(void) { return 100; }
+const char* dsa_last_error(void) { return g_last_error.c_str(); }
+int dsa_device_count(int* count_out) {
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        c = 0;
+    }
+    *count_out = c;
+    return DSA_OK;
+}
+int dsa_set_device(int device) {
+    DSA_TRY
+    DSA_CUDA(cudaSetDevice(device));
+    return DSA_OK;
+    DSA_CATCH
+}
+
+// ---- host logic ----------------------------------------------------------------------------------------------------
+int dsa_pma_geometry(int64_t nb_elements, int64_t* out4) {
+    Geometry g = geometry_for_build(nb_elements);
+    out4[0] = g.capacity; out4[1] = g.segment_capacity; out4[2] = g.nb_segments; out4[3] = g.height;
+    return DSA_OK;
+}
+int dsa_level_bounds(int64_t segment_capacity, int64_t height, int64_t* mn, int64_t* mx) {
+    if (height < 1 || height >= MAX_LEVELS) { g_last_error = "height out of range"; return DSA_ERR_ARGUMENT; }
+    level_bounds(segment_capacity, height, (T_H - T_0) / (double)height, (P_H - P_0) / (double)height, mn, mx);
+    return DSA_OK;
+}
+int64_t dsa_spread_dest(int64_t c, int64_t m, int64_t r) { return spread_dest(spread_make(c, m), r); }
+int64_t dsa_spread_rank(int64_t c, int64_t m, int64_t p) { return spread_rank_at(spread_make(c, m), p); }
+int64_t dsa_colmap_plan(const int64_t* slot_key, const uint8_t* slot_live, int64_t nslots, const int64_t* new_keys, int64_t nnew,
+                        int64_t* out_key, uint8_t* out_live, int64_t* out_old) {
+    std::vector<int64_t> k, o;
+    std::vector<uint8_t> l;
+    int64_t n = colmap_plan(slot_key, slot_live, nslots, new_keys, nnew, k, l, o);
+    for (int64_t i = 0; i < n; ++i) { out_key[i] = k[(size_t)i]; out_live[i] = l[(size_t)i]; out_old[i] = o[(size_t)i]; }
+    return n;
+}
+
+// ---- vector -----------------------------------------------------------------------------------------------------------
+int dsa_vec_create(int64_t expected_nb_elems, dsa_vec_t** out) {
+    DSA_TRY
+    require_device();
+    std::unique_ptr<dsa_vec> v(new dsa_vec());
+    v->sh.create();
+    v->pma.alloc(geometry_for_build(0, expected_nb_elems > 0 ? expected_nb_elems : 100));
+    v->pma.nnz = 0;
+    DSA_LAUNCH("layout_build", k_layout, grid_for(v->pma.g.capacity, 256), 256, 0, v->sh.st, v->pma.keys.p, v->pma.vals.p, v->pma.g.capacity,
+               (int64_t)0, (const int64_t*)v->pma.keys.p, (const double*)v->pma.vals.p, v->pma.leafcnt.p, (int64_t*)nullptr,
+               ilog2_i64(v->pma.g.segment_capacity));
+    DSA_CUDA(cudaStreamSynchronize(v->sh.st));
+    *out = v.release();
+    return DSA_OK;
+    DSA_CATCH
+}
+int dsa_vec_build(const int64_t* keys, const double* vals, int64_t n, int combine, int64_t len, int len_given, dsa_vec_t** out) {
+    DSA_TRY
+    require_device();
+    if (n < 0) throw DsaError{DSA_ERR_ARGUMENT, "negative length"};
+    std::unique_ptr<dsa_vec> v(new dsa_vec());
+    v->sh.create();
+    cudaStream_t st = v->sh.st;
+    if (n == 0) {
+        v->pma.build_from_sorted(nullptr, nullptr, 0, nullptr, st);
+        v->n = len_given ? len : 0;
+    } else {
+        int64_t* dk = h2d(v->stg.a, keys, n, st);
+        double* dv = h2d(v->stg.v, vals, n, st);
+        int64_t *uk, *nu_dev, nu = 0, maxkey = 0;
+        double* uv;
+        vec_sorted_unique(v.get(), dk, dv, n, true, combine, &uk, &uv, &nu, &nu_dev, nullptr, &maxkey);
+        v->pma.build_from_sorted(uk, uv, nu, nullptr, st);
+        v->n = len_given ? len : std::max<int64_t>(maxkey, 0);   // _guess_length (vector.jl:6) = maximum(keys; init = 0)
+    }
+    DSA_CUDA(cudaStreamSynchronize(st));
+    *out = v.release();
+    return DSA_OK;
+    DSA_CATCH
+}
+int dsa_vec_destroy(dsa_vec_t* v) {
+    delete v;
+    return DSA_OK;
+}
+int dsa_vec_clone(const dsa_vec_t* v, dsa_vec_t** out) {
+    DSA_TRY
+    std::unique_ptr<dsa_vec> c(new dsa_vec());
+    c->sh.create();
+    cudaStream_t st = c->sh.st;
+    DSA_CUDA(cudaStreamSynchronize(v->sh.st));
+    c->pma.alloc(v->pma.g);
+    c->pma.nnz = v->pma.nnz;
+    c->n = v->n;
+    DSA_CUDA(cudaMemcpyAsync(c->pma.keys.p, v->pma.keys.p, (size_t)v->pma.g.capacity * 8, cudaMemcpyDeviceToDevice, st));
+    DSA_CUDA(cudaMemcpyAsync(c->pma.vals.p, v->pma.vals.p, (size_t)v->pma.g.capacity * 8, cudaMemcpyDeviceToDevice, st));
+    DSA_CUDA(cudaMemcpyAsync(c->pma.leafcnt.p, v->pma.leafcnt.p, (size_t)v->pma.g.nb_segments * 4, cudaMemcpyDeviceToDevice, st));
+    DSA_CUDA(cudaStreamSynchronize(st));
+    *out = c.release();
+    return DSA_OK;
+    DSA_CATCH
+}
+int dsa_vec_set_stream(dsa_vec_t* v, void* cuda_stream) {
+    v->sh.set((cudaStream_t)cuda_stream);
+    return DSA_OK;
+}
+int dsa_vec_set_batch(dsa_vec_t* v, const int64_t* keys, const double* vals, int64_t n) {
+    DSA_TRY
+    if (n <= 0) return DSA_OK;
+    cudaStream_t st = v->sh.st;
+    int64_t* dk = h2d(v->stg.a, keys, n, st);
+    double* dv = h2d(v->stg.v, vals, n, st);
+    vec_set_batch_dev(v, dk, dv, n);
+    DSA_CUDA(cudaStreamSynchronize(st));
+    return DSA_OK;
+    DSA_CATCH
+}
+int dsa_vec_set_batch_d(dsa_vec_t* v, const int64_t* d_keys, const double* d_vals, int64_t n) {
+    DSA_TRY
+    vec_set_batch_dev(v, d_keys, d_vals, n);
+    return DSA_OK;
+    DSA_CATCH
+}
+int dsa_vec_get_batch(dsa_vec_t* v, const int64_t* keys, int64_t n, double* out) {
+    DSA_TRY
+    if (n <= 0) return DSA_OK;
+    cudaStream_t st = v->sh.st;
+    int64_t* dk = h2d(v->stg.a, keys, n, st);
+    double* dout = v->stg.out.ensure((size_t)n);
+    DSA_LAUNCH("get", k_get, grid_for(n, 256), 256, 0, st, v->pma.keys.p, v->pma.vals.p, v->pma.g.capacity, (const int32_t*)nullptr, dk, n,
+               (const int64_t*)nullptr, (const int64_t*)nullptr, dout);
+    DSA_CUDA(cudaMemcpyAsync(out, dout, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    DSA_CUDA(cudaStreamSynchronize(st));
+    return DSA_OK;
+    DSA_CATCH
+}
+int dsa_vec_info(const dsa_vec_t* v, int64_t* out6) {
+    out6[0] = v->pma.g.capacity; out6[1] = v->pma.g.segment_capacity; out6[2] = v->pma.g.nb_segments;
+    out6[3] = v->pma.nnz; out6[4] = v->pma.g.height; out6[5] = v->n;
+    return DSA_OK;
+}
+static int64_t compact_range(PcsrWorkspace& ws, const int64_t* d_keys, const double* d_vals, int64_t len, int skip_sem, int64_t* out_k,
+                             double* out_v, int64_t cap_out, cudaStream_t st) {
+    // returns the number of stored cells; fills the host outputs when they fit
+    if (len <= 0) return 0;
+    int32_t* flag = ws.flag32.ensure((size_t)len);
+    int32_t* idx = ws.idx32.ensure((size_t)len);
+    int64_t* tot = ws.nuniq.ensure(4);
+    const unsigned gr = grid_for(len, 256);
+    DSA_LAUNCH("flag_live", k_flag_live, gr, 256, 0, st, d_keys, len, flag, skip_sem);
+    exclusive_scan_i32<int32_t>(ws.batch.scan, flag, idx, len, tot, st);
+    int64_t h_tot = 0;
+    DSA_CUDA(cudaMemcpyAsync(&h_tot, tot, 8, cudaMemcpyDeviceToHost, st));
+    DSA_CUDA(cudaStreamSynchronize(st));
+    if (h_tot > 0 && out_k && h_tot <= cap_out) {
+        int64_t* ck = ws.tmp_k.ensure((size_t)h_tot);
+        double* cv = ws.tmp_v.ensure((size_t)h_tot);
+        DSA_LAUNCH("compact_cells", k_compact_cells, gr, 256, 0, st, d_keys, d_vals, len, idx, skip_sem, ck, cv);
+        DSA_CUDA(cudaMemcpyAsync(out_k, ck, (size_t)h_tot * 8, cudaMemcpyDeviceToHost, st));
+        DSA_CUDA(cudaMemcpyAsync(out_v, cv, (size_t)h_tot * 8, cudaMemcpyDeviceToHost, st));
+        DSA_CUDA(cudaStreamSynchronize(st));
+    }
+    return h_tot;
+}
+int dsa_vec_nonzeros(dsa_vec_t* v, int64_t* keys_out, double* vals_out, int64_t cap, int64_t* count_out) {
+    DSA_TRY
+    *count_out = compact_range(v->ws, v->pma.keys.p, v->pma.vals.p, v->pma.g.capacity, 0, keys_out, vals_out, cap, v->sh.st);
+    return DSA_OK;
+    DSA_CATCH
+}
+int dsa_vec_shrink_size(dsa_vec_t* v, int64_t* n_out) {
+    DSA_TRY
+    cudaStream_t st = v->sh.st;
+    int64_t* mx = v->ws.cs.ensure(CS_WORDS);
+    DSA_LAUNCH("set_i64", k_set_i64, 1, 1, 0, st, mx, (int64_t)INT64_MIN);
+    DSA_LAUNCH("max_live_key", k_max_live_key, (unsigned)std::min<int64_t>((v->pma.g.capacity + 255) / 256, 1184), 256, 0, st, v->pma.keys.p,
+               v->pma.g.capacity, mx);
+    int64_t h = 0;
+    DSA_CUDA(cudaMemcpyAsync(&h, mx, 8, cudaMemcpyDeviceToHost, st));
+    DSA_CUDA(cudaStreamSynchronize(st));
+    v->n = h == INT64_MIN ? 0 : std::max<int64_t>(h, 0);   // mapreduce(max; init = zero(K))  (vector.jl:7-8)
+    *n_out = v->n;
+    return DSA_OK;
+    DSA_CATCH
+}
+static void export_cells(PcsrWorkspace& ws, Staging& stg, const PmaCore& p, uint8_t* occ, int64_t* keys, double* vals, cudaStream_t st) {
+    const int64_t cap = p.g.capacity;
+    DBuf<uint8_t> d_occ;
+    d_occ.ensure((size_t)cap);
+    int64_t* dk = stg.a.ensure((size_t)cap);
+    double* dv = stg.v.ensure((size_t)cap);
+    DSA_LAUNCH("export_cells", k_export_cells, grid_for(cap, 256), 256, 0, st, p.keys.p, p.vals.p, cap, d_occ.p, dk, dv);
+    DSA_CUDA(cudaMemcpyAsync(occ, d_occ.p, (size_t)cap, cudaMemcpyDeviceToHost, st));
+    DSA_CUDA(cudaMemcpyAsync(keys, dk, (size_t)cap * 8, cudaMemcpyDeviceToHost, st));
+    DSA_CUDA(cudaMemcpyAsync(vals, dv, (size_t)cap * 8, cudaMemcpyDeviceToHost, st));
+    DSA_CUDA(cudaStreamSynchronize(st));
+    (void)ws;
+}
+int dsa_vec_export(dsa_vec_t* v, uint8_t* occupied, int64_t* keys, double* vals) {
+    DSA_TRY
+    export_cells(v->ws, v->stg, v->pma, occupied, keys, vals, v->sh.st);
+    return DSA_OK;
+    DSA_CATCH
+}
+
+// ---- matrix -----------------------------------------------------------------------------------------------------------
+int dsa_matrix_create(dsa_matrix_t** out) {
+    DSA_TRY
+    require_device();
+    std::unique_ptr<dsa_matrix> A(new dsa_matrix());
+    A->sh.create();
+    A->colmajor.init_empty(A->sh.st);
+    A->rowmajor.init_empty(A->sh.st);
+    DSA_CUDA(cudaStreamSynchronize(A->sh.st));
+    *out = A.release();
+    return DSA_OK;
+    DSA_CATCH
+}
+int dsa_matrix_build_coo(const int64_t* rows, const int64_t* cols, const double* vals, int64_t n, int64_t m, int64_t ncols, int dims_given,
+                         int combine, dsa_matrix_t** out) {
+    DSA_TRY
+    require_device();
+    if (n < 0) throw DsaError{DSA_ERR_ARGUMENT, "negative length"};
+    std::unique_ptr<dsa_matrix> A(new dsa_matrix());
+    A->sh.create();
+    cudaStream_t st = A->sh.st;
+    int64_t* dr = h2d(A->stg.a, rows, n, st);
+    int64_t* dc = h2d(A->stg.b, cols, n, st);
+    double* dv = h2d(A->stg.v, vals, n, st);
+    if (n > 0) {
+        int64_t* mm = A->ws.cs.ensure(CS_WORDS);
+        int64_t* hmm = A->ws.h_cs.ensure(CS_WORDS);
+        minmax_i64(dr, n, mm, st);
+        minmax_i64(dc, n, mm + 2, st);
+        DSA_CUDA(cudaMemcpyAsync(hmm, mm, 32, cudaMemcpyDeviceToHost, st));
+        DSA_CUDA(cudaStreamSynchronize(st));
+        if (hmm[0] < 1 || hmm[2] < 1)
+            throw DsaError{DSA_ERR_ARGUMENT, "row and column keys must be >= 1 (each is an in-array key of one orientation; key 0 is the semaphore key, pcsr.jl:23)"};
+        A->m = dims_given ? m : hmm[1];        // _guess_length (vector.jl:6)
+        A->n = dims_given ? ncols : hmm[3];
+    } else {
+        A->m = dims_given ? m : 0;
+        A->n = dims_given ? ncols : 0;
+    }
+    A->colmajor.build_coo_d(A->ws, dr, dc, dv, n, combine, st);   // dynamicsparsecolmajor(I, J, V)  (matrix.jl:17)
+    A->rowmajor.build_coo_d(A->ws, dc, dr, dv, n, combine, st);   // dynamicsparsecolmajor(J, I, V)
+    DSA_CUDA(cudaStreamSynchronize(st));
+    *out = A.release();
+    return DSA_OK;
+    DSA_CATCH
+}
+int dsa_matrix_destroy(dsa_matrix_t* A) {
+    delete A;
+    return DSA_OK;
+}
+int dsa_matrix_clone(const dsa_matrix_t* A, dsa_matrix_t** out) {
+    DSA_TRY
+    std::unique_ptr<dsa_matrix> C(new dsa_matrix());
+    C->sh.create();
+    DSA_CUDA(cudaStreamSynchronize(A->sh.st));
+    C->colmajor.clone_from(A->colmajor, C->sh.st);
+    C->rowmajor.clone_from(A->rowmajor, C->sh.st);
+    C->m = A->m;
+    C->n = A->n;
+    DSA_CUDA(cudaStreamSynchronize(C->sh.st));
+    *out = C.release();
+    return DSA_OK;
+    DSA_CATCH
+}
+int dsa_matrix_set_stream(dsa_matrix_t* A, void* cuda_stream) {
+    A->sh.set((cudaStream_t)cuda_stream);
+    return DSA_OK;
+}
+int dsa_matrix_set_batch(dsa_matrix_t* A, const int64_t* rows, const int64_t* cols, const double* vals, int64_t n) {
+    DSA_TRY
+    if (n <= 0) return DSA_OK;
+    cudaStream_t st = A->sh.st;
+    int64_t* dr = h2d(A->stg.a, rows, n, st);
+    int64_t* dc = h2d(A->stg.b, cols, n, st);
+    double* dv = h2d(A->stg.v, vals, n, st);
+    matrix_set_batch_dev(A, dr, dc, dv, n);
+    DSA_CUDA(cudaStreamSynchronize(st));
+    return DSA_OK;
+    DSA_CATCH
+}
+int dsa_matrix_set_batch_d(dsa_matrix_t* A, const int64_t* d_rows, const int64_t* d_cols, const double* d_vals, int64_t n, int64_t, int64_t) {
+    DSA_TRY
+    matrix_set_batch_dev(A, d_rows, d_cols, d_vals, n);
+    return DSA_OK;
+    DSA_CATCH
+}
+int dsa_matrix_get_batch(dsa_matrix_t* A, int which, const int64_t* rows, const int64_t* cols, int64_t n, double* out) {
+    DSA_TRY
+    if (n <= 0) return DSA_OK;
+    cudaStream_t st = A->sh.st;
+    int64_t* dr = h2d(A->stg.a, rows, n, st);
+    int64_t* dc = h2d(A->stg.b, cols, n, st);
+    double* dout = A->stg.out.ensure((size_t)n);
+    if (which == DSA_COLMAJOR) A->colmajor.get_batch_d(A->ws, dr, dc, n, dout, st);
+    else A->rowmajor.get_batch_d(A->ws, dc, dr, n, dout, st);
+    DSA_CUDA(cudaMemcpyAsync(out, dout, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    DSA_CUDA(cudaStreamSynchronize(st));
+    return DSA_OK;
+    DSA_CATCH
+}
+int dsa_matrix_delete_columns(dsa_matrix_t* A, const int64_t* cols, int64_t n) {
+    DSA_TRY
+    matrix_delete(A, false, cols, n);
+    DSA_CUDA(cudaStreamSynchronize(A->sh.st));
+    return DSA_OK;
+    DSA_CATCH
+}
+int dsa_matrix_delete_rows(dsa_matrix_t* A, const int64_t* rows, int64_t n) {
+    DSA_TRY
+    matrix_delete(A, true, rows, n);
+    DSA_CUDA(cudaStreamSynchronize(A->sh.st));
+    return DSA_OK;
+    DSA_CATCH
+}
+static int matrix_span(dsa_matrix_t* A, Pcsr& P, int64_t id, int64_t* keys_out, double* vals_out, int64_t cap, int64_t* count_out) {
+    DSA_TRY
+    cudaStream_t st = A->sh.st;
+    *count_out = 0;
+    const int32_t s = P.host_lookup(id);
+    if (s < 0) return DSA_OK;   // empty view (views.jl:11-12)
+    int32_t* d_s = A->d_slots.ensure(1);
+    DSA_CUDA(cudaMemcpyAsync(d_s, &s, 4, cudaMemcpyHostToDevice, st));
+    const int64_t tot = P.gather_spans(A->ws, d_s, 1, nullptr, true, st);
+    *count_out = tot;
+    if (tot > 0 && keys_out && tot <= cap) {
+        DSA_CUDA(cudaMemcpyAsync(keys_out, A->ws.tmp_k.p, (size_t)tot * 8, cudaMemcpyDeviceToHost, st));
+        DSA_CUDA(cudaMemcpyAsync(vals_out, A->ws.tmp_v.p, (size_t)tot * 8, cudaMemcpyDeviceToHost, st));
+        DSA_CUDA(cudaStreamSynchronize(st));
+    }
+    return DSA_OK;
+    DSA_CATCH
+}
+int dsa_matrix_column(dsa_matrix_t* A, int64_t col, int64_t* keys_out, double* vals_out, int64_t cap, int64_t* count_out) {
+    return matrix_span(A, A->colmajor, col, keys_out, vals_out, cap, count_out);
+}
+int dsa_matrix_row(dsa_matrix_t* A, int64_t row, int64_t* keys_out, double* vals_out, int64_t cap, int64_t* count_out) {
+    return matrix_span(A, A->rowmajor, row, keys_out, vals_out, cap, count_out);
+}
+int dsa_matrix_spmv(dsa_matrix_t* A, int trans, const int64_t* x_keys, const double* x_vals, int64_t nx, int64_t* y_keys, double* y_vals,
+                    int64_t cap, int64_t* count_out) {
+    DSA_TRY
+    cudaStream_t st = A->sh.st;
+    Pcsr& P = trans ? A->colmajor : A->rowmajor;
+    *count_out = 0;
+    const int64_t dim = std::max<int64_t>(P.max_inkey, 1);
+    double* xd = A->ws.xdense.ensure((size_t)dim);
+    uint8_t* xm = A->ws.xmask.ensure((size_t)dim);
+    DSA_CUDA(cudaMemsetAsync(xd, 0, (size_t)dim * 8, st));
+    DSA_CUDA(cudaMemsetAsync(xm, 0, (size_t)dim, st));
+    if (nx > 0) {
+        int64_t* dk = h2d(A->stg.a, x_keys, nx, st);
+        double* dv = h2d(A->stg.v, x_vals, nx, st);
+        DSA_LAUNCH("scatter_x", k_scatter_x, grid_for(nx, 256), 256, 0, st, dk, dv, nx, xd, xm, dim);
+    }
+    matrix_spmv_slots(A, trans, xd, xm, dim);
+    const int64_t ns = P.nslots();
+    if (ns == 0) return DSA_OK;
+    int32_t* flag = A->ws.flag32.ensure((size_t)ns);
+    int32_t* idx = A->ws.idx32.ensure((size_t)ns);
+    int64_t* tot = A->ws.nuniq.ensure(4);
+    DSA_LAUNCH("flag_touched", k_flag_touched, grid_for(ns, 256), 256, 0, st, A->ws.ycnt.p, P.d_sem.p, ns, flag);
+    exclusive_scan_i32<int32_t>(A->ws.batch.scan, flag, idx, ns, tot, st);
+    int64_t h_tot = 0;
+    DSA_CUDA(cudaMemcpyAsync(&h_tot, tot, 8, cudaMemcpyDeviceToHost, st));
+    DSA_CUDA(cudaStreamSynchronize(st));
+    *count_out = h_tot;
+    if (h_tot > 0 && y_keys && h_tot <= cap) {
+        int64_t* yk = A->ws.tmp_k.ensure((size_t)h_tot);
+        double* yv = A->ws.tmp_v.ensure((size_t)h_tot);
+        DSA_LAUNCH("compact_y", k_compact_y, grid_for(ns, 256), 256, 0, st, A->ws.yslot.p, P.d_slot_key.p, flag, idx, ns, yk, yv);
+        DSA_CUDA(cudaMemcpyAsync(y_keys, yk, (size_t)h_tot * 8, cudaMemcpyDeviceToHost, st));
+        DSA_CUDA(cudaMemcpyAsync(y_vals, yv, (size_t)h_tot * 8, cudaMemcpyDeviceToHost, st));
+        DSA_CUDA(cudaStreamSynchronize(st));
+    }
+    return DSA_OK;
+    DSA_CATCH
+}
+static void spmv_dense_dev(dsa_matrix_t* A, int trans, const double* d_x, int64_t nx, double* d_y, int64_t ny) {
+    cudaStream_t st = A->sh.st;
+    Pcsr& P = trans ? A->colmajor : A->rowmajor;
+    DSA_CUDA(cudaMemsetAsync(d_y, 0, (size_t)ny * 8, st));
+    matrix_spmv_slots(A, trans, d_x, nullptr, nx);
+    const int64_t ns = P.nslots();
+    if (ns > 0)
+        DSA_LAUNCH("spmv_to_dense", k_spmv_to_dense, grid_for(ns, 256), 256, 0, st, A->ws.yslot.p, P.d_sem.p, P.d_slot_key.p, ns, d_y, ny);
+}
+int dsa_matrix_spmv_dense(dsa_matrix_t* A, int trans, const double* x, int64_t nx, double* y, int64_t ny) {
+    DSA_TRY
+    cudaStream_t st = A->sh.st;
+    double* dx = h2d(A->stg.v, x, nx, st);
+    double* dy = A->stg.out.ensure((size_t)std::max<int64_t>(ny, 1));
+    spmv_dense_dev(A, trans, dx, nx, dy, ny);
+    if (ny > 0) DSA_CUDA(cudaMemcpyAsync(y, dy, (size_t)ny * 8, cudaMemcpyDeviceToHost, st));
+    DSA_CUDA(cudaStreamSynchronize(st));
+    return DSA_OK;
+    DSA_CATCH
+}
+int dsa_matrix_spmv_dense_d(dsa_matrix_t* A, int trans, const double* d_x, int64_t nx, double* d_y, int64_t ny) {
+    DSA_TRY
+    spmv_dense_dev(A, trans, d_x, nx, d_y, ny);
+    return DSA_OK;
+    DSA_CATCH
+}
+int dsa_matrix_info(const dsa_matrix_t* A, int which, int64_t* out10) {
+    const Pcsr& P = which == DSA_COLMAJOR ? A->colmajor : A->rowmajor;
+    out10[0] = P.pma.g.capacity; out10[1] = P.pma.g.segment_capacity; out10[2] = P.pma.g.nb_segments; out10[3] = P.pma.nnz;
+    out10[4] = P.pma.g.height; out10[5] = P.nb_partitions; out10[6] = P.nslots(); out10[7] = A->m; out10[8] = A->n; out10[9] = P.nnz();
+    return DSA_OK;
+}
+int dsa_matrix_export(dsa_matrix_t* A, int which, uint8_t* occupied, int64_t* keys, double* vals, int64_t* semaphores, int64_t* col_keys,
+                      uint8_t* col_live) {
+    DSA_TRY
+    Pcsr& P = which == DSA_COLMAJOR ? A->colmajor : A->rowmajor;
+    cudaStream_t st = A->sh.st;
+    export_cells(A->ws, A->stg, P.pma, occupied, keys, vals, st);
+    const int64_t ns = P.nslots();
+    if (ns > 0) {
+        DSA_CUDA(cudaMemcpyAsync(semaphores, P.d_sem.p, (size_t)ns * 8, cudaMemcpyDeviceToHost, st));
+        DSA_CUDA(cudaStreamSynchronize(st));
+        for (int64_t s = 0; s < ns; ++s) {
+            semaphores[s] = (P.slot_live[(size_t)s] && semaphores[s] >= 0) ? semaphores[s] + 1 : 0;   // 1-based, 0 = nothing
+            col_keys[s] = P.slot_live[(size_t)s] ? P.slot_key[(size_t)s] : 0;
+            col_live[s] = P.slot_live[(size_t)s];
+        }
+    }
+    return DSA_OK;
+    DSA_CATCH
+}
+
+// ---- multi-GPU routing ------------------------------------------------------------------------------------------------
+}  // extern "C"
+
+namespace dsa {
+__global__ void __launch_bounds__(256) k_route_owner(const int64_t* __restrict__ route_keys, int64_t n, const int64_t* __restrict__ splitters,
+                                                      int nranks, uint64_t* __restrict__ sk, uint32_t* __restrict__ idx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t k = route_keys[i];
+    int lo = 0, hi = nranks - 1;   // owner = number of splitters <= k
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (splitters[mid] <= k) lo = mid + 1;
+        else hi = mid;
+    }
+    sk[i] = (uint64_t)lo;
+    idx[i] = (uint32_t)i;
+}
+__global__ void __launch_bounds__(256) k_route_gather(const uint64_t* __restrict__ sk, const uint32_t* __restrict__ perm, int64_t n,
+                                                       const int64_t* __restrict__ rows, const int64_t* __restrict__ cols,
+                                                       const double* __restrict__ vals, int64_t* __restrict__ orows, int64_t* __restrict__ ocols,
+                                                       double* __restrict__ ovals, int64_t* __restrict__ counts) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t s = perm[i];
+    orows[i] = rows[s];
+    ocols[i] = cols[s];
+    ovals[i] = vals[s];
+    if (i == n - 1 || sk[i] != sk[i + 1]) counts[(int)sk[i] + 1] = i + 1;   // end offset of this owner's run
+}
+}  // namespace dsa
+
+extern "C" {
+
+int dsa_route_batch_d(const int64_t* d_route_keys, const int64_t* d_rows, const int64_t* d_cols, const double* d_vals, int64_t n,
+                      const int64_t* splitters, int nranks, int64_t* d_rows_out, int64_t* d_cols_out, double* d_vals_out,
+                      int64_t* counts_out, void* cuda_stream) {
+    DSA_TRY
+    static SortWorkspace sws;
+    static DBuf<uint64_t> sk;
+    static DBuf<uint32_t> perm;
+    static DBuf<int64_t> d_split, d_ends;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    for (int r = 0; r < nranks; ++r) counts_out[r] = 0;
+    if (n <= 0) return DSA_OK;
+    const int ns = std::max(nranks - 1, 0);
+    d_split.ensure((size_t)ns + 1);
+    d_ends.ensure((size_t)nranks + 1);
+    if (ns) DSA_CUDA(cudaMemcpyAsync(d_split.p, splitters, (size_t)ns * 8, cudaMemcpyHostToDevice, st));
+    DSA_CUDA(cudaMemsetAsync(d_ends.p, 0xff, (size_t)(nranks + 1) * 8, st));   // -1 = owner absent
+    sk.ensure((size_t)n);
+    perm.ensure((size_t)n);
+    const unsigned gr = grid_for(n, 256);
+    DSA_LAUNCH("route_owner", k_route_owner, gr, 256, 0, st, d_route_keys, n, d_split.p, nranks, sk.p, perm.p);
+    radix_sort_pairs(sws, sk.p, perm.p, n, std::max(1, bits_for((uint64_t)std::max(nranks - 1, 1))), st);
+    DSA_LAUNCH("route_gather", k_route_gather, gr, 256, 0, st, sk.p, perm.p, n, d_rows, d_cols, d_vals, d_rows_out, d_cols_out, d_vals_out,
+               d_ends.p);
+    std::vector<int64_t> ends((size_t)nranks + 1);
+    DSA_CUDA(cudaMemcpyAsync(ends.data(), d_ends.p, (size_t)(nranks + 1) * 8, cudaMemcpyDeviceToHost, st));
+    DSA_CUDA(cudaStreamSynchronize(st));
+    int64_t prev = 0;
+    for (int r = 0; r < nranks; ++r) {
+        int64_t e = ends[(size_t)r + 1];
+        if (e < 0) e = prev;
+        counts_out[r] = e - prev;
+        prev = e;
+    }
+    return DSA_OK;
+    DSA_CATCH
+}
+
+// ---- measurement ------------------------------------------------------------------------------------------------------
+int64_t dsa_launch_count(void) { return prof().launches; }
+int dsa_prof_enable(int on) {
+    prof().enabled = on != 0;
+    return DSA_OK;
+}
+int dsa_prof_reset(void) {
+    prof().entries.clear();
+    return DSA_OK;
+}
+int64_t dsa_prof_dump(char* buf, int64_t cap) {
+    std::string s;
+    for (auto& kv : prof().entries) {
+        char line[256];
+        snprintf(line, sizeof(line), "%s,%lld,%.6f\n", kv.first.c_str(), (long long)kv.second.count, kv.second.ms);
+        s += line;
+    }
+    if (buf && cap > 0) {
+        size_t n = std::min<size_t>(s.size(), (size_t)cap - 1);
+        memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return (int64_t)s.size() + 1;
+}
+
+}  // extern "C"

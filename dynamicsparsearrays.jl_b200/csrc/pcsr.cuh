@@ -1,0 +1,723 @@
+// libdsa — partitioned PMA (PackedCSC + MappedPackedCSC, pcsr.jl) on the device: column map, batched set (K1..K5),
+// bulk deletecolumn! (K5), column gather and the flat SpMV (K7).
+#pragma once
+#include <algorithm>
+#include <unordered_set>
+#include "pma.cuh"
+#include "sort.cuh"
+
+namespace dsa {
+
+// ---------------------------------------------------------------------------------------------
+// column lookup: partition key -> slot (= partition id - 1) by binary search over the sorted live keys
+// (find(mpcsc.col_keys, col), pcsr.jl:342 — tombstones are kept out of the searched list instead of being skipped)
+// also reduces: #ops whose column is absent, min/max in-array key, max partition key / in-array key of non-zero writes
+// ---------------------------------------------------------------------------------------------
+enum { CS_MISSING = 0, CS_MINKEY = 1, CS_MAXKEY = 2, CS_MAXPART_NZ = 3, CS_MAXKEY_NZ = 4, CS_MINPART = 5, CS_WORDS = 8 };
+
+__global__ void k_colstat_init(int64_t* cs) {
+    cs[CS_MISSING] = 0;
+    cs[CS_MINKEY] = INT64_MAX;
+    cs[CS_MAXKEY] = INT64_MIN;
+    cs[CS_MAXPART_NZ] = INT64_MIN;
+    cs[CS_MAXKEY_NZ] = INT64_MIN;
+    cs[CS_MINPART] = INT64_MAX;
+}
+
+__device__ __forceinline__ int32_t live_lookup(const int64_t* __restrict__ live_keys, const int32_t* __restrict__ live_slot,
+                                               int64_t nlive, int64_t key) {
+    int64_t lo = 0, hi = nlive;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (live_keys[mid] < key) lo = mid + 1;
+        else hi = mid;
+    }
+    return (lo < nlive && live_keys[lo] == key) ? live_slot[lo] : -1;
+}
+
+__global__ void __launch_bounds__(256) k_col_lookup(const int64_t* __restrict__ partkeys, const int64_t* __restrict__ inkeys,
+                                                     const double* __restrict__ vals, int64_t n,
+                                                     const int64_t* __restrict__ live_keys, const int32_t* __restrict__ live_slot,
+                                                     int64_t nlive, int32_t* __restrict__ op_slot, int64_t* __restrict__ cs) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t mink = INT64_MAX, maxk = INT64_MIN, maxp = INT64_MIN, maxknz = INT64_MIN, minp = INT64_MAX;
+    int miss = 0;
+    if (i < n) {
+        const int64_t pk = partkeys[i];
+        minp = pk;
+        const int32_t s = live_lookup(live_keys, live_slot, nlive, pk);
+        op_slot[i] = s;
+        miss = s < 0;
+        if (inkeys) {
+            const int64_t k = inkeys[i];
+            mink = maxk = k;
+            if (vals && vals[i] != 0.0) { maxp = pk; maxknz = k; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        int64_t a = __shfl_xor_sync(0xffffffffu, mink, o); mink = a < mink ? a : mink;
+        a = __shfl_xor_sync(0xffffffffu, maxk, o); maxk = a > maxk ? a : maxk;
+        a = __shfl_xor_sync(0xffffffffu, maxp, o); maxp = a > maxp ? a : maxp;
+        a = __shfl_xor_sync(0xffffffffu, maxknz, o); maxknz = a > maxknz ? a : maxknz;
+        a = __shfl_xor_sync(0xffffffffu, minp, o); minp = a < minp ? a : minp;
+        miss += __shfl_xor_sync(0xffffffffu, miss, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (miss) atomicAdd((unsigned long long*)&cs[CS_MISSING], (unsigned long long)miss);
+        if (mink != INT64_MAX) atomicMin((long long*)&cs[CS_MINKEY], (long long)mink);
+        if (maxk != INT64_MIN) atomicMax((long long*)&cs[CS_MAXKEY], (long long)maxk);
+        if (maxp != INT64_MIN) atomicMax((long long*)&cs[CS_MAXPART_NZ], (long long)maxp);
+        if (maxknz != INT64_MIN) atomicMax((long long*)&cs[CS_MAXKEY_NZ], (long long)maxknz);
+        if (minp != INT64_MAX) atomicMin((long long*)&cs[CS_MINPART], (long long)minp);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_flag_missing(const int32_t* __restrict__ op_slot, int64_t n, int32_t* __restrict__ flag) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = op_slot[i] < 0 ? 1 : 0;
+}
+__global__ void __launch_bounds__(256) k_compact_missing(const int32_t* __restrict__ op_slot, const int64_t* __restrict__ partkeys,
+                                                          const int32_t* __restrict__ idx, int64_t n, int64_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && op_slot[i] < 0) out[idx[i]] = partkeys[i];
+}
+
+// renumbering after new columns: partition ids are slot indices; moved semaphore cells get their new id (pcsr.jl:128-134)
+__global__ void __launch_bounds__(256) k_renumber(const int64_t* __restrict__ old_sem, const int32_t* __restrict__ old2new, int64_t nold,
+                                                   int64_t* __restrict__ new_sem, double* __restrict__ vals) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nold) return;
+    const int64_t pos = old_sem[s];
+    const int32_t t = old2new[s];
+    if (pos < 0 || t < 0) return;
+    new_sem[t] = pos;
+    if (t != s) vals[pos] = (double)(t + 1);
+}
+__global__ void __launch_bounds__(256) k_fill_i64(int64_t* a, int64_t n, int64_t v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = v;
+}
+
+// next_sem[s] = position of the first placed semaphore with slot > s, or capacity (pcsr.jl:177-186 _pos_of_partition_end + 1)
+__global__ void __launch_bounds__(256) k_flag_placed(const int64_t* __restrict__ sem, int64_t n, int32_t* __restrict__ flag) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = sem[i] >= 0 ? 1 : 0;
+}
+__global__ void __launch_bounds__(256) k_live_positions(const int64_t* __restrict__ sem, const int32_t* __restrict__ rank, int64_t n,
+                                                         int64_t* __restrict__ live_pos) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && sem[i] >= 0) live_pos[rank[i]] = sem[i];
+}
+__global__ void __launch_bounds__(256) k_next_sem(const int64_t* __restrict__ sem, const int32_t* __restrict__ rank, int64_t n,
+                                                   const int64_t* __restrict__ live_pos, const int64_t* __restrict__ nplaced_dev,
+                                                   int64_t cap, int64_t* __restrict__ next_sem) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t idx = (int64_t)rank[i] + (sem[i] >= 0 ? 1 : 0);
+    next_sem[i] = idx < *nplaced_dev ? live_pos[idx] : cap;
+}
+
+// ---------------------------------------------------------------------------------------------
+// batch assembly: ops + one semaphore insert per new partition; 64-bit sort key = (slot << kb) | in-array key
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_make_sortkeys(const int32_t* __restrict__ op_slot, const int64_t* __restrict__ inkeys, int64_t n,
+                                                        const int32_t* __restrict__ new_slots, int64_t nnew, int kb,
+                                                        uint64_t* __restrict__ sk, uint32_t* __restrict__ idx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        sk[i] = ((uint64_t)(uint32_t)op_slot[i] << kb) | (uint64_t)inkeys[i];
+        idx[i] = (uint32_t)i;
+    } else if (i < n + nnew) {
+        sk[i] = ((uint64_t)(uint32_t)new_slots[i - n] << kb);   // key 0 = semaphore key: sorts first in its partition
+        idx[i] = (uint32_t)i;
+    }
+}
+// plain PMA: sort key = key - min
+__global__ void __launch_bounds__(256) k_make_sortkeys_vec(const int64_t* __restrict__ keys, int64_t n, int64_t mink,
+                                                            uint64_t* __restrict__ sk, uint32_t* __restrict__ idx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        sk[i] = (uint64_t)(keys[i] - mink);
+        idx[i] = (uint32_t)i;
+    }
+}
+// last writer wins: keep the last element of every run of equal sort keys (stable sort => last in arrival order)
+__global__ void __launch_bounds__(256) k_flag_run_last(const uint64_t* __restrict__ sk, int64_t n, int32_t* __restrict__ flag) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = (i == n - 1 || sk[i] != sk[i + 1]) ? 1 : 0;
+}
+__global__ void __launch_bounds__(256) k_gather_unique_ops(const uint64_t* __restrict__ sk, const uint32_t* __restrict__ perm,
+                                                            const int32_t* __restrict__ flag, const int32_t* __restrict__ uidx, int64_t ntot,
+                                                            int64_t n, int kb, const int64_t* __restrict__ inkeys,
+                                                            const double* __restrict__ vals, int32_t* __restrict__ u_pid,
+                                                            int64_t* __restrict__ u_key, double* __restrict__ u_val) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ntot || !flag[i]) return;
+    const int32_t j = uidx[i];
+    const uint32_t src = perm[i];
+    const int32_t slot = (int32_t)(sk[i] >> kb);
+    if (u_pid) u_pid[j] = slot;
+    if ((int64_t)src < n) {
+        u_key[j] = inkeys[src];
+        u_val[j] = vals[src];
+    } else {   // semaphore of a new partition: (key 0, T(partition id))   pcsr.jl:39-40
+        u_key[j] = 0;
+        u_val[j] = (double)(slot + 1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// builders: duplicate-combine as a left fold in input order (vector.jl:21-31, pcsr.jl:373-398): the head of every run of
+// equal sort keys folds its run sequentially (stable sort => input order)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double combine_apply(int c, double a, double b) {
+    switch (c) {
+        case DSA_COMBINE_ADD: return __dadd_rn(a, b);
+        case DSA_COMBINE_MUL: return __dmul_rn(a, b);
+        case DSA_COMBINE_LAST: return b;
+        case DSA_COMBINE_FIRST: return a;
+        case DSA_COMBINE_MIN: return b < a ? b : a;
+        case DSA_COMBINE_MAX: return b > a ? b : a;
+    }
+    return __dadd_rn(a, b);
+}
+__global__ void __launch_bounds__(256) k_flag_run_first(const uint64_t* __restrict__ sk, int64_t n, int32_t* __restrict__ flag) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = (i == 0 || sk[i] != sk[i - 1]) ? 1 : 0;
+}
+// second-level run heads for the matrix builder: first element of every partition (column) in the sorted unique stream
+__global__ void __launch_bounds__(256) k_flag_part_first(const uint64_t* __restrict__ sk_hi, int64_t n, const int32_t* __restrict__ runflag,
+                                                          int32_t* __restrict__ flag) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = (runflag[i] && (i == 0 || sk_hi[i] != sk_hi[i - 1])) ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5 bulk deletecolumn!: spans of the deleted partitions
+// ---------------------------------------------------------------------------------------------
+// count the stored cells of (sem, next_sem) per listed slot — one warp per slot
+__global__ void __launch_bounds__(256) k_span_count(const int64_t* __restrict__ keys, const int32_t* __restrict__ slots, int64_t nslots,
+                                                     const int64_t* __restrict__ sem, const int64_t* __restrict__ next_sem,
+                                                     int32_t* __restrict__ counts) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= nslots) return;
+    const int32_t s = slots[w];
+    const int64_t from = sem[s] + 1, to = next_sem[s];
+    int c = 0;
+    for (int64_t p = from + lane; p < to; p += 32) c += keys[p] != GAP_KEY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) counts[w] = c;
+}
+// emit the stored cells of the span in order (views.jl:15-35 / pcsr.jl:248-258): (key, val) and the owning list index
+__global__ void __launch_bounds__(256) k_span_emit(const int64_t* __restrict__ keys, const double* __restrict__ vals,
+                                                    const int32_t* __restrict__ slots, int64_t nslots, const int64_t* __restrict__ sem,
+                                                    const int64_t* __restrict__ next_sem, const int32_t* __restrict__ offsets,
+                                                    int64_t* __restrict__ out_key, double* __restrict__ out_val,
+                                                    int64_t* __restrict__ out_owner, const int64_t* __restrict__ owner_keys) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= nslots) return;
+    const int32_t s = slots[w];
+    const int64_t from = sem[s] + 1, to = next_sem[s];
+    int64_t o = offsets[w];
+    for (int64_t base = from; base < to; base += 32) {
+        const int64_t p = base + lane;
+        const bool live = p < to && keys[p] != GAP_KEY;
+        const unsigned b = __ballot_sync(0xffffffffu, live);
+        if (live) {
+            const int64_t d = o + __popc(b & lanemask_lt());
+            out_key[d] = keys[p];
+            if (out_val) out_val[d] = vals[p];
+            if (out_owner) out_owner[d] = owner_keys[w];
+        }
+        o += __popc(b);
+    }
+}
+// purge! (writes.jl:80-92) of [sem, next_sem) for every listed slot + leaf bookkeeping
+__global__ void __launch_bounds__(256) k_span_purge(int64_t* __restrict__ keys, double* __restrict__ vals, const int32_t* __restrict__ slots,
+                                                     int64_t nslots, const int64_t* __restrict__ sem, const int64_t* __restrict__ next_sem,
+                                                     int32_t* __restrict__ leafcnt, uint8_t* __restrict__ touched, int lgS) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= nslots) return;
+    const int32_t s = slots[w];
+    const int64_t from = sem[s], to = next_sem[s];
+    for (int64_t p = from + lane; p < to; p += 32) {
+        if (keys[p] != GAP_KEY) {
+            keys[p] = GAP_KEY;
+            vals[p] = 0.0;
+            atomicSub(&leafcnt[p >> lgS], 1);
+            touched[p >> lgS] = 1;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_clear_sems(int64_t* __restrict__ sem, const int32_t* __restrict__ slots, int64_t nslots) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nslots) sem[slots[i]] = -1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7 SpMV over the gapped array — flat, cell-parallel, deterministic.
+// y[key(partition)] = sum over the partition's cells of x[cell key] * cell value, cells in ascending key order, i.e. the
+// per-output summation order of _mul_dyn_mat_col_loop! (operations.jl:97-103) when the twin orientation is scanned.
+// A warp streams a chunk of SPMV_CHUNK consecutive cells (coalesced 8 B lanes for keys and values), does a segmented
+// scan with the semaphore cells as in-band segment heads, writes every partition that ends inside the chunk, and leaves
+// (a) the partial of the cells before its first head in carry[chunk] and (b) the open partial of its last partition in y.
+// k_spmv_fixup then adds, per chunk with a head, the carries of the following head-less chunks in chunk order.
+// No atomics: the result is bit-reproducible.  mul and add are separate roundings (no FMA), as in the reference.
+// ---------------------------------------------------------------------------------------------
+constexpr int SPMV_STEPS = 8;
+constexpr int SPMV_CHUNK = 32 * SPMV_STEPS;
+
+template <bool SPARSE_X>
+__global__ void __launch_bounds__(256) k_spmv_flat(const int64_t* __restrict__ keys, const double* __restrict__ vals, int64_t cap,
+                                                    const double* __restrict__ x, const uint8_t* __restrict__ xmask, int64_t nx,
+                                                    double* __restrict__ yslot, int32_t* __restrict__ ycnt,
+                                                    double* __restrict__ carry, int32_t* __restrict__ carry_cnt,
+                                                    int32_t* __restrict__ chunk_last_slot, int64_t nchunks) {
+    const int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (chunk >= nchunks) return;
+    const unsigned lt = lanemask_lt();
+    int32_t cur_slot = -1;    // open partition (uniform across the warp)
+    double acc = 0.0;         // its partial so far
+    int32_t acc_cnt = 0;      // number of (x present) products folded into acc
+    bool prefix_open = true;  // no head seen yet in this chunk
+    const int64_t base = chunk * SPMV_CHUNK;
+#pragma unroll 2
+    for (int step = 0; step < SPMV_STEPS; ++step) {
+        const int64_t p = base + step * 32 + lane;
+        int64_t k = GAP_KEY;
+        double v = 0.0;
+        if (p < cap) {
+            k = keys[p];
+            v = vals[p];
+        }
+        const bool head = k == 0;
+        double t = 0.0;
+        int32_t tc = 0;
+        if (k > 0 && k <= nx) {
+            bool present = true;
+            if (SPARSE_X) present = xmask[k - 1] != 0;
+            if (present) {
+                t = __dmul_rn(x[k - 1], v);
+                tc = 1;
+            }
+        }
+        const unsigned hb = __ballot_sync(0xffffffffu, head);
+        // segmented inclusive scan (segments start at heads)
+        const unsigned hle = hb & (lt | (1u << lane));
+        const int seg_lo = hle ? 31 - __clz(hle) : 0;
+        double st = t;
+        int32_t sc = tc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double ot = __shfl_up_sync(0xffffffffu, st, o);
+            const int32_t oc = __shfl_up_sync(0xffffffffu, sc, o);
+            if (lane >= o && lane - o >= seg_lo) {
+                st = __dadd_rn(ot, st);
+                sc += oc;
+            }
+        }
+        // every head closes the partition that was open before it
+        const double prev_t = __shfl_up_sync(0xffffffffu, st, 1);
+        const int32_t prev_c = __shfl_up_sync(0xffffffffu, sc, 1);
+        const unsigned hlt = hb & lt;
+        const int prev_head_lane = hlt ? 31 - __clz(hlt) : -1;
+        const int32_t my_slot = head ? (int32_t)v - 1 : -1;
+        const int32_t prev_head_slot = __shfl_sync(0xffffffffu, my_slot, prev_head_lane < 0 ? 0 : prev_head_lane);
+        if (head) {
+            double tot = lane > 0 ? prev_t : 0.0;
+            int32_t totc = lane > 0 ? prev_c : 0;
+            if (prev_head_lane < 0) {   // the closing partition started before this step
+                tot = lane > 0 ? __dadd_rn(acc, tot) : acc;
+                totc += acc_cnt;
+                if (cur_slot >= 0) {
+                    yslot[cur_slot] = tot;
+                    ycnt[cur_slot] = totc;
+                } else if (prefix_open) {
+                    carry[chunk] = tot;
+                    carry_cnt[chunk] = totc;
+                }
+            } else {
+                yslot[prev_head_slot] = tot;
+                ycnt[prev_head_slot] = totc;
+            }
+        }
+        // carry into the next step: the segment open at lane 31
+        const double last_t = __shfl_sync(0xffffffffu, st, 31);
+        const int32_t last_c = __shfl_sync(0xffffffffu, sc, 31);
+        if (hb) {
+            const int last_head_lane = 31 - __clz(hb);
+            cur_slot = __shfl_sync(0xffffffffu, my_slot, last_head_lane);
+            acc = last_t;
+            acc_cnt = last_c;
+            prefix_open = false;
+        } else {
+            acc = __dadd_rn(acc, last_t);
+            acc_cnt += last_c;
+        }
+    }
+    if (lane == 0) {
+        if (cur_slot >= 0) {   // open partition at the end of the chunk: partial, completed by the fix-up
+            yslot[cur_slot] = acc;
+            ycnt[cur_slot] = acc_cnt;
+        } else {               // no head in the whole chunk
+            carry[chunk] = acc;
+            carry_cnt[chunk] = acc_cnt;
+        }
+        chunk_last_slot[chunk] = cur_slot;
+    }
+}
+
+// chunk c with a head: y[last partition of c] += carry[c+1] + carry[c+2] + ... up to and including the first chunk that has a head
+__global__ void __launch_bounds__(256) k_spmv_fixup(double* __restrict__ yslot, int32_t* __restrict__ ycnt, const double* __restrict__ carry,
+                                                     const int32_t* __restrict__ carry_cnt, const int32_t* __restrict__ chunk_last_slot,
+                                                     int64_t nchunks) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchunks) return;
+    const int32_t slot = chunk_last_slot[c];
+    if (slot < 0) return;
+    double a = yslot[slot];
+    int32_t n = ycnt[slot];
+    for (int64_t d = c + 1; d < nchunks; ++d) {
+        a = __dadd_rn(a, carry[d]);
+        n += carry_cnt[d];
+        if (chunk_last_slot[d] >= 0) break;
+    }
+    yslot[slot] = a;
+    ycnt[slot] = n;
+}
+
+// y by slot -> dense y indexed by partition key (1..ny)
+__global__ void __launch_bounds__(256) k_spmv_to_dense(const double* __restrict__ yslot, const int64_t* __restrict__ sem,
+                                                        const int64_t* __restrict__ slot_key, int64_t nslots, double* __restrict__ y, int64_t ny) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nslots || sem[s] < 0) return;
+    const int64_t k = slot_key[s];
+    if (k >= 1 && k <= ny) y[k - 1] = yslot[s];
+}
+// touched partitions (at least one product) for the sparse output (operations.jl:11-12, sparsevec(::Dict, n))
+__global__ void __launch_bounds__(256) k_flag_touched(const int32_t* __restrict__ ycnt, const int64_t* __restrict__ sem, int64_t nslots,
+                                                       int32_t* __restrict__ flag) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < nslots) flag[s] = (sem[s] >= 0 && ycnt[s] > 0) ? 1 : 0;
+}
+__global__ void __launch_bounds__(256) k_compact_y(const double* __restrict__ yslot, const int64_t* __restrict__ slot_key,
+                                                    const int32_t* __restrict__ flag, const int32_t* __restrict__ idx, int64_t nslots,
+                                                    int64_t* __restrict__ yk, double* __restrict__ yv) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < nslots && flag[s]) {
+        yk[idx[s]] = slot_key[s];
+        yv[idx[s]] = yslot[s];
+    }
+}
+__global__ void __launch_bounds__(256) k_scatter_x(const int64_t* __restrict__ xk, const double* __restrict__ xv, int64_t n,
+                                                    double* __restrict__ x, uint8_t* __restrict__ xmask, int64_t nx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int64_t k = xk[i];
+        if (k >= 1 && k <= nx) {
+            x[k - 1] = xv[i];
+            xmask[k - 1] = 1;
+        }
+    }
+}
+
+// =============================================================================================
+// MappedPackedCSC on the device
+// =============================================================================================
+struct PcsrWorkspace {
+    BatchWorkspace batch;
+    SortWorkspace sort;
+    DBuf<int32_t> op_slot, flag32, idx32, u_pid, new_slots, old2new, rank32, del_slots, cnt32;
+    DBuf<int64_t> miss_keys, cs, u_key, live_pos, nuniq, tmp_k, tmp_owner, del_keys;
+    DBuf<double> u_val, tmp_v, yslot, carry, xdense;
+    DBuf<uint64_t> sk;
+    DBuf<uint32_t> perm;
+    DBuf<uint8_t> xmask;
+    DBuf<int32_t> ycnt, carry_cnt, chunk_last;
+    HPinned<int64_t> h_cs;
+    std::vector<int64_t> h_tmp;
+};
+
+struct Pcsr {
+    PmaCore pma;
+    int64_t nb_partitions = 0;   // pcsr.jl:5
+    // col_keys with tombstones (pcsr.jl:17): host mirror is the authority for the map, device copies serve the kernels
+    std::vector<int64_t> slot_key;
+    std::vector<uint8_t> slot_live;
+    std::vector<int64_t> live_keys_h;   // sorted live keys
+    std::vector<int32_t> live_slot_h;
+    DBuf<int64_t> d_sem;        // per slot: 0-based position of the semaphore cell, -1 = deleted / not yet placed (pcsr.jl:6)
+    DBuf<int64_t> d_next;       // per slot: position of the next placed semaphore (exclusive end of the span)
+    DBuf<int64_t> d_slot_key;
+    DBuf<int64_t> d_live_keys;
+    DBuf<int32_t> d_live_slot;
+    bool next_dirty = true;
+    int64_t max_inkey = 0;      // upper bound of the in-array keys ever stored (sizes the dense x of SpMV)
+
+    int64_t nslots() const { return (int64_t)slot_key.size(); }
+    int64_t nlive() const { return (int64_t)live_keys_h.size(); }
+    int64_t nnz() const { return pma.nnz - nb_partitions; }   // pcsr.jl:11
+
+    void rebuild_live_and_upload(cudaStream_t st) {
+        live_keys_h.clear();
+        live_slot_h.clear();
+        for (int64_t s = 0; s < nslots(); ++s)
+            if (slot_live[s]) { live_keys_h.push_back(slot_key[s]); live_slot_h.push_back((int32_t)s); }
+        const size_t ns = (size_t)nslots(), nl = live_keys_h.size();
+        d_slot_key.ensure(ns + 1);
+        d_live_keys.ensure(nl + 1);
+        d_live_slot.ensure(nl + 1);
+        if (ns) DSA_CUDA(cudaMemcpyAsync(d_slot_key.p, slot_key.data(), ns * 8, cudaMemcpyHostToDevice, st));
+        if (nl) {
+            DSA_CUDA(cudaMemcpyAsync(d_live_keys.p, live_keys_h.data(), nl * 8, cudaMemcpyHostToDevice, st));
+            DSA_CUDA(cudaMemcpyAsync(d_live_slot.p, live_slot_h.data(), nl * 4, cudaMemcpyHostToDevice, st));
+        }
+        DSA_CUDA(cudaStreamSynchronize(st));   // host vectors may be modified after return
+    }
+
+    int32_t host_lookup(int64_t key) const {
+        auto it = std::lower_bound(live_keys_h.begin(), live_keys_h.end(), key);
+        if (it == live_keys_h.end() || *it != key) return -1;
+        return live_slot_h[(size_t)(it - live_keys_h.begin())];
+    }
+
+    void ensure_next(PcsrWorkspace& ws, cudaStream_t st) {
+        if (!next_dirty) return;
+        const int64_t ns = nslots();
+        d_next.ensure((size_t)ns + 1);
+        if (ns > 0) {
+            int32_t* flag = ws.flag32.ensure((size_t)ns);
+            int32_t* rank = ws.rank32.ensure((size_t)ns);
+            int64_t* lp = ws.live_pos.ensure((size_t)ns + 1);
+            int64_t* ndev = ws.nuniq.ensure(4);
+            const unsigned gr = grid_for(ns, 256);
+            DSA_LAUNCH("flag_placed", k_flag_placed, gr, 256, 0, st, d_sem.p, ns, flag);
+            exclusive_scan_i32<int32_t>(ws.batch.scan, flag, rank, ns, ndev + 1, st);
+            DSA_LAUNCH("live_positions", k_live_positions, gr, 256, 0, st, d_sem.p, rank, ns, lp);
+            DSA_LAUNCH("next_sem", k_next_sem, gr, 256, 0, st, d_sem.p, rank, ns, lp, ndev + 1, pma.g.capacity, d_next.p);
+        }
+        next_dirty = false;
+    }
+
+    // MappedPackedCSC(K, L, T) (pcsr.jl:82-86)
+    void init_empty(cudaStream_t st) {
+        pma.build_from_sorted(nullptr, nullptr, 0, nullptr, st);
+        nb_partitions = 0;
+        slot_key.clear();
+        slot_live.clear();
+        rebuild_live_and_upload(st);
+        d_sem.ensure(1);
+        next_dirty = true;
+        max_inkey = 0;
+    }
+
+    // _dynamicsparse (pcsr.jl:354-431): stable sort by (partition key, in-array key), left-fold combine, flatten as
+    // [sem_1, col_1..., sem_2, col_2...] (pcsr.jl:37-51), bulk layout + semaphore positions (pcsr.jl:52-61).
+    void build_coo_d(PcsrWorkspace& ws, const int64_t* d_inkeys, const int64_t* d_partkeys, const double* d_vals, int64_t n, int combine,
+                     cudaStream_t st);
+
+    // batched setindex! (pcsr.jl:341-347 per op): see DESIGN.md §4
+    void set_batch_d(PcsrWorkspace& ws, const int64_t* d_inkeys, const int64_t* d_partkeys, const double* d_vals, int64_t n,
+                     int64_t* max_part_nz, int64_t* max_key_nz, cudaStream_t st);
+
+    void get_batch_d(PcsrWorkspace& ws, const int64_t* d_inkeys, const int64_t* d_partkeys, int64_t n, double* d_out, cudaStream_t st) {
+        if (n <= 0) return;
+        ensure_next(ws, st);
+        int32_t* op_slot = ws.op_slot.ensure((size_t)n);
+        int64_t* cs = ws.cs.ensure(CS_WORDS);
+        DSA_LAUNCH("colstat_init", k_colstat_init, 1, 1, 0, st, cs);
+        DSA_LAUNCH("col_lookup", k_col_lookup, grid_for(n, 256), 256, 0, st, d_partkeys, (const int64_t*)nullptr, (const double*)nullptr, n,
+                   d_live_keys.p, d_live_slot.p, nlive(), op_slot, cs);
+        DSA_LAUNCH("get", k_get, grid_for(n, 256), 256, 0, st, pma.keys.p, pma.vals.p, pma.g.capacity, op_slot, d_inkeys, n, d_sem.p,
+                   d_next.p, d_out);
+    }
+
+    // spans of the listed slots, emitted in list order: returns total count; outputs in ws.tmp_k / tmp_v / tmp_owner
+    int64_t gather_spans(PcsrWorkspace& ws, const int32_t* d_slots, int64_t nsl, const int64_t* d_owner_keys, bool want_vals, cudaStream_t st) {
+        ensure_next(ws, st);
+        int32_t* cnt = ws.cnt32.ensure((size_t)nsl + 1);
+        int32_t* off = ws.idx32.ensure((size_t)nsl + 1);
+        int64_t* tot = ws.nuniq.ensure(4);
+        DSA_LAUNCH("span_count", k_span_count, grid_for(nsl * 32, 256), 256, 0, st, pma.keys.p, d_slots, nsl, d_sem.p, d_next.p, cnt);
+        exclusive_scan_i32<int32_t>(ws.batch.scan, cnt, off, nsl, tot, st);
+        int64_t h_tot = 0;
+        DSA_CUDA(cudaMemcpyAsync(&h_tot, tot, 8, cudaMemcpyDeviceToHost, st));
+        DSA_CUDA(cudaStreamSynchronize(st));
+        if (h_tot > 0) {
+            ws.tmp_k.ensure((size_t)h_tot);
+            if (want_vals) ws.tmp_v.ensure((size_t)h_tot);
+            if (d_owner_keys) ws.tmp_owner.ensure((size_t)h_tot);
+            DSA_LAUNCH("span_emit", k_span_emit, grid_for(nsl * 32, 256), 256, 0, st, pma.keys.p, pma.vals.p, d_slots, nsl, d_sem.p, d_next.p,
+                       off, ws.tmp_k.p, want_vals ? ws.tmp_v.p : (double*)nullptr, d_owner_keys ? ws.tmp_owner.p : (int64_t*)nullptr,
+                       d_owner_keys);
+        }
+        return h_tot;
+    }
+
+    // deletepartition! for a list of slots (pcsr.jl:188-204): purge spans, rebalance, tombstone
+    void delete_slots(PcsrWorkspace& ws, const std::vector<int32_t>& slots, const int32_t* d_slots, cudaStream_t st) {
+        const int64_t nsl = (int64_t)slots.size();
+        if (nsl == 0) return;
+        ensure_next(ws, st);
+        pma.prepare_batch_scratch(ws.batch, 0, st);
+        DSA_LAUNCH("span_purge", k_span_purge, grid_for(nsl * 32, 256), 256, 0, st, pma.keys.p, pma.vals.p, d_slots, nsl, d_sem.p, d_next.p,
+                   pma.leafcnt.p, ws.batch.touched.p, ilog2_i64(pma.g.segment_capacity));
+        DSA_LAUNCH("clear_sems", k_clear_sems, grid_for(nsl, 256), 256, 0, st, d_sem.p, d_slots, nsl);
+        pma.rebalance_after(ws.batch, 0, d_sem.p, st);
+        for (int32_t s : slots) slot_live[(size_t)s] = 0;   // pcsr.jl:202,209
+        nb_partitions -= nsl;                                // pcsr.jl:191
+        rebuild_live_and_upload(st);
+        next_dirty = true;
+    }
+
+    // flat SpMV; results by slot in ws.yslot / ws.ycnt
+    void spmv_slots(PcsrWorkspace& ws, const double* d_x, const uint8_t* d_xmask, int64_t nx, cudaStream_t st) {
+        const int64_t cap = pma.g.capacity;
+        const int64_t nchunks = (cap + SPMV_CHUNK - 1) / SPMV_CHUNK;
+        const int64_t ns = nslots();
+        double* yslot = ws.yslot.ensure((size_t)ns + 1);
+        int32_t* ycnt = ws.ycnt.ensure((size_t)ns + 1);
+        double* carry = ws.carry.ensure((size_t)nchunks);
+        int32_t* ccnt = ws.carry_cnt.ensure((size_t)nchunks);
+        int32_t* clast = ws.chunk_last.ensure((size_t)nchunks);
+        const unsigned gr = grid_for(nchunks * 32, 256);
+        if (d_xmask)
+            DSA_LAUNCH("spmv_flat", (k_spmv_flat<true>), gr, 256, 0, st, pma.keys.p, pma.vals.p, cap, d_x, d_xmask, nx, yslot, ycnt, carry,
+                       ccnt, clast, nchunks);
+        else
+            DSA_LAUNCH("spmv_flat", (k_spmv_flat<false>), gr, 256, 0, st, pma.keys.p, pma.vals.p, cap, d_x, d_xmask, nx, yslot, ycnt, carry,
+                       ccnt, clast, nchunks);
+        DSA_LAUNCH("spmv_fixup", k_spmv_fixup, grid_for(nchunks, 256), 256, 0, st, yslot, ycnt, carry, ccnt, clast, nchunks);
+    }
+
+    void clone_from(const Pcsr& o, cudaStream_t st) {
+        pma.g = o.pma.g;
+        pma.nnz = o.pma.nnz;
+        pma.alloc(o.pma.g);
+        DSA_CUDA(cudaMemcpyAsync(pma.keys.p, o.pma.keys.p, (size_t)pma.g.capacity * 8, cudaMemcpyDeviceToDevice, st));
+        DSA_CUDA(cudaMemcpyAsync(pma.vals.p, o.pma.vals.p, (size_t)pma.g.capacity * 8, cudaMemcpyDeviceToDevice, st));
+        DSA_CUDA(cudaMemcpyAsync(pma.leafcnt.p, o.pma.leafcnt.p, (size_t)pma.g.nb_segments * 4, cudaMemcpyDeviceToDevice, st));
+        nb_partitions = o.nb_partitions;
+        slot_key = o.slot_key;
+        slot_live = o.slot_live;
+        max_inkey = o.max_inkey;
+        d_sem.ensure((size_t)nslots() + 1);
+        if (nslots()) DSA_CUDA(cudaMemcpyAsync(d_sem.p, o.d_sem.p, (size_t)nslots() * 8, cudaMemcpyDeviceToDevice, st));
+        rebuild_live_and_upload(st);
+        next_dirty = true;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+inline int bits_for(uint64_t v) {
+    int b = 0;
+    while (v) { ++b; v >>= 1; }
+    return b;
+}
+
+__global__ void __launch_bounds__(256) k_pack_build_keys(const int64_t* __restrict__ partkeys, const int64_t* __restrict__ inkeys, int64_t n,
+                                                          int64_t pmin, int64_t kmin, int kb, uint64_t* __restrict__ sk,
+                                                          uint32_t* __restrict__ idx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        sk[i] = ((uint64_t)(partkeys[i] - pmin) << kb) | (uint64_t)(inkeys[i] - kmin);
+        idx[i] = (uint32_t)i;
+    }
+}
+__global__ void __launch_bounds__(256) k_shift_keys(const uint64_t* __restrict__ sk, int64_t n, int kb, uint64_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = sk[i] >> kb;
+}
+// left-fold combine of every run, emitted in flattened [sem, col...] order:
+//   element with unique index u in partition c (1-based) lands at rank u + c; the semaphore of c at (first u of c) + c - 1
+__global__ void __launch_bounds__(256) k_build_flatten(const uint64_t* __restrict__ sk, const uint32_t* __restrict__ perm,
+                                                        const int32_t* __restrict__ runflag, const int32_t* __restrict__ uidx,
+                                                        const int32_t* __restrict__ partflag, const int32_t* __restrict__ pidx, int64_t n,
+                                                        const int64_t* __restrict__ inkeys, const int64_t* __restrict__ partkeys,
+                                                        const double* __restrict__ vals, int combine, int with_sems,
+                                                        int64_t* __restrict__ out_k, double* __restrict__ out_v,
+                                                        int64_t* __restrict__ out_partkey) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !runflag[i]) return;
+    const uint32_t src = perm[i];
+    double acc = vals[src];
+    for (int64_t j = i + 1; j < n && sk[j] == sk[i]; ++j) acc = combine_apply(combine, acc, vals[perm[j]]);
+    const int64_t u = uidx[i];
+    if (with_sems) {
+        const int64_t c = (int64_t)pidx[i] + (partflag[i] ? 1 : 0);   // 1-based partition id (pidx = exclusive scan of partflag)
+        out_k[u + c] = inkeys[src];
+        out_v[u + c] = acc;
+        if (partflag[i]) {
+            out_k[u + c - 1] = 0;            // semaphore_key (pcsr.jl:23,39)
+            out_v[u + c - 1] = (double)c;    // T(semaphore_id) (pcsr.jl:40)
+            out_partkey[c - 1] = partkeys[src];
+        }
+    } else {
+        out_k[u] = inkeys[src];
+        out_v[u] = acc;
+    }
+}
+
+inline void Pcsr::build_coo_d(PcsrWorkspace& ws, const int64_t* d_inkeys, const int64_t* d_partkeys, const double* d_vals, int64_t n,
+                              int combine, cudaStream_t st) {
+    if (n == 0) {   // pcsr.jl:443
+        init_empty(st);
+        return;
+    }
+    // ranges of both keys -> bit widths of the packed sort key
+    int64_t* mm = ws.cs.ensure(CS_WORDS);
+    int64_t* hmm = ws.h_cs.ensure(CS_WORDS);
+    minmax_i64(d_partkeys, n, mm, st);
+    minmax_i64(d_inkeys, n, mm + 2, st);
+    DSA_CUDA(cudaMemcpyAsync(hmm, mm, 4 * 8, cudaMemcpyDeviceToHost, st));
+    DSA_CUDA(cudaStreamSynchronize(st));
+    const int64_t pmin = hmm[0], pmax = hmm[1], kmin = hmm[2], kmax = hmm[3];
+    if (kmin < 1) throw DsaError{DSA_ERR_ARGUMENT, "in-array keys must be >= 1 (key 0 is the semaphore key, pcsr.jl:23)"};
+    const int kb = std::max(1, bits_for((uint64_t)(kmax - kmin)));
+    const int pb = std::max(1, bits_for((uint64_t)pmax - (uint64_t)pmin));
+    if (kb + pb > 64) throw DsaError{DSA_ERR_ARGUMENT, "key ranges too wide: bits(row range) + bits(column range) must be <= 64"};
+    uint64_t* sk = ws.sk.ensure((size_t)n);
+    uint32_t* perm = ws.perm.ensure((size_t)n);
+    const unsigned gr = grid_for(n, 256);
+    DSA_LAUNCH("pack_build_keys", k_pack_build_keys, gr, 256, 0, st, d_partkeys, d_inkeys, n, pmin, kmin, kb, sk, perm);
+    radix_sort_pairs(ws.sort, sk, perm, n, kb + pb, st);
+    int32_t* runflag = ws.flag32.ensure((size_t)n);
+    int32_t* uidx = ws.idx32.ensure((size_t)n);
+    int32_t* partflag = ws.rank32.ensure((size_t)n);
+    int32_t* pidx = ws.cnt32.ensure((size_t)n);
+    int64_t* tot = ws.nuniq.ensure(4);
+    DSA_LAUNCH("flag_run_first", k_flag_run_first, gr, 256, 0, st, sk, n, runflag);
+    exclusive_scan_i32<int32_t>(ws.batch.scan, runflag, uidx, n, tot, st);
+    // partition heads: compare the partition part of the sort key
+    uint64_t* skhi = ws.sort.keys_alt.ensure((size_t)n);   // free after the sort
+    DSA_LAUNCH("shift_keys", k_shift_keys, gr, 256, 0, st, sk, n, kb, skhi);
+    DSA_LAUNCH("flag_part_first", k_flag_part_first, gr, 256, 0, st, skhi, n, runflag, partflag);
+    exclusive_scan_i32<int32_t>(ws.batch.scan, partflag, pidx, n, tot + 1, st);
+    int64_t h_tot[2];
+    DSA_CUDA(cudaMemcpyAsync(h_tot, tot, 16, cudaMemcpyDeviceToHost, st));
+    DSA_CUDA(cudaStreamSynchronize(st));
+    const int64_t nuniq = h_tot[0], nparts = h_tot[1];
+    int64_t* fk = ws.u_key.ensure((size_t)(nuniq + nparts));
+    double* fv = ws.u_val.ensure((size_t)(nuniq + nparts));
+    int64_t* pk = ws.miss_keys.ensure((size_t)nparts);
+    DSA_LAUNCH("build_flatten", k_build_flatten, gr, 256, 0, st, sk, perm, runflag, uidx, partflag, pidx, n, d_inkeys, d_partkeys, d_vals,
+               combine, 1, fk, fv, pk);
+    d_sem.ensure((size_t)nparts + 1);
+    pma.build_from_sorted(fk, fv, nuniq + nparts, d_sem.p, st);
+    slot_key.resize((size_t)nparts);
+    slot_live.assign((size_t)nparts, 1);
+    DSA_CUDA(cudaMemcpyAsync(slot_key.data(), pk, (size_t)nparts * 8, cudaMemcpyDeviceToHost, st));
+    DSA_CUDA(cudaStreamSynchronize(st));
+    nb_partitions = nparts;
+    max_inkey = kmax;
+    rebuild_live_and_upload(st);
+    next_dirty = true;
+}
+
+}  // namespace dsa

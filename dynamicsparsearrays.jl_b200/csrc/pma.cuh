@@ -1,0 +1,617 @@
+// libdsa — the packed memory array on the device: layout, bulk build (K4), finds (K6), batched merge with
+// density tree / window selection (K2, K3) and redistribute (K4).  Shared by the vector and both PCSR orientations.
+//
+// HBM layout (SoA, all 8-byte lanes so a warp streams 256 B per load):
+//   keys[capacity]  int64   GAP_KEY = `nothing`; 0 = semaphore key (pcsr.jl:23); >= 1 user keys
+//   vals[capacity]  double  value, or the partition id of a semaphore cell (pcsr.jl:39-40)
+//   leafcnt[nb_segments] int32   stored cells per segment (what _nbcells, utils.jl:48, recounts every time)
+//   post[2*nb_segments]  int32   implicit tree of post-batch counts, level h at off[h] (pma.jl:105-141 walks it leaf->root)
+#pragma once
+#include "common.cuh"
+#include "hostlogic.hpp"
+#include "primitives.cuh"
+#include "spread.cuh"
+
+namespace dsa {
+
+struct Levels {
+    int64_t off[MAX_LEVELS];   // offset of level h in the tree arrays
+    int64_t mn[MAX_LEVELS];    // accept iff mn[h] <= count <= mx[h]   (pma.jl:119-123)
+    int64_t mx[MAX_LEVELS];
+    int64_t nsegs;
+    int H;
+    int lgS;
+};
+
+enum : uint8_t { FL_OVERWRITE = 1, FL_DELETE = 2, FL_INSERT = 4 };
+enum { ST_OVER = 0, ST_UNDER = 1, ST_NINS = 2, ST_ROOT = 3, ST_MISSING = 4, ST_MINKEY = 5, ST_MAXKEY = 6, ST_ANYHIGH = 7, ST_WORDS = 16 };
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+__device__ __forceinline__ int64_t warp_sum_i64(int64_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4 bulk layout: destination-driven spread of n sorted elements over `cap` cells (pma.jl:27-55 + moves.jl:120).
+// One thread per cell: rank via the closed form, coalesced gather + coalesced store, leaf counts by ballot,
+// semaphores[id] = position for key-0 cells (pcsr.jl:55-61).  If src == nullptr only gaps are written and cells that
+// already hold an element are left alone (used after a scatter into a fresh array).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_layout(int64_t* __restrict__ keys, double* __restrict__ vals, int64_t cap, int64_t n,
+                                                 const int64_t* __restrict__ src_k, const double* __restrict__ src_v,
+                                                 int32_t* __restrict__ leafcnt, int64_t* __restrict__ sem, int lgS) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const Spread sp = spread_make(cap, n);
+    int64_t r = -1;
+    if (p < cap) r = spread_rank_at(sp, p);
+    const bool live = r >= 0;
+    if (p < cap) {
+        if (src_k) {
+            if (live) {
+                int64_t k = src_k[r];
+                double v = src_v[r];
+                keys[p] = k;
+                vals[p] = v;
+                if (sem && k == 0) sem[(int64_t)v - 1] = p;
+            } else {
+                keys[p] = GAP_KEY;
+                vals[p] = 0.0;
+            }
+        } else if (!live) {
+            keys[p] = GAP_KEY;
+            vals[p] = 0.0;
+        }
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, live);
+    const int S = 1 << lgS;
+    if (p < cap && (p & (S - 1)) == 0) {
+        unsigned m = S >= 32 ? 0xffffffffu : ((1u << S) - 1u);
+        leafcnt[p >> lgS] = __popc((b >> lane) & m);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6 find: the reference's gapped binary search (finds.jl:29-57), 0-based, one thread per query.
+// Returns the position of the exact hit or of the predecessor (-1 = none); *hit tells which.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t gapped_find(const int64_t* __restrict__ keys, int64_t key, int64_t from, int64_t to, bool* hit) {
+    int64_t lo = from, hi = to;
+    while (lo <= hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        int64_t i = mid;
+        int64_t k = keys[i];
+        while (k == GAP_KEY && i > lo) {   // walk left to the nearest element (finds.jl:33-35)
+            --i;
+            k = keys[i];
+        }
+        if (k == GAP_KEY) {
+            lo = mid + 1;
+        } else if (k > key) {
+            hi = i - 1;
+        } else if (k < key) {
+            lo = mid + 1;
+        } else {
+            *hit = true;
+            return i;
+        }
+    }
+    *hit = false;
+    int64_t i = hi;
+    while (i >= 0 && keys[i] == GAP_KEY) --i;   // finds.jl:49-56
+    return i;
+}
+
+// Locate every (sorted, unique) op.  pid == nullptr: plain PMA, search the whole array.  Otherwise the partition span is
+// [sem[pid], next_sem[pid]) and, like pcsr.jl:305-307, inserts search (sem, end] while deletes search [sem, end].
+// sem[pid] < 0 marks a partition created by this batch: everything goes right before the next live semaphore.
+__global__ void __launch_bounds__(256) k_locate(const int64_t* __restrict__ keys, int64_t cap, const int32_t* __restrict__ op_pid,
+                                                 const int64_t* __restrict__ op_key, const double* __restrict__ op_val, int64_t nops,
+                                                 const int64_t* __restrict__ sem, const int64_t* __restrict__ next_sem,
+                                                 int64_t* __restrict__ op_pos, uint8_t* __restrict__ op_flag,
+                                                 const int64_t* __restrict__ n_dev) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (n_dev ? *n_dev : nops)) return;
+    const int64_t key = op_key[i];
+    const bool is_set = op_val[i] != 0.0;   // pma.jl:197, pcsr.jl:301
+    int64_t pos;
+    bool hit = false;
+    if (op_pid) {
+        const int32_t pid = op_pid[i];
+        const int64_t s = sem[pid];
+        const int64_t e = next_sem[pid];
+        if (s < 0 || key == 0) {
+            pos = e - 1;   // new partition (or its semaphore): before the next live semaphore (pcsr.jl:121-126,101)
+        } else {
+            pos = gapped_find(keys, key, is_set ? s + 1 : s, e - 1, &hit);
+        }
+    } else {
+        pos = gapped_find(keys, key, 0, cap - 1, &hit);
+    }
+    op_pos[i] = pos;
+    op_flag[i] = hit ? (is_set ? FL_OVERWRITE : FL_DELETE) : ((is_set || (op_pid && key == 0)) ? FL_INSERT : 0);
+}
+
+// batched getindex (pma.jl:189-193 / pcsr.jl:228-232): value or 0.0.  pid < 0 = column absent (pcsr.jl:263-265).
+__global__ void __launch_bounds__(256) k_get(const int64_t* __restrict__ keys, const double* __restrict__ vals, int64_t cap,
+                                              const int32_t* __restrict__ q_pid, const int64_t* __restrict__ q_key, int64_t nq,
+                                              const int64_t* __restrict__ sem, const int64_t* __restrict__ next_sem,
+                                              double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    bool hit = false;
+    int64_t pos = -1;
+    if (q_pid) {
+        const int32_t pid = q_pid[i];
+        if (pid >= 0 && sem[pid] >= 0) pos = gapped_find(keys, q_key[i], sem[pid], next_sem[pid] - 1, &hit);
+    } else {
+        pos = gapped_find(keys, q_key[i], 0, cap - 1, &hit);
+    }
+    out[i] = hit ? vals[pos] : 0.0;
+}
+
+// hits: overwrite in place (writes.jl:16-19) or blank the cell (writes.jl:65-68); misses with a value become inserts
+__global__ void __launch_bounds__(256) k_apply_hits(int64_t* __restrict__ keys, double* __restrict__ vals,
+                                                     const int64_t* __restrict__ op_pos, const uint8_t* __restrict__ op_flag,
+                                                     const double* __restrict__ op_val, int64_t nops, int32_t* __restrict__ leafcnt,
+                                                     uint8_t* __restrict__ touched, int lgS, const int64_t* __restrict__ n_dev) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (n_dev ? *n_dev : nops)) return;
+    const uint8_t f = op_flag[i];
+    if (f == FL_OVERWRITE) {
+        vals[op_pos[i]] = op_val[i];
+    } else if (f == FL_DELETE) {
+        const int64_t p = op_pos[i];
+        keys[p] = GAP_KEY;
+        vals[p] = 0.0;
+        atomicSub(&leafcnt[p >> lgS], 1);
+        touched[p >> lgS] = 1;
+    }
+}
+
+// order-preserving compaction of the inserts (ins_idx = exclusive scan of the insert flags)
+__global__ void __launch_bounds__(256) k_flag_eq(const uint8_t* __restrict__ f, int64_t n, uint8_t what, int32_t* __restrict__ out,
+                                                  const int64_t* __restrict__ n_dev) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (i < (n_dev ? *n_dev : n) && f[i] == what) ? 1 : 0;
+}
+__global__ void __launch_bounds__(256) k_compact_inserts(const int64_t* __restrict__ op_key, const double* __restrict__ op_val,
+                                                          const int64_t* __restrict__ op_pos, const uint8_t* __restrict__ op_flag,
+                                                          const int32_t* __restrict__ ins_idx, int64_t nops,
+                                                          int64_t* __restrict__ ins_key, double* __restrict__ ins_val,
+                                                          int64_t* __restrict__ ins_pos, const int64_t* __restrict__ n_dev) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (n_dev ? *n_dev : nops)) return;
+    if (op_flag[i] != FL_INSERT) return;
+    const int32_t j = ins_idx[i];
+    ins_key[j] = op_key[i];
+    ins_val[j] = op_val[i];
+    ins_pos[j] = op_pos[i];
+}
+// per-leaf bookkeeping of the compacted inserts: every new key belongs to the leaf of its predecessor cell; inserts are
+// sorted, so the inserts of one leaf are contiguous and ins_first[leaf] is the index of the first one
+__global__ void __launch_bounds__(256) k_insert_leaf_info(const int64_t* __restrict__ ins_pos, const int64_t* __restrict__ nins_dev,
+                                                           int32_t* __restrict__ inscnt, int32_t* __restrict__ ins_first,
+                                                           uint8_t* __restrict__ touched, int lgS) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= *nins_dev) return;
+    const int64_t pos = ins_pos[j];
+    const int64_t leaf = (pos < 0 ? 0 : pos) >> lgS;
+    atomicAdd(&inscnt[leaf], 1);
+    bool first = true;
+    if (j > 0) {
+        const int64_t pq = ins_pos[j - 1];
+        first = ((pq < 0 ? 0 : pq) >> lgS) != leaf;
+    }
+    if (first) {
+        ins_first[leaf] = (int32_t)j;
+        touched[leaf] = 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3 density tree: post[0][l] = leafcnt[l] + inscnt[l]; 10 levels per block in shared memory, upper levels by one block
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_tree_low(const int32_t* __restrict__ leafcnt, const int32_t* __restrict__ inscnt,
+                                                    int32_t* __restrict__ post, Levels L) {
+    __shared__ int32_t s[1024];
+    const int64_t idx = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    int32_t v = 0;
+    if (idx < L.nsegs) {
+        v = leafcnt[idx] + (inscnt ? inscnt[idx] : 0);
+        post[L.off[0] + idx] = v;
+    }
+    s[threadIdx.x] = v;
+    __syncthreads();
+    const int top = L.H < 10 ? L.H : 10;
+    for (int k = 1; k <= top; ++k) {
+        const int nk = 1024 >> k;
+        int32_t t = 0;
+        if ((int)threadIdx.x < nk) t = s[2 * threadIdx.x] + s[2 * threadIdx.x + 1];
+        __syncthreads();
+        if ((int)threadIdx.x < nk) {
+            s[threadIdx.x] = t;
+            const int64_t node = (((int64_t)blockIdx.x * 1024) >> k) + threadIdx.x;
+            if (node < (L.nsegs >> k)) post[L.off[k] + node] = t;
+        }
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(1024) k_tree_high(int32_t* __restrict__ post, Levels L) {
+    for (int k = 11; k <= L.H; ++k) {
+        const int64_t nodes = L.nsegs >> k;
+        for (int64_t i = threadIdx.x; i < nodes; i += 1024)
+            post[L.off[k] + i] = post[L.off[k - 1] + 2 * i] + post[L.off[k - 1] + 2 * i + 1];
+        __syncthreads();
+    }
+}
+
+// every touched leaf walks leaf -> root and marks the first window inside its density bounds (pma.jl:113-129)
+__global__ void __launch_bounds__(256) k_select_windows(const uint8_t* __restrict__ touched, const int32_t* __restrict__ post,
+                                                         uint8_t* __restrict__ mark, Levels L, int64_t* __restrict__ status) {
+    const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L.nsegs || !touched[l]) return;
+    for (int h = 0; h <= L.H; ++h) {
+        const int64_t c = post[L.off[h] + (l >> h)];
+        if (L.mn[h] <= c && c <= L.mx[h]) {
+            mark[L.off[h] + (l >> h)] = 1;
+            if (h > 0) status[ST_ANYHIGH] = 1;
+            return;
+        }
+    }
+    const int64_t c = post[L.off[L.H]];
+    if (c > L.mx[L.H]) status[ST_OVER] = 1;   // density > t  -> _extend!  (pma.jl:132-134)
+    else status[ST_UNDER] = 1;                // density < p  -> _shrink!  (pma.jl:135-139)
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2 + K4 merge / redistribute.  One warp per leaf (lane = cell).  The leaf's final window is its outermost marked
+// ancestor (lane h probes level h, one ballot).  Rank of an item inside its window = prefix of post counts over the
+// preceding leaves (read off the implicit tree, <= h loads) + position inside the leaf's merged run; destination =
+// window start + closed-form spread! offset.  h == 0: rewritten in place from registers; h >= 1: scattered into the
+// shadow array and copied back by k_copyback; root mode: scattered into the freshly allocated (resized) array.
+// ---------------------------------------------------------------------------------------------
+struct MergeArgs {
+    const int64_t* src_k;
+    const double* src_v;
+    int64_t* cur_k;   // == src (mutable) for in-place leaves
+    double* cur_v;
+    int64_t* dst_k;   // shadow or new array
+    double* dst_v;
+    const int32_t* post;
+    const uint8_t* mark;
+    const int32_t* inscnt;
+    const int32_t* ins_first;
+    const int64_t* ins_key;
+    const double* ins_val;
+    const int64_t* ins_pos;
+    int32_t* leafcnt;
+    int64_t* sem;   // nullable; 0-based positions per partition id
+    int root_mode;
+    int64_t root_c, root_m;
+};
+
+__device__ __forceinline__ int window_height(const uint8_t* __restrict__ mark, const Levels& L, int64_t l, int lane) {
+    bool mk = false;
+    if (lane <= L.H) mk = mark[L.off[lane] + (l >> lane)] != 0;
+    const unsigned b = __ballot_sync(0xffffffffu, mk);
+    return b ? 31 - __clz(b) : -1;
+}
+
+__global__ void __launch_bounds__(256) k_merge_scatter(MergeArgs A, Levels L) {
+    const int64_t l = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (l >= L.nsegs) return;
+    int h;
+    if (A.root_mode) h = L.H;
+    else {
+        h = window_height(A.mark, L, l, lane);
+        if (h < 0) return;
+    }
+    const int nins = A.inscnt[l];
+    if (!A.root_mode && h == 0 && nins == 0) return;   // leaf accepted, nothing inserted: nothing moves (pma.jl:96-99)
+    const int S = 1 << L.lgS;
+    const int64_t first_leaf = (l >> h) << h;
+    const int64_t c = A.root_mode ? A.root_c : ((int64_t)S << h);
+    const int64_t m = A.root_mode ? A.root_m : (int64_t)A.post[L.off[h] + (l >> h)];
+    int64_t term = 0;
+    if (lane < h && ((l >> lane) & 1)) term = A.post[L.off[lane] + ((l >> lane) - 1)];
+    const int64_t base = warp_sum_i64(term);
+    const int64_t p0 = l << L.lgS;
+    const int64_t p = p0 + lane;
+    int64_t key = GAP_KEY;
+    double val = 0.0;
+    if (lane < S) {
+        key = A.src_k[p];
+        val = A.src_v[p];
+    }
+    const bool live = key != GAP_KEY;
+    const unsigned lm = __ballot_sync(0xffffffffu, live);
+    const int srank = __popc(lm & lanemask_lt());
+    const int64_t i0 = nins ? A.ins_first[l] : 0;
+    int cntb = 0;
+    if (live && nins) {   // inserts whose predecessor lies before this cell
+        int lo = 0, hi = nins;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (A.ins_pos[i0 + mid] < p) lo = mid + 1;
+            else hi = mid;
+        }
+        cntb = lo;
+    }
+    const Spread sp = spread_make(c, m);
+    const int64_t wbase = A.root_mode ? 0 : (first_leaf << L.lgS);
+    int64_t* dk;
+    double* dv;
+    if (!A.root_mode && h == 0) {
+        dk = A.cur_k;
+        dv = A.cur_v;
+        __syncwarp();
+        if (lane < S) {
+            dk[p] = GAP_KEY;
+            dv[p] = 0.0;
+        }
+        __syncwarp();
+    } else {
+        dk = A.dst_k;
+        dv = A.dst_v;
+    }
+    if (live) {
+        const int64_t d = wbase + spread_dest(sp, base + srank + cntb);
+        dk[d] = key;
+        dv[d] = val;
+        if (A.sem && key == 0) A.sem[(int64_t)val - 1] = d;   // moves.jl:160-166
+    }
+    for (int j = lane; j < nins; j += 32) {
+        const int64_t ipos = A.ins_pos[i0 + j];
+        const int q = (int)(ipos - p0);   // -1 .. S-1
+        const int surv_le = q < 0 ? 0 : __popc(lm & (q >= 31 ? 0xffffffffu : ((2u << q) - 1u)));
+        const int64_t d = wbase + spread_dest(sp, base + surv_le + j);
+        const int64_t ik = A.ins_key[i0 + j];
+        const double iv = A.ins_val[i0 + j];
+        dk[d] = ik;
+        dv[d] = iv;
+        if (A.sem && ik == 0) A.sem[(int64_t)iv - 1] = d;
+    }
+    if (!A.root_mode && h == 0 && lane == 0) A.leafcnt[l] = (int32_t)m;
+}
+
+// windows of height >= 1: copy the shadow back, writing the analytic gaps and the new leaf counts
+__global__ void __launch_bounds__(256) k_copyback(int64_t* __restrict__ keys, double* __restrict__ vals,
+                                                   const int64_t* __restrict__ scr_k, const double* __restrict__ scr_v,
+                                                   const int32_t* __restrict__ post, const uint8_t* __restrict__ mark,
+                                                   int32_t* __restrict__ leafcnt, Levels L) {
+    const int64_t l = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (l >= L.nsegs) return;
+    const int h = window_height(mark, L, l, lane);
+    if (h < 1) return;
+    const int S = 1 << L.lgS;
+    const int64_t first_leaf = (l >> h) << h;
+    const Spread sp = spread_make((int64_t)S << h, (int64_t)post[L.off[h] + (l >> h)]);
+    const int64_t p = (l << L.lgS) + lane;
+    bool live = false;
+    if (lane < S) {
+        live = spread_rank_at(sp, p - (first_leaf << L.lgS)) >= 0;
+        keys[p] = live ? scr_k[p] : GAP_KEY;
+        vals[p] = live ? scr_v[p] : 0.0;
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, live);
+    if (lane == 0) leafcnt[l] = __popc(b);
+}
+
+// recount (used after clone/import and by tests)
+__global__ void __launch_bounds__(256) k_count_leaves(const int64_t* __restrict__ keys, int64_t cap, int32_t* __restrict__ leafcnt, int lgS) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool live = p < cap && keys[p] != GAP_KEY;
+    const unsigned b = __ballot_sync(0xffffffffu, live);
+    const int S = 1 << lgS;
+    if (p < cap && (p & (S - 1)) == 0) {
+        unsigned m = S >= 32 ? 0xffffffffu : ((1u << S) - 1u);
+        leafcnt[p >> lgS] = __popc((b >> lane) & m);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// order-preserving compaction of the stored cells of [from, to) (iterate pma.jl:165-180, nonzeroinds/nonzeros
+// vector.jl:93-109): per-cell flags -> scan -> scatter
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_flag_live(const int64_t* __restrict__ keys, int64_t n, int32_t* __restrict__ flag, int skip_sem) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) {
+        const int64_t k = keys[p];
+        flag[p] = (k != GAP_KEY && !(skip_sem && k == 0)) ? 1 : 0;
+    }
+}
+__global__ void __launch_bounds__(256) k_compact_cells(const int64_t* __restrict__ keys, const double* __restrict__ vals, int64_t n,
+                                                        const int32_t* __restrict__ idx, int skip_sem, int64_t* __restrict__ ok,
+                                                        double* __restrict__ ov) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) {
+        const int64_t k = keys[p];
+        if (k != GAP_KEY && !(skip_sem && k == 0)) {
+            ok[idx[p]] = k;
+            ov[idx[p]] = vals[p];
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_export_cells(const int64_t* __restrict__ keys, const double* __restrict__ vals, int64_t cap,
+                                                       uint8_t* __restrict__ occ, int64_t* __restrict__ ok, double* __restrict__ ov) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < cap) {
+        const int64_t k = keys[p];
+        const bool live = k != GAP_KEY;
+        occ[p] = live ? 1 : 0;
+        ok[p] = live ? k : 0;
+        ov[p] = live ? vals[p] : 0.0;
+    }
+}
+
+// =============================================================================================
+// Host-side PMA core
+// =============================================================================================
+struct BatchWorkspace {   // per-handle scratch reused by every batch
+    DBuf<int64_t> op_pos;
+    DBuf<uint8_t> op_flag;
+    DBuf<int32_t> ins_idx, flag32;
+    DBuf<int64_t> ins_key, ins_pos;
+    DBuf<double> ins_val;
+    DBuf<int32_t> inscnt, ins_first, post;
+    DBuf<uint8_t> touched, mark;
+    DBuf<int64_t> shadow_k;
+    DBuf<double> shadow_v;
+    DBuf<int64_t> status;
+    HPinned<int64_t> h_status;
+    ScanWorkspace scan;
+};
+
+struct PmaCore {
+    Geometry g{};
+    int64_t nnz = 0;   // nb_elements (pma.jl:12)
+    DBuf<int64_t> keys;
+    DBuf<double> vals;
+    DBuf<int32_t> leafcnt;
+
+    Levels levels() const {
+        Levels L;
+        memset(&L, 0, sizeof(L));
+        L.nsegs = g.nb_segments;
+        L.H = (int)g.height;
+        L.lgS = ilog2_i64(g.segment_capacity);
+        int64_t o = 0;
+        for (int h = 0; h <= L.H; ++h) {
+            L.off[h] = o;
+            o += g.nb_segments >> h;
+        }
+        level_bounds(g.segment_capacity, g.height, g.t_d, g.p_d, L.mn, L.mx);
+        return L;
+    }
+    int64_t tree_size() const { return 2 * g.nb_segments + 8; }
+
+    void alloc(const Geometry& ng) {
+        g = ng;
+        keys.ensure((size_t)g.capacity);
+        vals.ensure((size_t)g.capacity);
+        leafcnt.ensure((size_t)g.nb_segments);
+    }
+
+    // PackedMemoryArray(keys, values; sort = false) (pma.jl:69-84) / empty constructor (pma.jl:86-91)
+    void build_from_sorted(const int64_t* d_k, const double* d_v, int64_t n, int64_t* d_sem, cudaStream_t st) {
+        alloc(geometry_for_build(n));
+        nnz = n;
+        const int lgS = ilog2_i64(g.segment_capacity);
+        if (n == 0) {   // all gaps: any non-null source will do, it is never dereferenced
+            d_k = keys.p;
+            d_v = vals.p;
+        }
+        DSA_LAUNCH("layout_build", k_layout, grid_for(g.capacity, 256), 256, 0, st, keys.p, vals.p, g.capacity, n, d_k, d_v,
+                   leafcnt.p, d_sem, lgS);
+    }
+
+    // The batch tail shared by every mutation: ops are located (op_pos/op_flag), deletes/purges already counted in leafcnt
+    // + touched.  Builds the density tree, selects windows, merges/redistributes, resizes when the root fails.
+    // d_sem (nullable) = semaphore positions to refresh.  Returns through nnz.
+    void rebalance_after(BatchWorkspace& ws, int64_t nins, int64_t* d_sem, cudaStream_t st) {
+        Levels L = levels();
+        const int64_t nsegs = g.nb_segments;
+        int32_t* post = ws.post.ensure((size_t)tree_size());
+        uint8_t* mark = ws.mark.ensure((size_t)tree_size());
+        int64_t* status = ws.status.ensure(ST_WORDS);
+        DSA_CUDA(cudaMemsetAsync(mark, 0, (size_t)tree_size(), st));
+        DSA_LAUNCH("tree_low", k_tree_low, grid_for(nsegs, 1024), 1024, 0, st, leafcnt.p, ws.inscnt.p, post, L);
+        if (L.H > 10) DSA_LAUNCH("tree_high", k_tree_high, 1, 1024, 0, st, post, L);
+        DSA_LAUNCH("select_windows", k_select_windows, grid_for(nsegs, 256), 256, 0, st, ws.touched.p, post, mark, L, status);
+        // status[ST_ROOT] <- root count
+        DSA_CUDA(cudaMemcpyAsync(status + ST_ROOT, post + L.off[L.H], sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        int64_t* hs = ws.h_status.ensure(ST_WORDS);
+        DSA_CUDA(cudaMemcpyAsync(hs, status, ST_WORDS * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        DSA_CUDA(cudaStreamSynchronize(st));
+        const int64_t N = (int64_t)(int32_t)(hs[ST_ROOT] & 0xffffffff);
+        MergeArgs A;
+        memset(&A, 0, sizeof(A));
+        A.src_k = keys.p; A.src_v = vals.p; A.cur_k = keys.p; A.cur_v = vals.p;
+        A.post = post; A.mark = mark; A.inscnt = ws.inscnt.p; A.ins_first = ws.ins_first.p;
+        A.ins_key = ws.ins_key.p; A.ins_val = ws.ins_val.p; A.ins_pos = ws.ins_pos.p;
+        A.leafcnt = leafcnt.p; A.sem = d_sem;
+        const unsigned warp_grid = grid_for(nsegs * 32, 256);
+        if (hs[ST_OVER] || hs[ST_UNDER]) {
+            // root failed: _extend!/_shrink! (pma.jl:132-139) until the root accepts, then one full spread into the new array
+            Geometry ng = geometry_after_root_failure(g, N);
+            DBuf<int64_t> nk;
+            DBuf<double> nv;
+            nk.ensure((size_t)ng.capacity);
+            nv.ensure((size_t)ng.capacity);
+            A.dst_k = nk.p; A.dst_v = nv.p; A.root_mode = 1; A.root_c = ng.capacity; A.root_m = N;
+            DSA_LAUNCH("merge_scatter_root", k_merge_scatter, warp_grid, 256, 0, st, A, L);
+            g = ng;
+            leafcnt.ensure((size_t)g.nb_segments);
+            DSA_LAUNCH("layout_gaps", k_layout, grid_for(g.capacity, 256), 256, 0, st, nk.p, nv.p, g.capacity, N,
+                       (const int64_t*)nullptr, (const double*)nullptr, leafcnt.p, (int64_t*)nullptr, ilog2_i64(g.segment_capacity));
+            DSA_CUDA(cudaStreamSynchronize(st));
+            keys.swap(nk);
+            vals.swap(nv);
+        } else {
+            const bool any_high = hs[ST_ANYHIGH] != 0;   // some window above leaf level: needs the shadow array
+            if (any_high) {
+                A.dst_k = ws.shadow_k.ensure((size_t)g.capacity);
+                A.dst_v = ws.shadow_v.ensure((size_t)g.capacity);
+            }
+            DSA_LAUNCH("merge_scatter", k_merge_scatter, warp_grid, 256, 0, st, A, L);
+            if (any_high)
+                DSA_LAUNCH("copyback", k_copyback, warp_grid, 256, 0, st, keys.p, vals.p, A.dst_k, A.dst_v, post, mark, leafcnt.p, L);
+        }
+        nnz = N;
+        (void)nins;
+    }
+
+    void prepare_batch_scratch(BatchWorkspace& ws, int64_t nops, cudaStream_t st) {
+        const int64_t nsegs = g.nb_segments;
+        ws.op_pos.ensure((size_t)nops + 1);
+        ws.op_flag.ensure((size_t)nops + 1);
+        ws.ins_idx.ensure((size_t)nops + 1);
+        ws.ins_key.ensure((size_t)nops + 1);
+        ws.ins_val.ensure((size_t)nops + 1);
+        ws.ins_pos.ensure((size_t)nops + 1);
+        ws.inscnt.ensure((size_t)nsegs);
+        ws.ins_first.ensure((size_t)nsegs);
+        ws.touched.ensure((size_t)nsegs);
+        int64_t* status = ws.status.ensure(ST_WORDS);
+        DSA_CUDA(cudaMemsetAsync(ws.inscnt.p, 0, (size_t)nsegs * sizeof(int32_t), st));
+        DSA_CUDA(cudaMemsetAsync(ws.touched.p, 0, (size_t)nsegs, st));
+        DSA_CUDA(cudaMemsetAsync(status, 0, ST_WORDS * sizeof(int64_t), st));
+    }
+
+    // sorted unique ops -> located, applied, merged.  op_pid/sem/next_sem nullable (plain PMA).
+    void apply_sorted_ops(BatchWorkspace& ws, const int32_t* op_pid, const int64_t* op_key, const double* op_val, int64_t nops,
+                          int64_t* d_sem, const int64_t* d_next_sem, cudaStream_t st, bool scratch_ready = false,
+                          const int64_t* n_dev = nullptr) {
+        if (!scratch_ready) prepare_batch_scratch(ws, nops, st);
+        const int lgS = ilog2_i64(g.segment_capacity);
+        int64_t nins = 0;
+        if (nops > 0) {
+            const unsigned gr = grid_for(nops, 256);
+            DSA_LAUNCH("locate", k_locate, gr, 256, 0, st, keys.p, g.capacity, op_pid, op_key, op_val, nops, d_sem, d_next_sem,
+                       ws.op_pos.p, ws.op_flag.p, n_dev);
+            DSA_LAUNCH("apply_hits", k_apply_hits, gr, 256, 0, st, keys.p, vals.p, ws.op_pos.p, ws.op_flag.p, op_val, nops,
+                       leafcnt.p, ws.touched.p, lgS, n_dev);
+            // ins_idx = exclusive scan of (flag == FL_INSERT)
+            int32_t* f32 = ws.flag32.ensure((size_t)nops);
+            DSA_LAUNCH("flag_inserts", k_flag_eq, gr, 256, 0, st, ws.op_flag.p, nops, (uint8_t)FL_INSERT, f32, n_dev);
+            exclusive_scan_i32<int32_t>(ws.scan, f32, ws.ins_idx.p, nops, ws.status.p + ST_NINS, st);
+            DSA_LAUNCH("compact_inserts", k_compact_inserts, gr, 256, 0, st, op_key, op_val, ws.op_pos.p, ws.op_flag.p, ws.ins_idx.p,
+                       nops, ws.ins_key.p, ws.ins_val.p, ws.ins_pos.p, n_dev);
+            DSA_LAUNCH("insert_leaf_info", k_insert_leaf_info, gr, 256, 0, st, ws.ins_pos.p, ws.status.p + ST_NINS, ws.inscnt.p,
+                       ws.ins_first.p, ws.touched.p, lgS);
+        }
+        rebalance_after(ws, nins, d_sem, st);
+    }
+};
+
+}  // namespace dsa

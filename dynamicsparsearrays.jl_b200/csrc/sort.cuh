@@ -1,0 +1,124 @@
+// libdsa K1 — device radix sort of the pending batch.
+//
+// LSD radix sort of (uint64 key, uint32 payload) pairs over the bit range [0, nbits), 8 bits per
+// pass, stable.  Each pass: (1) per-tile digit histogram, (2) exclusive scan of the (digit-major,
+// tile-minor) count table, (3) stable scatter: every warp ranks its keys with __match_any_sync
+// in tile order, so equal digits keep their input order.  Tiles are 256 threads x 16 keys.
+#pragma once
+#include "common.cuh"
+#include "primitives.cuh"
+
+namespace dsa {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;   // 4096 keys per tile
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_RADIX = 256;
+
+// counts[digit * ntiles + tile]
+__global__ void __launch_bounds__(RS_THREADS) k_rs_histogram(const uint64_t* __restrict__ keys, int64_t n, int shift,
+                                                              int32_t* __restrict__ counts, int64_t ntiles) {
+    __shared__ int32_t h[RS_RADIX];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * RS_TILE;
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        int64_t idx = base + (int64_t)i * RS_THREADS + threadIdx.x;
+        if (idx < n) atomicAdd(&h[(unsigned)((keys[idx] >> shift) & 0xff)], 1);
+    }
+    __syncthreads();
+    counts[(int64_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
+}
+
+// offsets = exclusive scan of counts (digit-major).  Warp w owns keys [w*512, (w+1)*512) of the tile, processed in
+// 16 rounds of 32 consecutive keys, so (warp, round, lane) order == input order.
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                                            uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n,
+                                                            int shift, const int32_t* __restrict__ offsets, int64_t ntiles) {
+    __shared__ int32_t wcnt[RS_WARPS][RS_RADIX];   // per-warp digit counts, then exclusive per-warp bases
+    __shared__ int32_t dbase[RS_RADIX];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int d = threadIdx.x; d < RS_WARPS * RS_RADIX; d += RS_THREADS) (&wcnt[0][0])[d] = 0;
+    dbase[threadIdx.x] = offsets[(int64_t)threadIdx.x * ntiles + blockIdx.x];
+    __syncthreads();
+    const int64_t wbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)wid * (RS_ITEMS * 32);
+    uint64_t k[RS_ITEMS];
+    int32_t rank[RS_ITEMS];
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        int64_t idx = wbase + r * 32 + lane;
+        bool valid = idx < n;
+        k[r] = valid ? keys_in[idx] : ~uint64_t(0);
+        unsigned d = (unsigned)((k[r] >> shift) & 0xff);
+        // invalid lanes use a digit id outside the radix so they never match valid ones
+        unsigned dm = valid ? d : 0x100u;
+        unsigned peers = __match_any_sync(0xffffffffu, dm);
+        int before = __popc(peers & ((1u << lane) - 1));
+        int32_t basecnt = 0;
+        if (valid) basecnt = wcnt[wid][d];
+        __syncwarp();
+        if (valid && before == 0) wcnt[wid][d] = basecnt + __popc(peers);
+        __syncwarp();
+        rank[r] = basecnt + before;
+    }
+    __syncthreads();
+    // exclusive scan over warps per digit (thread d handles digit d)
+    {
+        int d = threadIdx.x;
+        int32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) {
+            int32_t c = wcnt[w][d];
+            wcnt[w][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        int64_t idx = wbase + r * 32 + lane;
+        if (idx < n) {
+            unsigned d = (unsigned)((k[r] >> shift) & 0xff);
+            int64_t dst = (int64_t)dbase[d] + wcnt[wid][d] + rank[r];
+            keys_out[dst] = k[r];
+            vals_out[dst] = vals_in[idx];
+        }
+    }
+}
+
+struct SortWorkspace {
+    DBuf<int32_t> counts;
+    DBuf<uint64_t> keys_alt;
+    DBuf<uint32_t> vals_alt;
+    ScanWorkspace scan;
+};
+
+// Sorts in place (result ends in d_keys / d_vals). nbits = number of significant low bits of the keys.
+inline void radix_sort_pairs(SortWorkspace& ws, uint64_t* d_keys, uint32_t* d_vals, int64_t n, int nbits, cudaStream_t st) {
+    if (n <= 1 || nbits <= 0) return;
+    const int64_t ntiles = (n + RS_TILE - 1) / RS_TILE;
+    int32_t* counts = ws.counts.ensure((size_t)(ntiles * RS_RADIX));
+    uint64_t* ka = ws.keys_alt.ensure((size_t)n);
+    uint32_t* va = ws.vals_alt.ensure((size_t)n);
+    uint64_t* kin = d_keys;
+    uint32_t* vin = d_vals;
+    uint64_t* kout = ka;
+    uint32_t* vout = va;
+    const int npass = (nbits + 7) / 8;
+    for (int pass = 0; pass < npass; ++pass) {
+        const int shift = pass * 8;
+        DSA_LAUNCH("rs_histogram", k_rs_histogram, (unsigned)ntiles, RS_THREADS, 0, st, kin, n, shift, counts, ntiles);
+        exclusive_scan_i32<int32_t>(ws.scan, counts, counts, ntiles * RS_RADIX, nullptr, st);
+        DSA_LAUNCH("rs_scatter", k_rs_scatter, (unsigned)ntiles, RS_THREADS, 0, st, kin, vin, kout, vout, n, shift, counts, ntiles);
+        std::swap(kin, kout);
+        std::swap(vin, vout);
+    }
+    if (kin != d_keys) {
+        DSA_CUDA(cudaMemcpyAsync(d_keys, kin, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+        DSA_CUDA(cudaMemcpyAsync(d_vals, vin, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    }
+}
+
+}  // namespace dsa
