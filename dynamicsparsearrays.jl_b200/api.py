@@ -517,11 +517,7 @@ def closefillmode(matrix):   # closefillmode! (matrix.jl:126-134)
 
 def addrow(matrix, row, colids, vals):   # addrow! (matrix.jl:113-124)
     if matrix.fillmode:
-        colids, vals = _i64(colids), _f64(vals)
-        nz = vals != 0
-        if nz.any():
-            matrix._m = max(matrix._m, row)
-            matrix._n = max(matrix._n, int(colids[nz].max()))
+        # like the reference, addrow! in fill mode does not touch the dimensions (matrix.jl:116-117)
         matrix.buffer.addrow(row, colids, vals)
     else:
         for c, v in zip(colids, vals):
