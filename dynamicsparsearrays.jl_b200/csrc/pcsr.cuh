@@ -63,7 +63,24 @@ __global__ void __launch_bounds__(256) k_col_lookup(const int64_t* __restrict__ 
         a = __shfl_xor_sync(0xffffffffu, minp, o); minp = a < minp ? a : minp;
         miss += __shfl_xor_sync(0xffffffffu, miss, o);
     }
-    if ((threadIdx.x & 31) == 0) {
+    // block-level combine, then one set of atomics per CTA
+    __shared__ int64_t sh[5][8];
+    __shared__ int shm[8];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        sh[0][wid] = mink; sh[1][wid] = maxk; sh[2][wid] = maxp; sh[3][wid] = maxknz; sh[4][wid] = minp;
+        shm[wid] = miss;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) {
+            mink = sh[0][w] < mink ? sh[0][w] : mink;
+            maxk = sh[1][w] > maxk ? sh[1][w] : maxk;
+            maxp = sh[2][w] > maxp ? sh[2][w] : maxp;
+            maxknz = sh[3][w] > maxknz ? sh[3][w] : maxknz;
+            minp = sh[4][w] < minp ? sh[4][w] : minp;
+            miss += shm[w];
+        }
         if (miss) atomicAdd((unsigned long long*)&cs[CS_MISSING], (unsigned long long)miss);
         if (mink != INT64_MAX) atomicMin((long long*)&cs[CS_MINKEY], (long long)mink);
         if (maxk != INT64_MIN) atomicMax((long long*)&cs[CS_MAXKEY], (long long)maxk);

@@ -21,10 +21,13 @@ struct Levels {
     int64_t nsegs;
     int H;
     int lgS;
+    int hsmall;                // windows with h <= hsmall hold <= SMALL_CELLS cells: one CTA re-lays them in shared memory
+    uint32_t leafmask[33];     // leafmask[m] = cells a leaf of S cells occupies when spread! lays m elements over it
 };
+constexpr int SMALL_CELLS = 2048;
 
 enum : uint8_t { FL_OVERWRITE = 1, FL_DELETE = 2, FL_INSERT = 4 };
-enum { ST_OVER = 0, ST_UNDER = 1, ST_NINS = 2, ST_ROOT = 3, ST_MISSING = 4, ST_MINKEY = 5, ST_MAXKEY = 6, ST_ANYHIGH = 7, ST_WORDS = 16 };
+enum { ST_OVER = 0, ST_UNDER = 1, ST_NINS = 2, ST_ROOT = 3, ST_NHIGH = 4, ST_ANYBIG = 5, ST_ANYHIGH = 7, ST_WORDS = 16 };
 
 __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;
@@ -252,22 +255,72 @@ __global__ void __launch_bounds__(1024) k_tree_high(int32_t* __restrict__ post, 
     }
 }
 
-// every touched leaf walks leaf -> root and marks the first window inside its density bounds (pma.jl:113-129)
+// every touched leaf walks leaf -> root and marks the first window inside its density bounds (pma.jl:113-129).
+// Windows above leaf level are also appended (once) to a work list.
 __global__ void __launch_bounds__(256) k_select_windows(const uint8_t* __restrict__ touched, const int32_t* __restrict__ post,
-                                                         uint8_t* __restrict__ mark, Levels L, int64_t* __restrict__ status) {
+                                                         uint8_t* __restrict__ mark, Levels L, int64_t* __restrict__ status,
+                                                         int32_t* __restrict__ hi_h, int64_t* __restrict__ hi_w) {
     const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= L.nsegs || !touched[l]) return;
     for (int h = 0; h <= L.H; ++h) {
         const int64_t c = post[L.off[h] + (l >> h)];
         if (L.mn[h] <= c && c <= L.mx[h]) {
-            mark[L.off[h] + (l >> h)] = 1;
-            if (h > 0) status[ST_ANYHIGH] = 1;
+            const int64_t idx = L.off[h] + (l >> h);
+            if (h == 0) {
+                mark[idx] = 1;
+            } else {
+                unsigned* word = (unsigned*)(mark + (idx & ~(int64_t)3));
+                const unsigned bit = 1u << (8 * (unsigned)(idx & 3));
+                const unsigned old = atomicOr(word, bit);
+                if (!(old & bit)) {   // first marker of this window
+                    const unsigned long long slot = atomicAdd((unsigned long long*)&status[ST_NHIGH], 1ull);
+                    hi_h[slot] = h;
+                    hi_w[slot] = l >> h;
+                    status[ST_ANYHIGH] = 1;
+                    if (h > L.hsmall) status[ST_ANYBIG] = 1;
+                }
+            }
             return;
         }
     }
     const int64_t c = post[L.off[L.H]];
     if (c > L.mx[L.H]) status[ST_OVER] = 1;   // density > t  -> _extend!  (pma.jl:132-134)
     else status[ST_UNDER] = 1;                // density < p  -> _shrink!  (pma.jl:135-139)
+}
+
+// one CTA per listed window: outermost (no marked ancestor)?  then its leaves are covered by it
+__global__ void __launch_bounds__(128) k_cover_windows(const int32_t* __restrict__ hi_h, const int64_t* __restrict__ hi_w,
+                                                        const uint8_t* __restrict__ mark, Levels L, uint8_t* __restrict__ hi_max,
+                                                        uint8_t* __restrict__ cover) {
+    __shared__ int is_max;
+    const int64_t i = blockIdx.x;
+    const int h = hi_h[i];
+    const int64_t w = hi_w[i];
+    if (threadIdx.x == 0) {
+        int mx = 1;
+        for (int g = h + 1; g <= L.H; ++g)
+            if (mark[L.off[g] + (w >> (g - h))]) { mx = 0; break; }
+        is_max = mx;
+        hi_max[i] = (uint8_t)mx;
+    }
+    __syncthreads();
+    if (!is_max) return;
+    const int64_t first = w << h, n = (int64_t)1 << h;
+    for (int64_t j = threadIdx.x; j < n; j += blockDim.x) cover[first + j] = (uint8_t)(h + 1);
+}
+
+__device__ __forceinline__ int nth_set_bit(unsigned m, int n) {   // position of the n-th (0-based) set bit of m
+    int pos = 0;
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const unsigned low = (m >> pos) & ((1u << s) - 1u);
+        const int c = __popc(low);
+        if (n >= c) {
+            n -= c;
+            pos += s;
+        }
+    }
+    return pos;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -295,6 +348,11 @@ struct MergeArgs {
     int64_t* sem;   // nullable; 0-based positions per partition id
     int root_mode;
     int64_t root_c, root_m;
+    int min_h;                 // dense path: only windows with outermost height >= min_h (the big ones)
+    const uint8_t* cover;      // per leaf: 0 = not inside a window above leaf level
+    const int32_t* hi_h;       // work list of windows above leaf level
+    const int64_t* hi_w;
+    const uint8_t* hi_max;
 };
 
 __device__ __forceinline__ int window_height(const uint8_t* __restrict__ mark, const Levels& L, int64_t l, int lane) {
@@ -312,7 +370,7 @@ __global__ void __launch_bounds__(256) k_merge_scatter(MergeArgs A, Levels L) {
     if (A.root_mode) h = L.H;
     else {
         h = window_height(A.mark, L, l, lane);
-        if (h < 0) return;
+        if (h < A.min_h) return;
     }
     const int nins = A.inscnt[l];
     if (!A.root_mode && h == 0 && nins == 0) return;   // leaf accepted, nothing inserted: nothing moves (pma.jl:96-99)
@@ -382,16 +440,172 @@ __global__ void __launch_bounds__(256) k_merge_scatter(MergeArgs A, Levels L) {
     if (!A.root_mode && h == 0 && lane == 0) A.leafcnt[l] = (int32_t)m;
 }
 
+// ---------------------------------------------------------------------------------------------
+// K2 leaf merge (the common case: the leaf itself is the accepted window).  S lanes per leaf, 32/S leaves per warp,
+// dense over the leaves with a two-load early exit.  The merged run is re-laid in place from registers; destinations
+// come from the precomputed spread! occupancy mask of (S cells, m elements) — no floating point on this path.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_leaf_merge(MergeArgs A, Levels L) {
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int lgS = L.lgS, S = 1 << lgS;
+    const int grp = lane >> lgS, q = lane & (S - 1), gshift = grp << lgS;
+    const int64_t l = gw * (32 >> lgS) + grp;
+    const bool valid = l < L.nsegs;
+    const int nins = valid ? A.inscnt[l] : 0;
+    const bool active = valid && nins > 0 && A.cover[l] == 0;
+    if (!__any_sync(0xffffffffu, active)) return;
+    const int64_t p0 = l << lgS, p = p0 + q;
+    int64_t key = GAP_KEY;
+    double val = 0.0;
+    if (valid) {
+        key = A.src_k[p];
+        val = A.src_v[p];
+    }
+    const bool live = key != GAP_KEY;
+    const unsigned lm_all = __ballot_sync(0xffffffffu, live);
+    const unsigned gmask = S >= 32 ? 0xffffffffu : ((1u << S) - 1u);
+    const unsigned lm = (lm_all >> gshift) & gmask;
+    const int srank = __popc(lm & ((1u << q) - 1u));
+    // lane q of the group holds insert q of the leaf (an accepted leaf has at most S items)
+    const bool has_ins = active && q < nins;
+    int64_t ipos = INT64_MAX, ik = 0;
+    double iv = 0.0;
+    if (has_ins) {
+        const int64_t i0 = A.ins_first[l];
+        ipos = A.ins_pos[i0 + q];
+        ik = A.ins_key[i0 + q];
+        iv = A.ins_val[i0 + q];
+    }
+    const int maxn = __reduce_max_sync(0xffffffffu, active ? nins : 0);
+    int cntb = 0;   // inserts whose predecessor lies before this cell
+    for (int j = 0; j < maxn; ++j) {
+        const int64_t pj = __shfl_sync(0xffffffffu, ipos, gshift + (j & (S - 1)));
+        if (j < nins && pj < p) ++cntb;
+    }
+    const int m = __popc(lm) + nins;
+    const unsigned mask = L.leafmask[m];
+    __syncwarp();
+    if (active) {
+        if (!((mask >> q) & 1u)) {
+            A.cur_k[p] = GAP_KEY;
+            A.cur_v[p] = 0.0;
+        }
+        if (live) {
+            const int64_t d = p0 + nth_set_bit(mask, srank + cntb);
+            A.cur_k[d] = key;
+            A.cur_v[d] = val;
+            if (A.sem && key == 0) A.sem[(int64_t)val - 1] = d;   // moves.jl:160-166
+        }
+        if (has_ins) {
+            const int qq = (int)(ipos - p0);   // -1 .. S-1
+            const int surv_le = qq < 0 ? 0 : __popc(lm & (qq >= 31 ? 0xffffffffu : ((2u << qq) - 1u)));
+            const int64_t d = p0 + nth_set_bit(mask, surv_le + q);
+            A.cur_k[d] = ik;
+            A.cur_v[d] = iv;
+            if (A.sem && ik == 0) A.sem[(int64_t)iv - 1] = d;
+        }
+        if (q == 0) A.leafcnt[l] = m;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4 small windows (height >= 1, <= SMALL_CELLS cells): one CTA per listed outermost window.  The merged, ranked items
+// are scattered to their spread! offsets in shared memory, then the window is written back coalesced (pack! + spread!,
+// moves.jl:94-172, in one pass), with leaf counts and semaphore positions.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_window_small(MergeArgs A, Levels L) {
+    __shared__ int64_t sk[SMALL_CELLS];
+    __shared__ double sv[SMALL_CELLS];
+    const int64_t i = blockIdx.x;
+    if (!A.hi_max[i]) return;
+    const int h = A.hi_h[i];
+    if (h > L.hsmall) return;
+    const int64_t w = A.hi_w[i];
+    const int lgS = L.lgS, S = 1 << lgS;
+    const int c = S << h;
+    const int64_t m = A.post[L.off[h] + w];
+    const int64_t first_leaf = w << h;
+    const int64_t ws_cell = first_leaf << lgS;
+    for (int t = threadIdx.x; t < c; t += blockDim.x) {
+        sk[t] = GAP_KEY;
+        sv[t] = 0.0;
+    }
+    __syncthreads();
+    const Spread sp = spread_make(c, m);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int64_t j = wid; j < ((int64_t)1 << h); j += nw) {
+        const int64_t l = first_leaf + j;
+        int64_t term = 0;
+        if (lane < h && ((l >> lane) & 1)) term = A.post[L.off[lane] + ((l >> lane) - 1)];
+        const int64_t base = warp_sum_i64(term);
+        const int nins = A.inscnt[l];
+        const int64_t i0 = nins ? A.ins_first[l] : 0;
+        const int64_t p0 = l << lgS, p = p0 + lane;
+        int64_t key = GAP_KEY;
+        double val = 0.0;
+        if (lane < S) {
+            key = A.src_k[p];
+            val = A.src_v[p];
+        }
+        const bool live = key != GAP_KEY;
+        const unsigned lm = __ballot_sync(0xffffffffu, live);
+        const int srank = __popc(lm & lanemask_lt());
+        int cntb = 0;
+        if (live && nins) {
+            int lo = 0, hi = nins;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (A.ins_pos[i0 + mid] < p) lo = mid + 1;
+                else hi = mid;
+            }
+            cntb = lo;
+        }
+        if (live) {
+            const int64_t d = spread_dest(sp, base + srank + cntb);
+            sk[d] = key;
+            sv[d] = val;
+        }
+        for (int jj = lane; jj < nins; jj += 32) {
+            const int64_t ipos = A.ins_pos[i0 + jj];
+            const int qq = (int)(ipos - p0);
+            const int surv_le = qq < 0 ? 0 : __popc(lm & (qq >= 31 ? 0xffffffffu : ((2u << qq) - 1u)));
+            const int64_t d = spread_dest(sp, base + surv_le + jj);
+            sk[d] = A.ins_key[i0 + jj];
+            sv[d] = A.ins_val[i0 + jj];
+        }
+    }
+    __syncthreads();
+    for (int t0 = 0; t0 < c; t0 += blockDim.x) {
+        const int t = t0 + threadIdx.x;
+        const bool in = t < c;
+        int64_t k = GAP_KEY;
+        if (in) {
+            k = sk[t];
+            const double v = sv[t];
+            const int64_t p = ws_cell + t;
+            A.cur_k[p] = k;
+            A.cur_v[p] = v;
+            if (A.sem && k == 0) A.sem[(int64_t)v - 1] = p;
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, in && k != GAP_KEY);
+        if (in && (t & (S - 1)) == 0) {
+            const unsigned mm = S >= 32 ? 0xffffffffu : ((1u << S) - 1u);
+            A.leafcnt[(ws_cell + t) >> lgS] = __popc((b >> lane) & mm);
+        }
+    }
+}
+
 // windows of height >= 1: copy the shadow back, writing the analytic gaps and the new leaf counts
 __global__ void __launch_bounds__(256) k_copyback(int64_t* __restrict__ keys, double* __restrict__ vals,
                                                    const int64_t* __restrict__ scr_k, const double* __restrict__ scr_v,
                                                    const int32_t* __restrict__ post, const uint8_t* __restrict__ mark,
-                                                   int32_t* __restrict__ leafcnt, Levels L) {
+                                                   int32_t* __restrict__ leafcnt, Levels L, int min_h) {
     const int64_t l = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (l >= L.nsegs) return;
     const int h = window_height(mark, L, l, lane);
-    if (h < 1) return;
+    if (h < 1 || h < min_h) return;
     const int S = 1 << L.lgS;
     const int64_t first_leaf = (l >> h) << h;
     const Spread sp = spread_make((int64_t)S << h, (int64_t)post[L.off[h] + (l >> h)]);
@@ -464,7 +678,9 @@ struct BatchWorkspace {   // per-handle scratch reused by every batch
     DBuf<int64_t> ins_key, ins_pos;
     DBuf<double> ins_val;
     DBuf<int32_t> inscnt, ins_first, post;
-    DBuf<uint8_t> touched, mark;
+    DBuf<uint8_t> touched, mark, cover, hi_max;
+    DBuf<int32_t> hi_h;
+    DBuf<int64_t> hi_w;
     DBuf<int64_t> shadow_k;
     DBuf<double> shadow_v;
     DBuf<int64_t> status;
@@ -491,6 +707,15 @@ struct PmaCore {
             o += g.nb_segments >> h;
         }
         level_bounds(g.segment_capacity, g.height, g.t_d, g.p_d, L.mn, L.mx);
+        const int S = (int)g.segment_capacity;
+        L.hsmall = 0;
+        while (L.hsmall < L.H && ((int64_t)S << (L.hsmall + 1)) <= SMALL_CELLS) ++L.hsmall;
+        for (int m = 0; m <= S; ++m) {
+            const Spread sp = spread_make(S, m);
+            uint32_t mask = 0;
+            for (int r = 0; r < m; ++r) mask |= 1u << (unsigned)spread_dest(sp, r);
+            L.leafmask[m] = mask;
+        }
         return L;
     }
     int64_t tree_size() const { return 2 * g.nb_segments + 8; }
@@ -524,10 +749,15 @@ struct PmaCore {
         int32_t* post = ws.post.ensure((size_t)tree_size());
         uint8_t* mark = ws.mark.ensure((size_t)tree_size());
         int64_t* status = ws.status.ensure(ST_WORDS);
+        uint8_t* cover = ws.cover.ensure((size_t)nsegs);
+        int32_t* hi_h = ws.hi_h.ensure((size_t)nsegs + 1);
+        int64_t* hi_w = ws.hi_w.ensure((size_t)nsegs + 1);
+        uint8_t* hi_max = ws.hi_max.ensure((size_t)nsegs + 1);
         DSA_CUDA(cudaMemsetAsync(mark, 0, (size_t)tree_size(), st));
+        DSA_CUDA(cudaMemsetAsync(cover, 0, (size_t)nsegs, st));
         DSA_LAUNCH("tree_low", k_tree_low, grid_for(nsegs, 1024), 1024, 0, st, leafcnt.p, ws.inscnt.p, post, L);
         if (L.H > 10) DSA_LAUNCH("tree_high", k_tree_high, 1, 1024, 0, st, post, L);
-        DSA_LAUNCH("select_windows", k_select_windows, grid_for(nsegs, 256), 256, 0, st, ws.touched.p, post, mark, L, status);
+        DSA_LAUNCH("select_windows", k_select_windows, grid_for(nsegs, 256), 256, 0, st, ws.touched.p, post, mark, L, status, hi_h, hi_w);
         // status[ST_ROOT] <- root count
         DSA_CUDA(cudaMemcpyAsync(status + ST_ROOT, post + L.off[L.H], sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
         int64_t* hs = ws.h_status.ensure(ST_WORDS);
@@ -540,6 +770,7 @@ struct PmaCore {
         A.post = post; A.mark = mark; A.inscnt = ws.inscnt.p; A.ins_first = ws.ins_first.p;
         A.ins_key = ws.ins_key.p; A.ins_val = ws.ins_val.p; A.ins_pos = ws.ins_pos.p;
         A.leafcnt = leafcnt.p; A.sem = d_sem;
+        A.cover = cover; A.hi_h = hi_h; A.hi_w = hi_w; A.hi_max = hi_max;
         const unsigned warp_grid = grid_for(nsegs * 32, 256);
         if (hs[ST_OVER] || hs[ST_UNDER]) {
             // root failed: _extend!/_shrink! (pma.jl:132-139) until the root accepts, then one full spread into the new array
@@ -558,14 +789,23 @@ struct PmaCore {
             keys.swap(nk);
             vals.swap(nv);
         } else {
-            const bool any_high = hs[ST_ANYHIGH] != 0;   // some window above leaf level: needs the shadow array
-            if (any_high) {
+            const int64_t nhigh = hs[ST_NHIGH];
+            if (nhigh > 0)
+                DSA_LAUNCH("cover_windows", k_cover_windows, (unsigned)nhigh, 128, 0, st, hi_h, hi_w, mark, L, hi_max, cover);
+            // leaves accepted at their own level (the common case), in place
+            const int leaves_per_warp = 32 >> L.lgS;
+            DSA_LAUNCH("leaf_merge", k_leaf_merge, grid_for(((nsegs + leaves_per_warp - 1) / leaves_per_warp) * 32, 256), 256, 0, st, A, L);
+            // outermost windows of <= SMALL_CELLS cells: one CTA each, through shared memory
+            if (nhigh > 0) DSA_LAUNCH("window_small", k_window_small, (unsigned)nhigh, 256, 0, st, A, L);
+            // bigger windows (rare: cascades): dense warp-per-leaf scatter into the shadow array + copy back
+            if (hs[ST_ANYBIG]) {
                 A.dst_k = ws.shadow_k.ensure((size_t)g.capacity);
                 A.dst_v = ws.shadow_v.ensure((size_t)g.capacity);
+                A.min_h = L.hsmall + 1;
+                DSA_LAUNCH("merge_scatter_big", k_merge_scatter, warp_grid, 256, 0, st, A, L);
+                DSA_LAUNCH("copyback_big", k_copyback, warp_grid, 256, 0, st, keys.p, vals.p, A.dst_k, A.dst_v, post, mark, leafcnt.p, L,
+                           L.hsmall + 1);
             }
-            DSA_LAUNCH("merge_scatter", k_merge_scatter, warp_grid, 256, 0, st, A, L);
-            if (any_high)
-                DSA_LAUNCH("copyback", k_copyback, warp_grid, 256, 0, st, keys.p, vals.p, A.dst_k, A.dst_v, post, mark, leafcnt.p, L);
         }
         nnz = N;
         (void)nins;
