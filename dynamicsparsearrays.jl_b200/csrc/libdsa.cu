@@ -27,7 +27,7 @@ static BatchStats lookup_and_stats(Pcsr& P, PcsrWorkspace& ws, const int64_t* d_
     int64_t* hcs = ws.h_cs.ensure(CS_WORDS);
     DSA_LAUNCH("colstat_init", k_colstat_init, 1, 1, 0, st, cs);
     DSA_LAUNCH("col_lookup", k_col_lookup, grid_for(n, 256), 256, 0, st, d_partkeys, d_inkeys, d_vals, n, P.d_live_keys.p, P.d_live_slot.p,
-               P.nlive(), op_slot, cs);
+               P.nlive(), P.keymap(), P.keymap_min, P.keymap_len, op_slot, cs);
     DSA_CUDA(cudaMemcpyAsync(hcs, cs, CS_WORDS * 8, cudaMemcpyDeviceToHost, st));
     DSA_CUDA(cudaStreamSynchronize(st));
     return BatchStats{hcs[CS_MISSING], hcs[CS_MINKEY], hcs[CS_MAXKEY], hcs[CS_MAXPART_NZ], hcs[CS_MAXKEY_NZ], hcs[CS_MINPART]};
@@ -90,7 +90,7 @@ void Pcsr::set_batch_d(PcsrWorkspace& ws, const int64_t* d_inkeys, const int64_t
         int64_t* cs = ws.cs.ensure(CS_WORDS);
         DSA_LAUNCH("colstat_init", k_colstat_init, 1, 1, 0, st, cs);
         DSA_LAUNCH("col_lookup", k_col_lookup, gr, 256, 0, st, d_partkeys, (const int64_t*)nullptr, (const double*)nullptr, n, d_live_keys.p,
-                   d_live_slot.p, nlive(), ws.op_slot.p, cs);
+                   d_live_slot.p, nlive(), keymap(), keymap_min, keymap_len, ws.op_slot.p, cs);
     }
     ensure_next(ws, st);
     const int64_t nnew = (int64_t)new_slots_h.size();

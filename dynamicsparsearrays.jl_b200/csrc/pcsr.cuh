@@ -38,14 +38,21 @@ __device__ __forceinline__ int32_t live_lookup(const int64_t* __restrict__ live_
 __global__ void __launch_bounds__(256) k_col_lookup(const int64_t* __restrict__ partkeys, const int64_t* __restrict__ inkeys,
                                                      const double* __restrict__ vals, int64_t n,
                                                      const int64_t* __restrict__ live_keys, const int32_t* __restrict__ live_slot,
-                                                     int64_t nlive, int32_t* __restrict__ op_slot, int64_t* __restrict__ cs) {
+                                                     int64_t nlive, const int32_t* __restrict__ keymap, int64_t keymap_min,
+                                                     int64_t keymap_len, int32_t* __restrict__ op_slot, int64_t* __restrict__ cs) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t mink = INT64_MAX, maxk = INT64_MIN, maxp = INT64_MIN, maxknz = INT64_MIN, minp = INT64_MAX;
     int miss = 0;
     if (i < n) {
         const int64_t pk = partkeys[i];
         minp = pk;
-        const int32_t s = live_lookup(live_keys, live_slot, nlive, pk);
+        int32_t s;
+        if (keymap) {   // dense key range: direct-address table (one load instead of a binary search)
+            const int64_t r = pk - keymap_min;
+            s = (r >= 0 && r < keymap_len) ? keymap[r] : -1;
+        } else {
+            s = live_lookup(live_keys, live_slot, nlive, pk);
+        }
         op_slot[i] = s;
         miss = s < 0;
         if (inkeys) {
@@ -474,9 +481,13 @@ struct Pcsr {
     DBuf<int64_t> d_slot_key;
     DBuf<int64_t> d_live_keys;
     DBuf<int32_t> d_live_slot;
+    DBuf<int32_t> d_keymap;     // optional direct-address table key - keymap_min -> slot (dense key ranges only)
+    std::vector<int32_t> keymap_h;
+    int64_t keymap_min = 0, keymap_len = 0;
     bool next_dirty = true;
     int64_t max_inkey = 0;      // upper bound of the in-array keys ever stored (sizes the dense x of SpMV)
 
+    const int32_t* keymap() const { return keymap_len > 0 ? d_keymap.p : nullptr; }
     int64_t nslots() const { return (int64_t)slot_key.size(); }
     int64_t nlive() const { return (int64_t)live_keys_h.size(); }
     int64_t nnz() const { return pma.nnz - nb_partitions; }   // pcsr.jl:11
@@ -491,9 +502,19 @@ struct Pcsr {
         d_live_keys.ensure(nl + 1);
         d_live_slot.ensure(nl + 1);
         if (ns) DSA_CUDA(cudaMemcpyAsync(d_slot_key.p, slot_key.data(), ns * 8, cudaMemcpyHostToDevice, st));
+        keymap_len = 0;
         if (nl) {
             DSA_CUDA(cudaMemcpyAsync(d_live_keys.p, live_keys_h.data(), nl * 8, cudaMemcpyHostToDevice, st));
             DSA_CUDA(cudaMemcpyAsync(d_live_slot.p, live_slot_h.data(), nl * 4, cudaMemcpyHostToDevice, st));
+            const uint64_t range = (uint64_t)live_keys_h.back() - (uint64_t)live_keys_h.front() + 1;
+            if (range <= std::max<uint64_t>(8 * (uint64_t)nl, 1u << 16) && range <= (1u << 27)) {
+                keymap_min = live_keys_h.front();
+                keymap_len = (int64_t)range;
+                keymap_h.assign((size_t)range, -1);
+                for (size_t i = 0; i < nl; ++i) keymap_h[(size_t)(live_keys_h[i] - keymap_min)] = live_slot_h[i];
+                d_keymap.ensure((size_t)range);
+                DSA_CUDA(cudaMemcpyAsync(d_keymap.p, keymap_h.data(), (size_t)range * 4, cudaMemcpyHostToDevice, st));
+            }
         }
         DSA_CUDA(cudaStreamSynchronize(st));   // host vectors may be modified after return
     }
@@ -550,7 +571,7 @@ struct Pcsr {
         int64_t* cs = ws.cs.ensure(CS_WORDS);
         DSA_LAUNCH("colstat_init", k_colstat_init, 1, 1, 0, st, cs);
         DSA_LAUNCH("col_lookup", k_col_lookup, grid_for(n, 256), 256, 0, st, d_partkeys, (const int64_t*)nullptr, (const double*)nullptr, n,
-                   d_live_keys.p, d_live_slot.p, nlive(), op_slot, cs);
+                   d_live_keys.p, d_live_slot.p, nlive(), keymap(), keymap_min, keymap_len, op_slot, cs);
         DSA_LAUNCH("get", k_get, grid_for(n, 256), 256, 0, st, pma.keys.p, pma.vals.p, pma.g.capacity, op_slot, d_inkeys, n, d_sem.p,
                    d_next.p, d_out);
     }

@@ -452,15 +452,24 @@ __global__ void __launch_bounds__(256) k_leaf_merge(MergeArgs A, Levels L) {
     const int grp = lane >> lgS, q = lane & (S - 1), gshift = grp << lgS;
     const int64_t l = gw * (32 >> lgS) + grp;
     const bool valid = l < L.nsegs;
-    const int nins = valid ? A.inscnt[l] : 0;
-    const bool active = valid && nins > 0 && A.cover[l] == 0;
+    // round 1: two independent loads decide whether the leaf is merged here
+    int nins = 0;
+    uint8_t cov = 1;
+    if (valid) {
+        nins = A.inscnt[l];
+        cov = A.cover[l];
+    }
+    const bool active = valid && nins > 0 && cov == 0;
     if (!__any_sync(0xffffffffu, active)) return;
+    // round 2: the leaf's cells and the index of its first insert, issued together
     const int64_t p0 = l << lgS, p = p0 + q;
     int64_t key = GAP_KEY;
     double val = 0.0;
-    if (valid) {
+    int64_t i0 = 0;
+    if (active) {
         key = A.src_k[p];
         val = A.src_v[p];
+        i0 = A.ins_first[l];
     }
     const bool live = key != GAP_KEY;
     const unsigned lm_all = __ballot_sync(0xffffffffu, live);
@@ -471,8 +480,7 @@ __global__ void __launch_bounds__(256) k_leaf_merge(MergeArgs A, Levels L) {
     const bool has_ins = active && q < nins;
     int64_t ipos = INT64_MAX, ik = 0;
     double iv = 0.0;
-    if (has_ins) {
-        const int64_t i0 = A.ins_first[l];
+    if (has_ins) {   // round 3
         ipos = A.ins_pos[i0 + q];
         ik = A.ins_key[i0 + q];
         iv = A.ins_val[i0 + q];

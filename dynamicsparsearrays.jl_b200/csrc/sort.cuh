@@ -88,16 +88,164 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __res
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Single-sweep variant (used for n < 2^30): the digit histograms of ALL passes are computed by one read of the keys;
+// each pass is then ONE kernel in which a tile publishes its digit counts and resolves its global offsets by decoupled
+// look-back over the preceding tiles (tiles take their index from an atomic ticket, so a tile only ever waits on tiles
+// that are already running).  6 launches for a 34-bit key instead of 25.
+// ---------------------------------------------------------------------------------------------
+constexpr int OS_THREADS = 256;
+constexpr int OS_ROUNDS = 8;                         // keys per thread
+constexpr int OS_TILE = OS_THREADS * OS_ROUNDS;      // 2048 keys per tile
+constexpr int OS_WARPS = OS_THREADS / 32;
+constexpr int OS_MAX_PASS = 8;
+constexpr uint32_t OS_FLAG_LOCAL = 1u << 30, OS_FLAG_INCL = 2u << 30, OS_VALUE_MASK = (1u << 30) - 1u;
+
+// ghist[pass * 256 + digit] += count
+__global__ void __launch_bounds__(256) k_os_histogram(const uint64_t* __restrict__ keys, int64_t n, int npass, uint32_t* __restrict__ ghist) {
+    __shared__ uint32_t h[OS_MAX_PASS * RS_RADIX];
+    for (int i = threadIdx.x; i < npass * RS_RADIX; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = keys[i];
+        for (int p = 0; p < npass; ++p) atomicAdd(&h[p * RS_RADIX + (unsigned)((k >> (8 * p)) & 0xff)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < npass * RS_RADIX; i += blockDim.x)
+        if (h[i]) atomicAdd(&ghist[i], h[i]);
+}
+// exclusive scan of each pass's 256 bins, in place (one block of 256 threads)
+__global__ void __launch_bounds__(256) k_os_scan_hist(uint32_t* __restrict__ ghist, int npass) {
+    __shared__ uint32_t s[RS_RADIX];
+    for (int p = 0; p < npass; ++p) {
+        const uint32_t v = ghist[p * RS_RADIX + threadIdx.x];
+        s[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < RS_RADIX; o <<= 1) {
+            uint32_t t = threadIdx.x >= (unsigned)o ? s[threadIdx.x - o] : 0;
+            __syncthreads();
+            s[threadIdx.x] += t;
+            __syncthreads();
+        }
+        ghist[p * RS_RADIX + threadIdx.x] = s[threadIdx.x] - v;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(OS_THREADS) k_os_pass(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                                         uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n,
+                                                         int shift, const uint32_t* __restrict__ gbase, volatile uint32_t* status,
+                                                         unsigned* __restrict__ ticket) {
+    __shared__ int32_t wcnt[OS_WARPS][RS_RADIX];
+    __shared__ uint32_t dbase[RS_RADIX];
+    __shared__ unsigned tile_s;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) tile_s = atomicAdd(ticket, 1u);
+    for (int d = threadIdx.x; d < OS_WARPS * RS_RADIX; d += OS_THREADS) (&wcnt[0][0])[d] = 0;
+    __syncthreads();
+    const unsigned tile = tile_s;
+    const int64_t wbase = (int64_t)tile * OS_TILE + (int64_t)wid * (OS_ROUNDS * 32);
+    uint64_t k[OS_ROUNDS];
+    int32_t rank[OS_ROUNDS];
+#pragma unroll
+    for (int r = 0; r < OS_ROUNDS; ++r) {
+        const int64_t idx = wbase + r * 32 + lane;
+        k[r] = idx < n ? keys_in[idx] : ~uint64_t(0);
+    }
+#pragma unroll
+    for (int r = 0; r < OS_ROUNDS; ++r) {
+        const int64_t idx = wbase + r * 32 + lane;
+        const bool valid = idx < n;
+        const unsigned d = (unsigned)((k[r] >> shift) & 0xff);
+        const unsigned peers = __match_any_sync(0xffffffffu, valid ? d : 0x100u);
+        const int before = __popc(peers & ((1u << lane) - 1u));
+        int32_t basecnt = 0;
+        if (valid) basecnt = wcnt[wid][d];
+        __syncwarp();
+        if (valid && before == 0) wcnt[wid][d] = basecnt + __popc(peers);
+        __syncwarp();
+        rank[r] = basecnt + before;
+    }
+    __syncthreads();
+    {   // thread d owns digit d: tile count, per-warp exclusive offsets, publish, look back
+        const int d = threadIdx.x;
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < OS_WARPS; ++w) {
+            const int32_t c = wcnt[w][d];
+            wcnt[w][d] = (int32_t)run;
+            run += (uint32_t)c;
+        }
+        volatile uint32_t* mine = status + (size_t)tile * RS_RADIX + d;
+        uint32_t excl = 0;
+        if (tile == 0) {
+            *mine = OS_FLAG_INCL | run;
+        } else {
+            *mine = OS_FLAG_LOCAL | run;
+            int64_t t = (int64_t)tile - 1;
+            while (true) {
+                uint32_t sv;
+                do { sv = status[(size_t)t * RS_RADIX + d]; } while ((sv >> 30) == 0);
+                excl += sv & OS_VALUE_MASK;
+                if ((sv >> 30) == 2u) break;
+                --t;
+            }
+            *mine = OS_FLAG_INCL | (excl + run);
+        }
+        dbase[d] = gbase[d] + excl;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < OS_ROUNDS; ++r) {
+        const int64_t idx = wbase + r * 32 + lane;
+        if (idx < n) {
+            const unsigned d = (unsigned)((k[r] >> shift) & 0xff);
+            const int64_t dst = (int64_t)dbase[d] + wcnt[wid][d] + rank[r];
+            keys_out[dst] = k[r];
+            vals_out[dst] = vals_in[idx];
+        }
+    }
+}
+
 struct SortWorkspace {
     DBuf<int32_t> counts;
     DBuf<uint64_t> keys_alt;
     DBuf<uint32_t> vals_alt;
+    DBuf<uint32_t> os_state;   // [ghist: npass*256][tickets: npass][status: npass*ntiles*256]
     ScanWorkspace scan;
 };
 
 // Sorts in place (result ends in d_keys / d_vals). nbits = number of significant low bits of the keys.
 inline void radix_sort_pairs(SortWorkspace& ws, uint64_t* d_keys, uint32_t* d_vals, int64_t n, int nbits, cudaStream_t st) {
     if (n <= 1 || nbits <= 0) return;
+    if (n < (int64_t(1) << 30) && (nbits + 7) / 8 <= OS_MAX_PASS) {
+        const int npass = (nbits + 7) / 8;
+        const int64_t ntiles = (n + OS_TILE - 1) / OS_TILE;
+        const size_t nstate = (size_t)npass * RS_RADIX + 64 + (size_t)npass * ntiles * RS_RADIX;
+        uint32_t* state = ws.os_state.ensure(nstate);
+        DSA_CUDA(cudaMemsetAsync(state, 0, nstate * sizeof(uint32_t), st));
+        uint32_t* ghist = state;
+        unsigned* tickets = state + (size_t)npass * RS_RADIX;
+        uint32_t* status = state + (size_t)npass * RS_RADIX + 64;
+        uint64_t* ka = ws.keys_alt.ensure((size_t)n);
+        uint32_t* va = ws.vals_alt.ensure((size_t)n);
+        const unsigned hgrid = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 4);
+        DSA_LAUNCH("os_histogram", k_os_histogram, hgrid, 256, 0, st, d_keys, n, npass, ghist);
+        DSA_LAUNCH("os_scan_hist", k_os_scan_hist, 1, 256, 0, st, ghist, npass);
+        uint64_t *kin = d_keys, *kout = ka;
+        uint32_t *vin = d_vals, *vout = va;
+        for (int pass = 0; pass < npass; ++pass) {
+            DSA_LAUNCH("os_pass", k_os_pass, (unsigned)ntiles, OS_THREADS, 0, st, kin, vin, kout, vout, n, pass * 8, ghist + pass * RS_RADIX,
+                       status + (size_t)pass * ntiles * RS_RADIX, tickets + pass);
+            std::swap(kin, kout);
+            std::swap(vin, vout);
+        }
+        if (kin != d_keys) {
+            DSA_CUDA(cudaMemcpyAsync(d_keys, kin, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+            DSA_CUDA(cudaMemcpyAsync(d_vals, vin, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        }
+        return;
+    }
     const int64_t ntiles = (n + RS_TILE - 1) / RS_TILE;
     int32_t* counts = ws.counts.ensure((size_t)(ntiles * RS_RADIX));
     uint64_t* ka = ws.keys_alt.ensure((size_t)n);
