@@ -84,15 +84,13 @@ void Pcsr::set_batch_d(PcsrWorkspace& ws, const int64_t* d_inkeys, const int64_t
         slot_key.swap(out_key);
         slot_live.swap(out_live);
         nb_partitions += (int64_t)distinct.size();
-        rebuild_live_and_upload(st);
-        next_dirty = true;
+        rebuild_live_and_upload(st, &new_slots_h);
         // slots changed: look every op up again
         int64_t* cs = ws.cs.ensure(CS_WORDS);
         DSA_LAUNCH("colstat_init", k_colstat_init, 1, 1, 0, st, cs);
         DSA_LAUNCH("col_lookup", k_col_lookup, gr, 256, 0, st, d_partkeys, (const int64_t*)nullptr, (const double*)nullptr, n, d_live_keys.p,
                    d_live_slot.p, nlive(), keymap(), keymap_min, keymap_len, ws.op_slot.p, cs);
     }
-    ensure_next(ws, st);
     const int64_t nnew = (int64_t)new_slots_h.size();
     const int64_t ntot = n + nnew;
     int32_t* d_new = ws.new_slots.ensure((size_t)nnew + 1);
@@ -116,9 +114,9 @@ void Pcsr::set_batch_d(PcsrWorkspace& ws, const int64_t* d_inkeys, const int64_t
     DSA_LAUNCH("gather_unique_ops", k_gather_unique_ops, grt, 256, 0, st, sk, perm, flag, uidx, ntot, n, kb, d_inkeys, d_vals, u_pid, u_key,
                u_val);
     if (nnew) DSA_CUDA(cudaStreamSynchronize(st));   // new_slots_h is read by the async copy above
-    pma.apply_sorted_ops(ws.batch, u_pid, u_key, u_val, ntot, d_sem.p, d_next.p, st, false, nuniq_dev);
+    pma.apply_sorted_ops(ws.batch, u_pid, u_key, u_val, ntot, d_sem.p, d_next_slot.p, st, false, nuniq_dev);
     if (bs.maxkey > max_inkey) max_inkey = bs.maxkey;
-    next_dirty = true;
+    if (nnew) rebuild_live_and_upload(st);   // the new partitions are placed now: they end the spans before them
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -488,7 +486,7 @@ int dsa_vec_get_batch(dsa_vec_t* v, const int64_t* keys, int64_t n, double* out)
     int64_t* dk = h2d(v->stg.a, keys, n, st);
     double* dout = v->stg.out.ensure((size_t)n);
     DSA_LAUNCH("get", k_get, grid_for(n, 256), 256, 0, st, v->pma.keys.p, v->pma.vals.p, v->pma.g.capacity, (const int32_t*)nullptr, dk, n,
-               (const int64_t*)nullptr, (const int64_t*)nullptr, dout);
+               (const int64_t*)nullptr, (const int32_t*)nullptr, dout);
     DSA_CUDA(cudaMemcpyAsync(out, dout, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     DSA_CUDA(cudaStreamSynchronize(st));
     return DSA_OK;

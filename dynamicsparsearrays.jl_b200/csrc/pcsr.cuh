@@ -123,25 +123,6 @@ __global__ void __launch_bounds__(256) k_fill_i64(int64_t* a, int64_t n, int64_t
     if (i < n) a[i] = v;
 }
 
-// next_sem[s] = position of the first placed semaphore with slot > s, or capacity (pcsr.jl:177-186 _pos_of_partition_end + 1)
-__global__ void __launch_bounds__(256) k_flag_placed(const int64_t* __restrict__ sem, int64_t n, int32_t* __restrict__ flag) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) flag[i] = sem[i] >= 0 ? 1 : 0;
-}
-__global__ void __launch_bounds__(256) k_live_positions(const int64_t* __restrict__ sem, const int32_t* __restrict__ rank, int64_t n,
-                                                         int64_t* __restrict__ live_pos) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && sem[i] >= 0) live_pos[rank[i]] = sem[i];
-}
-__global__ void __launch_bounds__(256) k_next_sem(const int64_t* __restrict__ sem, const int32_t* __restrict__ rank, int64_t n,
-                                                   const int64_t* __restrict__ live_pos, const int64_t* __restrict__ nplaced_dev,
-                                                   int64_t cap, int64_t* __restrict__ next_sem) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int64_t idx = (int64_t)rank[i] + (sem[i] >= 0 ? 1 : 0);
-    next_sem[i] = idx < *nplaced_dev ? live_pos[idx] : cap;
-}
-
 // ---------------------------------------------------------------------------------------------
 // batch assembly: ops + one semaphore insert per new partition; 64-bit sort key = (slot << kb) | in-array key
 // ---------------------------------------------------------------------------------------------
@@ -222,13 +203,13 @@ __global__ void __launch_bounds__(256) k_flag_part_first(const uint64_t* __restr
 // ---------------------------------------------------------------------------------------------
 // count the stored cells of (sem, next_sem) per listed slot — one warp per slot
 __global__ void __launch_bounds__(256) k_span_count(const int64_t* __restrict__ keys, const int32_t* __restrict__ slots, int64_t nslots,
-                                                     const int64_t* __restrict__ sem, const int64_t* __restrict__ next_sem,
+                                                     const int64_t* __restrict__ sem, const int32_t* __restrict__ next_slot, int64_t cap,
                                                      int32_t* __restrict__ counts) {
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= nslots) return;
     const int32_t s = slots[w];
-    const int64_t from = sem[s] + 1, to = next_sem[s];
+    const int64_t from = sem[s] + 1, to = span_end(sem, next_slot, s, cap);
     int c = 0;
     for (int64_t p = from + lane; p < to; p += 32) c += keys[p] != GAP_KEY;
 #pragma unroll
@@ -238,14 +219,14 @@ __global__ void __launch_bounds__(256) k_span_count(const int64_t* __restrict__ 
 // emit the stored cells of the span in order (views.jl:15-35 / pcsr.jl:248-258): (key, val) and the owning list index
 __global__ void __launch_bounds__(256) k_span_emit(const int64_t* __restrict__ keys, const double* __restrict__ vals,
                                                     const int32_t* __restrict__ slots, int64_t nslots, const int64_t* __restrict__ sem,
-                                                    const int64_t* __restrict__ next_sem, const int32_t* __restrict__ offsets,
+                                                    const int32_t* __restrict__ next_slot, int64_t cap, const int32_t* __restrict__ offsets,
                                                     int64_t* __restrict__ out_key, double* __restrict__ out_val,
                                                     int64_t* __restrict__ out_owner, const int64_t* __restrict__ owner_keys) {
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= nslots) return;
     const int32_t s = slots[w];
-    const int64_t from = sem[s] + 1, to = next_sem[s];
+    const int64_t from = sem[s] + 1, to = span_end(sem, next_slot, s, cap);
     int64_t o = offsets[w];
     for (int64_t base = from; base < to; base += 32) {
         const int64_t p = base + lane;
@@ -262,13 +243,13 @@ __global__ void __launch_bounds__(256) k_span_emit(const int64_t* __restrict__ k
 }
 // purge! (writes.jl:80-92) of [sem, next_sem) for every listed slot + leaf bookkeeping
 __global__ void __launch_bounds__(256) k_span_purge(int64_t* __restrict__ keys, double* __restrict__ vals, const int32_t* __restrict__ slots,
-                                                     int64_t nslots, const int64_t* __restrict__ sem, const int64_t* __restrict__ next_sem,
+                                                     int64_t nslots, const int64_t* __restrict__ sem, const int32_t* __restrict__ next_slot, int64_t cap,
                                                      int32_t* __restrict__ leafcnt, uint8_t* __restrict__ touched, int lgS) {
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= nslots) return;
     const int32_t s = slots[w];
-    const int64_t from = sem[s], to = next_sem[s];
+    const int64_t from = sem[s], to = span_end(sem, next_slot, s, cap);
     for (int64_t p = from + lane; p < to; p += 32) {
         if (keys[p] != GAP_KEY) {
             keys[p] = GAP_KEY;
@@ -477,14 +458,14 @@ struct Pcsr {
     std::vector<int64_t> live_keys_h;   // sorted live keys
     std::vector<int32_t> live_slot_h;
     DBuf<int64_t> d_sem;        // per slot: 0-based position of the semaphore cell, -1 = deleted / not yet placed (pcsr.jl:6)
-    DBuf<int64_t> d_next;       // per slot: position of the next placed semaphore (exclusive end of the span)
+    DBuf<int32_t> d_next_slot;  // per slot: next live, already placed slot (-1 = none): the span ends at its semaphore
     DBuf<int64_t> d_slot_key;
     DBuf<int64_t> d_live_keys;
     DBuf<int32_t> d_live_slot;
     DBuf<int32_t> d_keymap;     // optional direct-address table key - keymap_min -> slot (dense key ranges only)
     std::vector<int32_t> keymap_h;
     int64_t keymap_min = 0, keymap_len = 0;
-    bool next_dirty = true;
+    std::vector<int32_t> next_slot_h;
     int64_t max_inkey = 0;      // upper bound of the in-array keys ever stored (sizes the dense x of SpMV)
 
     const int32_t* keymap() const { return keymap_len > 0 ? d_keymap.p : nullptr; }
@@ -492,9 +473,24 @@ struct Pcsr {
     int64_t nlive() const { return (int64_t)live_keys_h.size(); }
     int64_t nnz() const { return pma.nnz - nb_partitions; }   // pcsr.jl:11
 
-    void rebuild_live_and_upload(cudaStream_t st) {
+    // unplaced (nullable): slots created by the running batch whose semaphore is not in the array yet
+    void rebuild_live_and_upload(cudaStream_t st, const std::vector<int32_t>* unplaced = nullptr) {
         live_keys_h.clear();
         live_slot_h.clear();
+        {
+            const int64_t nsl = nslots();
+            std::vector<uint8_t> placed(slot_live.begin(), slot_live.end());
+            if (unplaced)
+                for (int32_t u : *unplaced) placed[(size_t)u] = 0;
+            next_slot_h.assign((size_t)nsl, -1);
+            int32_t nxt = -1;
+            for (int64_t q = nsl - 1; q >= 0; --q) {
+                next_slot_h[(size_t)q] = nxt;
+                if (placed[(size_t)q]) nxt = (int32_t)q;
+            }
+            d_next_slot.ensure((size_t)nsl + 1);
+            if (nsl) DSA_CUDA(cudaMemcpyAsync(d_next_slot.p, next_slot_h.data(), (size_t)nsl * 4, cudaMemcpyHostToDevice, st));
+        }
         for (int64_t s = 0; s < nslots(); ++s)
             if (slot_live[s]) { live_keys_h.push_back(slot_key[s]); live_slot_h.push_back((int32_t)s); }
         const size_t ns = (size_t)nslots(), nl = live_keys_h.size();
@@ -525,24 +521,6 @@ struct Pcsr {
         return live_slot_h[(size_t)(it - live_keys_h.begin())];
     }
 
-    void ensure_next(PcsrWorkspace& ws, cudaStream_t st) {
-        if (!next_dirty) return;
-        const int64_t ns = nslots();
-        d_next.ensure((size_t)ns + 1);
-        if (ns > 0) {
-            int32_t* flag = ws.flag32.ensure((size_t)ns);
-            int32_t* rank = ws.rank32.ensure((size_t)ns);
-            int64_t* lp = ws.live_pos.ensure((size_t)ns + 1);
-            int64_t* ndev = ws.nuniq.ensure(4);
-            const unsigned gr = grid_for(ns, 256);
-            DSA_LAUNCH("flag_placed", k_flag_placed, gr, 256, 0, st, d_sem.p, ns, flag);
-            exclusive_scan_i32<int32_t>(ws.batch.scan, flag, rank, ns, ndev + 1, st);
-            DSA_LAUNCH("live_positions", k_live_positions, gr, 256, 0, st, d_sem.p, rank, ns, lp);
-            DSA_LAUNCH("next_sem", k_next_sem, gr, 256, 0, st, d_sem.p, rank, ns, lp, ndev + 1, pma.g.capacity, d_next.p);
-        }
-        next_dirty = false;
-    }
-
     // MappedPackedCSC(K, L, T) (pcsr.jl:82-86)
     void init_empty(cudaStream_t st) {
         pma.build_from_sorted(nullptr, nullptr, 0, nullptr, st);
@@ -551,7 +529,6 @@ struct Pcsr {
         slot_live.clear();
         rebuild_live_and_upload(st);
         d_sem.ensure(1);
-        next_dirty = true;
         max_inkey = 0;
     }
 
@@ -566,23 +543,21 @@ struct Pcsr {
 
     void get_batch_d(PcsrWorkspace& ws, const int64_t* d_inkeys, const int64_t* d_partkeys, int64_t n, double* d_out, cudaStream_t st) {
         if (n <= 0) return;
-        ensure_next(ws, st);
         int32_t* op_slot = ws.op_slot.ensure((size_t)n);
         int64_t* cs = ws.cs.ensure(CS_WORDS);
         DSA_LAUNCH("colstat_init", k_colstat_init, 1, 1, 0, st, cs);
         DSA_LAUNCH("col_lookup", k_col_lookup, grid_for(n, 256), 256, 0, st, d_partkeys, (const int64_t*)nullptr, (const double*)nullptr, n,
                    d_live_keys.p, d_live_slot.p, nlive(), keymap(), keymap_min, keymap_len, op_slot, cs);
         DSA_LAUNCH("get", k_get, grid_for(n, 256), 256, 0, st, pma.keys.p, pma.vals.p, pma.g.capacity, op_slot, d_inkeys, n, d_sem.p,
-                   d_next.p, d_out);
+                   d_next_slot.p, d_out);
     }
 
     // spans of the listed slots, emitted in list order: returns total count; outputs in ws.tmp_k / tmp_v / tmp_owner
     int64_t gather_spans(PcsrWorkspace& ws, const int32_t* d_slots, int64_t nsl, const int64_t* d_owner_keys, bool want_vals, cudaStream_t st) {
-        ensure_next(ws, st);
         int32_t* cnt = ws.cnt32.ensure((size_t)nsl + 1);
         int32_t* off = ws.idx32.ensure((size_t)nsl + 1);
         int64_t* tot = ws.nuniq.ensure(4);
-        DSA_LAUNCH("span_count", k_span_count, grid_for(nsl * 32, 256), 256, 0, st, pma.keys.p, d_slots, nsl, d_sem.p, d_next.p, cnt);
+        DSA_LAUNCH("span_count", k_span_count, grid_for(nsl * 32, 256), 256, 0, st, pma.keys.p, d_slots, nsl, d_sem.p, d_next_slot.p, pma.g.capacity, cnt);
         exclusive_scan_i32<int32_t>(ws.batch.scan, cnt, off, nsl, tot, st);
         int64_t h_tot = 0;
         DSA_CUDA(cudaMemcpyAsync(&h_tot, tot, 8, cudaMemcpyDeviceToHost, st));
@@ -591,7 +566,7 @@ struct Pcsr {
             ws.tmp_k.ensure((size_t)h_tot);
             if (want_vals) ws.tmp_v.ensure((size_t)h_tot);
             if (d_owner_keys) ws.tmp_owner.ensure((size_t)h_tot);
-            DSA_LAUNCH("span_emit", k_span_emit, grid_for(nsl * 32, 256), 256, 0, st, pma.keys.p, pma.vals.p, d_slots, nsl, d_sem.p, d_next.p,
+            DSA_LAUNCH("span_emit", k_span_emit, grid_for(nsl * 32, 256), 256, 0, st, pma.keys.p, pma.vals.p, d_slots, nsl, d_sem.p, d_next_slot.p, pma.g.capacity,
                        off, ws.tmp_k.p, want_vals ? ws.tmp_v.p : (double*)nullptr, d_owner_keys ? ws.tmp_owner.p : (int64_t*)nullptr,
                        d_owner_keys);
         }
@@ -602,16 +577,14 @@ struct Pcsr {
     void delete_slots(PcsrWorkspace& ws, const std::vector<int32_t>& slots, const int32_t* d_slots, cudaStream_t st) {
         const int64_t nsl = (int64_t)slots.size();
         if (nsl == 0) return;
-        ensure_next(ws, st);
         pma.prepare_batch_scratch(ws.batch, 0, st);
-        DSA_LAUNCH("span_purge", k_span_purge, grid_for(nsl * 32, 256), 256, 0, st, pma.keys.p, pma.vals.p, d_slots, nsl, d_sem.p, d_next.p,
-                   pma.leafcnt.p, ws.batch.touched.p, ilog2_i64(pma.g.segment_capacity));
+        DSA_LAUNCH("span_purge", k_span_purge, grid_for(nsl * 32, 256), 256, 0, st, pma.keys.p, pma.vals.p, d_slots, nsl, d_sem.p, d_next_slot.p, pma.g.capacity,
+                   pma.leafcnt.p, ws.batch.touched, ilog2_i64(pma.g.segment_capacity));
         DSA_LAUNCH("clear_sems", k_clear_sems, grid_for(nsl, 256), 256, 0, st, d_sem.p, d_slots, nsl);
         pma.rebalance_after(ws.batch, 0, d_sem.p, st);
         for (int32_t s : slots) slot_live[(size_t)s] = 0;   // pcsr.jl:202,209
         nb_partitions -= nsl;                                // pcsr.jl:191
         rebuild_live_and_upload(st);
-        next_dirty = true;
     }
 
     // flat SpMV; results by slot in ws.yslot / ws.ycnt
@@ -648,7 +621,6 @@ struct Pcsr {
         d_sem.ensure((size_t)nslots() + 1);
         if (nslots()) DSA_CUDA(cudaMemcpyAsync(d_sem.p, o.d_sem.p, (size_t)nslots() * 8, cudaMemcpyDeviceToDevice, st));
         rebuild_live_and_upload(st);
-        next_dirty = true;
     }
 };
 
@@ -755,7 +727,6 @@ inline void Pcsr::build_coo_d(PcsrWorkspace& ws, const int64_t* d_inkeys, const 
     nb_partitions = nparts;
     max_inkey = kmax;
     rebuild_live_and_upload(st);
-    next_dirty = true;
 }
 
 }  // namespace dsa

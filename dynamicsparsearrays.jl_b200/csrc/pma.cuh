@@ -111,12 +111,19 @@ __device__ __forceinline__ int64_t gapped_find(const int64_t* __restrict__ keys,
     return i;
 }
 
+// exclusive end of the span of partition `s`: the position of the next placed semaphore, or the capacity
+// (pcsr.jl:177-186 _pos_of_partition_end + 1).  next_slot[s] = next live, already placed slot (-1 = none).
+__device__ __forceinline__ int64_t span_end(const int64_t* __restrict__ sem, const int32_t* __restrict__ next_slot, int32_t s, int64_t cap) {
+    const int32_t ns = next_slot[s];
+    return ns >= 0 ? sem[ns] : cap;
+}
+
 // Locate every (sorted, unique) op.  pid == nullptr: plain PMA, search the whole array.  Otherwise the partition span is
 // [sem[pid], next_sem[pid]) and, like pcsr.jl:305-307, inserts search (sem, end] while deletes search [sem, end].
 // sem[pid] < 0 marks a partition created by this batch: everything goes right before the next live semaphore.
 __global__ void __launch_bounds__(256) k_locate(const int64_t* __restrict__ keys, int64_t cap, const int32_t* __restrict__ op_pid,
                                                  const int64_t* __restrict__ op_key, const double* __restrict__ op_val, int64_t nops,
-                                                 const int64_t* __restrict__ sem, const int64_t* __restrict__ next_sem,
+                                                 const int64_t* __restrict__ sem, const int32_t* __restrict__ next_slot,
                                                  int64_t* __restrict__ op_pos, uint8_t* __restrict__ op_flag,
                                                  const int64_t* __restrict__ n_dev) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -128,7 +135,7 @@ __global__ void __launch_bounds__(256) k_locate(const int64_t* __restrict__ keys
     if (op_pid) {
         const int32_t pid = op_pid[i];
         const int64_t s = sem[pid];
-        const int64_t e = next_sem[pid];
+        const int64_t e = span_end(sem, next_slot, pid, cap);
         if (s < 0 || key == 0) {
             pos = e - 1;   // new partition (or its semaphore): before the next live semaphore (pcsr.jl:121-126,101)
         } else {
@@ -144,7 +151,7 @@ __global__ void __launch_bounds__(256) k_locate(const int64_t* __restrict__ keys
 // batched getindex (pma.jl:189-193 / pcsr.jl:228-232): value or 0.0.  pid < 0 = column absent (pcsr.jl:263-265).
 __global__ void __launch_bounds__(256) k_get(const int64_t* __restrict__ keys, const double* __restrict__ vals, int64_t cap,
                                               const int32_t* __restrict__ q_pid, const int64_t* __restrict__ q_key, int64_t nq,
-                                              const int64_t* __restrict__ sem, const int64_t* __restrict__ next_sem,
+                                              const int64_t* __restrict__ sem, const int32_t* __restrict__ next_slot,
                                               double* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nq) return;
@@ -152,7 +159,7 @@ __global__ void __launch_bounds__(256) k_get(const int64_t* __restrict__ keys, c
     int64_t pos = -1;
     if (q_pid) {
         const int32_t pid = q_pid[i];
-        if (pid >= 0 && sem[pid] >= 0) pos = gapped_find(keys, q_key[i], sem[pid], next_sem[pid] - 1, &hit);
+        if (pid >= 0 && sem[pid] >= 0) pos = gapped_find(keys, q_key[i], sem[pid], span_end(sem, next_slot, pid, cap) - 1, &hit);
     } else {
         pos = gapped_find(keys, q_key[i], 0, cap - 1, &hit);
     }
@@ -350,6 +357,7 @@ struct MergeArgs {
     int64_t root_c, root_m;
     int min_h;                 // dense path: only windows with outermost height >= min_h (the big ones)
     const uint8_t* cover;      // per leaf: 0 = not inside a window above leaf level
+    const uint8_t* destpos;    // [33][32] spread! offset of rank r in a leaf holding m elements
     const int32_t* hi_h;       // work list of windows above leaf level
     const int64_t* hi_w;
     const uint8_t* hi_max;
@@ -476,22 +484,26 @@ __global__ void __launch_bounds__(256) k_leaf_merge(MergeArgs A, Levels L) {
     const unsigned gmask = S >= 32 ? 0xffffffffu : ((1u << S) - 1u);
     const unsigned lm = (lm_all >> gshift) & gmask;
     const int srank = __popc(lm & ((1u << q) - 1u));
-    // lane q of the group holds insert q of the leaf (an accepted leaf has at most S items)
+    // round 3: lane q of the group holds insert q of the leaf (an accepted leaf has at most S items)
     const bool has_ins = active && q < nins;
-    int64_t ipos = INT64_MAX, ik = 0;
+    int qq = -2;
+    int64_t ik = 0;
     double iv = 0.0;
-    if (has_ins) {   // round 3
-        ipos = A.ins_pos[i0 + q];
+    if (has_ins) {
+        qq = (int)(A.ins_pos[i0 + q] - p0);   // predecessor cell inside the leaf, -1 = before the first cell
         ik = A.ins_key[i0 + q];
         iv = A.ins_val[i0 + q];
     }
-    const int maxn = __reduce_max_sync(0xffffffffu, active ? nins : 0);
-    int cntb = 0;   // inserts whose predecessor lies before this cell
-    for (int j = 0; j < maxn; ++j) {
-        const int64_t pj = __shfl_sync(0xffffffffu, ipos, gshift + (j & (S - 1)));
-        if (j < nins && pj < p) ++cntb;
+    // rank of insert q in the merged run = survivors up to its predecessor + the inserts before it
+    int rj = 0;
+    unsigned insbit = 0;
+    if (has_ins) {
+        rj = (qq < 0 ? 0 : __popc(lm & (qq >= 31 ? 0xffffffffu : ((2u << qq) - 1u)))) + q;
+        insbit = 1u << rj;
     }
+    const unsigned insmask = __reduce_or_sync(gmask << gshift, insbit);   // merged ranks taken by the inserts
     const int m = __popc(lm) + nins;
+    const uint8_t* __restrict__ dtab = A.destpos + m * 32;                  // spread! offset of every rank for (S cells, m elements)
     const unsigned mask = L.leafmask[m];
     __syncwarp();
     if (active) {
@@ -500,15 +512,20 @@ __global__ void __launch_bounds__(256) k_leaf_merge(MergeArgs A, Levels L) {
             A.cur_v[p] = 0.0;
         }
         if (live) {
-            const int64_t d = p0 + nth_set_bit(mask, srank + cntb);
+            // the srank-th rank not taken by an insert: least fixed point of R = srank + #inserts at ranks <= R
+            int R = srank;
+            while (true) {
+                const int Rn = srank + __popc(insmask & (R >= 31 ? 0xffffffffu : ((2u << R) - 1u)));
+                if (Rn == R) break;
+                R = Rn;
+            }
+            const int64_t d = p0 + dtab[R];
             A.cur_k[d] = key;
             A.cur_v[d] = val;
             if (A.sem && key == 0) A.sem[(int64_t)val - 1] = d;   // moves.jl:160-166
         }
         if (has_ins) {
-            const int qq = (int)(ipos - p0);   // -1 .. S-1
-            const int surv_le = qq < 0 ? 0 : __popc(lm & (qq >= 31 ? 0xffffffffu : ((2u << qq) - 1u)));
-            const int64_t d = p0 + nth_set_bit(mask, surv_le + q);
+            const int64_t d = p0 + dtab[rj];
             A.cur_k[d] = ik;
             A.cur_v[d] = iv;
             if (A.sem && ik == 0) A.sem[(int64_t)iv - 1] = d;
@@ -685,13 +702,19 @@ struct BatchWorkspace {   // per-handle scratch reused by every batch
     DBuf<int32_t> ins_idx, flag32;
     DBuf<int64_t> ins_key, ins_pos;
     DBuf<double> ins_val;
-    DBuf<int32_t> inscnt, ins_first, post;
-    DBuf<uint8_t> touched, mark, cover, hi_max;
+    DBuf<int32_t> ins_first, post;
+    DBuf<uint8_t> hi_max;
+    // everything that must start a batch as zero lives in ONE block cleared by one memset:
+    DBuf<uint8_t> zero_blk;
+    int64_t* status = nullptr;   // ST_WORDS
+    int32_t* inscnt = nullptr;   // per leaf
+    uint8_t* mark = nullptr;     // implicit tree
+    uint8_t* touched = nullptr;  // per leaf
+    uint8_t* cover = nullptr;    // per leaf
     DBuf<int32_t> hi_h;
     DBuf<int64_t> hi_w;
     DBuf<int64_t> shadow_k;
     DBuf<double> shadow_v;
-    DBuf<int64_t> status;
     HPinned<int64_t> h_status;
     ScanWorkspace scan;
 };
@@ -702,6 +725,22 @@ struct PmaCore {
     DBuf<int64_t> keys;
     DBuf<double> vals;
     DBuf<int32_t> leafcnt;
+    DBuf<uint8_t> destpos;     // leaf-level spread! table, rebuilt when the segment capacity is (re)set
+    int64_t destpos_S = -1;
+
+    void ensure_destpos(cudaStream_t st) {
+        const int S = (int)g.segment_capacity;
+        if (destpos_S == S) return;
+        std::vector<uint8_t> h(33 * 32, 0);
+        for (int m = 0; m <= S; ++m) {
+            const Spread sp = spread_make(S, m);
+            for (int r = 0; r < m; ++r) h[(size_t)m * 32 + r] = (uint8_t)spread_dest(sp, r);
+        }
+        destpos.ensure(h.size());
+        DSA_CUDA(cudaMemcpyAsync(destpos.p, h.data(), h.size(), cudaMemcpyHostToDevice, st));
+        DSA_CUDA(cudaStreamSynchronize(st));
+        destpos_S = S;
+    }
 
     Levels levels() const {
         Levels L;
@@ -755,17 +794,15 @@ struct PmaCore {
         Levels L = levels();
         const int64_t nsegs = g.nb_segments;
         int32_t* post = ws.post.ensure((size_t)tree_size());
-        uint8_t* mark = ws.mark.ensure((size_t)tree_size());
-        int64_t* status = ws.status.ensure(ST_WORDS);
-        uint8_t* cover = ws.cover.ensure((size_t)nsegs);
+        uint8_t* mark = ws.mark;
+        int64_t* status = ws.status;
+        uint8_t* cover = ws.cover;
         int32_t* hi_h = ws.hi_h.ensure((size_t)nsegs + 1);
         int64_t* hi_w = ws.hi_w.ensure((size_t)nsegs + 1);
         uint8_t* hi_max = ws.hi_max.ensure((size_t)nsegs + 1);
-        DSA_CUDA(cudaMemsetAsync(mark, 0, (size_t)tree_size(), st));
-        DSA_CUDA(cudaMemsetAsync(cover, 0, (size_t)nsegs, st));
-        DSA_LAUNCH("tree_low", k_tree_low, grid_for(nsegs, 1024), 1024, 0, st, leafcnt.p, ws.inscnt.p, post, L);
+        DSA_LAUNCH("tree_low", k_tree_low, grid_for(nsegs, 1024), 1024, 0, st, leafcnt.p, ws.inscnt, post, L);
         if (L.H > 10) DSA_LAUNCH("tree_high", k_tree_high, 1, 1024, 0, st, post, L);
-        DSA_LAUNCH("select_windows", k_select_windows, grid_for(nsegs, 256), 256, 0, st, ws.touched.p, post, mark, L, status, hi_h, hi_w);
+        DSA_LAUNCH("select_windows", k_select_windows, grid_for(nsegs, 256), 256, 0, st, ws.touched, post, mark, L, status, hi_h, hi_w);
         // status[ST_ROOT] <- root count
         DSA_CUDA(cudaMemcpyAsync(status + ST_ROOT, post + L.off[L.H], sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
         int64_t* hs = ws.h_status.ensure(ST_WORDS);
@@ -775,10 +812,12 @@ struct PmaCore {
         MergeArgs A;
         memset(&A, 0, sizeof(A));
         A.src_k = keys.p; A.src_v = vals.p; A.cur_k = keys.p; A.cur_v = vals.p;
-        A.post = post; A.mark = mark; A.inscnt = ws.inscnt.p; A.ins_first = ws.ins_first.p;
+        A.post = post; A.mark = mark; A.inscnt = ws.inscnt; A.ins_first = ws.ins_first.p;
         A.ins_key = ws.ins_key.p; A.ins_val = ws.ins_val.p; A.ins_pos = ws.ins_pos.p;
         A.leafcnt = leafcnt.p; A.sem = d_sem;
         A.cover = cover; A.hi_h = hi_h; A.hi_w = hi_w; A.hi_max = hi_max;
+        ensure_destpos(st);
+        A.destpos = destpos.p;
         const unsigned warp_grid = grid_for(nsegs * 32, 256);
         if (hs[ST_OVER] || hs[ST_UNDER]) {
             // root failed: _extend!/_shrink! (pma.jl:132-139) until the root accepts, then one full spread into the new array
@@ -827,36 +866,40 @@ struct PmaCore {
         ws.ins_key.ensure((size_t)nops + 1);
         ws.ins_val.ensure((size_t)nops + 1);
         ws.ins_pos.ensure((size_t)nops + 1);
-        ws.inscnt.ensure((size_t)nsegs);
         ws.ins_first.ensure((size_t)nsegs);
-        ws.touched.ensure((size_t)nsegs);
-        int64_t* status = ws.status.ensure(ST_WORDS);
-        DSA_CUDA(cudaMemsetAsync(ws.inscnt.p, 0, (size_t)nsegs * sizeof(int32_t), st));
-        DSA_CUDA(cudaMemsetAsync(ws.touched.p, 0, (size_t)nsegs, st));
-        DSA_CUDA(cudaMemsetAsync(status, 0, ST_WORDS * sizeof(int64_t), st));
+        const size_t tsz = ((size_t)tree_size() + 15) & ~(size_t)15;
+        const size_t lsz = ((size_t)nsegs + 15) & ~(size_t)15;
+        const size_t total = ST_WORDS * 8 + (size_t)nsegs * 4 + 16 + tsz + 2 * lsz;
+        uint8_t* z = ws.zero_blk.ensure(total);
+        ws.status = (int64_t*)z;
+        ws.inscnt = (int32_t*)(z + ST_WORDS * 8);
+        ws.mark = z + ST_WORDS * 8 + (((size_t)nsegs * 4 + 15) & ~(size_t)15);
+        ws.touched = ws.mark + tsz;
+        ws.cover = ws.touched + lsz;
+        DSA_CUDA(cudaMemsetAsync(z, 0, total, st));
     }
 
     // sorted unique ops -> located, applied, merged.  op_pid/sem/next_sem nullable (plain PMA).
     void apply_sorted_ops(BatchWorkspace& ws, const int32_t* op_pid, const int64_t* op_key, const double* op_val, int64_t nops,
-                          int64_t* d_sem, const int64_t* d_next_sem, cudaStream_t st, bool scratch_ready = false,
+                          int64_t* d_sem, const int32_t* d_next_slot, cudaStream_t st, bool scratch_ready = false,
                           const int64_t* n_dev = nullptr) {
         if (!scratch_ready) prepare_batch_scratch(ws, nops, st);
         const int lgS = ilog2_i64(g.segment_capacity);
         int64_t nins = 0;
         if (nops > 0) {
             const unsigned gr = grid_for(nops, 256);
-            DSA_LAUNCH("locate", k_locate, gr, 256, 0, st, keys.p, g.capacity, op_pid, op_key, op_val, nops, d_sem, d_next_sem,
+            DSA_LAUNCH("locate", k_locate, gr, 256, 0, st, keys.p, g.capacity, op_pid, op_key, op_val, nops, d_sem, d_next_slot,
                        ws.op_pos.p, ws.op_flag.p, n_dev);
             DSA_LAUNCH("apply_hits", k_apply_hits, gr, 256, 0, st, keys.p, vals.p, ws.op_pos.p, ws.op_flag.p, op_val, nops,
-                       leafcnt.p, ws.touched.p, lgS, n_dev);
+                       leafcnt.p, ws.touched, lgS, n_dev);
             // ins_idx = exclusive scan of (flag == FL_INSERT)
             int32_t* f32 = ws.flag32.ensure((size_t)nops);
             DSA_LAUNCH("flag_inserts", k_flag_eq, gr, 256, 0, st, ws.op_flag.p, nops, (uint8_t)FL_INSERT, f32, n_dev);
-            exclusive_scan_i32<int32_t>(ws.scan, f32, ws.ins_idx.p, nops, ws.status.p + ST_NINS, st);
+            exclusive_scan_i32<int32_t>(ws.scan, f32, ws.ins_idx.p, nops, ws.status + ST_NINS, st);
             DSA_LAUNCH("compact_inserts", k_compact_inserts, gr, 256, 0, st, op_key, op_val, ws.op_pos.p, ws.op_flag.p, ws.ins_idx.p,
                        nops, ws.ins_key.p, ws.ins_val.p, ws.ins_pos.p, n_dev);
-            DSA_LAUNCH("insert_leaf_info", k_insert_leaf_info, gr, 256, 0, st, ws.ins_pos.p, ws.status.p + ST_NINS, ws.inscnt.p,
-                       ws.ins_first.p, ws.touched.p, lgS);
+            DSA_LAUNCH("insert_leaf_info", k_insert_leaf_info, gr, 256, 0, st, ws.ins_pos.p, ws.status + ST_NINS, ws.inscnt,
+                       ws.ins_first.p, ws.touched, lgS);
         }
         rebalance_after(ws, nins, d_sem, st);
     }

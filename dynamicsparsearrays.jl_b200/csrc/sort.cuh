@@ -99,6 +99,7 @@ constexpr int OS_ROUNDS = 8;                         // keys per thread
 constexpr int OS_TILE = OS_THREADS * OS_ROUNDS;      // 2048 keys per tile
 constexpr int OS_WARPS = OS_THREADS / 32;
 constexpr int OS_MAX_PASS = 8;
+constexpr int OS_LOOK = 8;
 constexpr uint32_t OS_FLAG_LOCAL = 1u << 30, OS_FLAG_INCL = 2u << 30, OS_VALUE_MASK = (1u << 30) - 1u;
 
 // ghist[pass * 256 + digit] += count
@@ -146,23 +147,31 @@ __global__ void __launch_bounds__(OS_THREADS) k_os_pass(const uint64_t* __restri
     const unsigned tile = tile_s;
     const int64_t wbase = (int64_t)tile * OS_TILE + (int64_t)wid * (OS_ROUNDS * 32);
     uint64_t k[OS_ROUNDS];
+    uint32_t v[OS_ROUNDS];
     int32_t rank[OS_ROUNDS];
+    unsigned peers[OS_ROUNDS];
 #pragma unroll
-    for (int r = 0; r < OS_ROUNDS; ++r) {
+    for (int r = 0; r < OS_ROUNDS; ++r) {   // all loads in flight together
         const int64_t idx = wbase + r * 32 + lane;
         k[r] = idx < n ? keys_in[idx] : ~uint64_t(0);
+        v[r] = idx < n ? vals_in[idx] : 0u;
     }
 #pragma unroll
-    for (int r = 0; r < OS_ROUNDS; ++r) {
+    for (int r = 0; r < OS_ROUNDS; ++r) {   // independent matches pipeline through the MIO queue
+        const int64_t idx = wbase + r * 32 + lane;
+        const unsigned d = (unsigned)((k[r] >> shift) & 0xff);
+        peers[r] = __match_any_sync(0xffffffffu, idx < n ? d : 0x100u);
+    }
+#pragma unroll
+    for (int r = 0; r < OS_ROUNDS; ++r) {   // serial part: running per-warp digit counters
         const int64_t idx = wbase + r * 32 + lane;
         const bool valid = idx < n;
         const unsigned d = (unsigned)((k[r] >> shift) & 0xff);
-        const unsigned peers = __match_any_sync(0xffffffffu, valid ? d : 0x100u);
-        const int before = __popc(peers & ((1u << lane) - 1u));
+        const int before = __popc(peers[r] & ((1u << lane) - 1u));
         int32_t basecnt = 0;
         if (valid) basecnt = wcnt[wid][d];
         __syncwarp();
-        if (valid && before == 0) wcnt[wid][d] = basecnt + __popc(peers);
+        if (valid && before == 0) wcnt[wid][d] = basecnt + __popc(peers[r]);
         __syncwarp();
         rank[r] = basecnt + before;
     }
@@ -182,13 +191,23 @@ __global__ void __launch_bounds__(OS_THREADS) k_os_pass(const uint64_t* __restri
             *mine = OS_FLAG_INCL | run;
         } else {
             *mine = OS_FLAG_LOCAL | run;
+            // decoupled look-back, OS_LOOK predecessors per round trip (all tiles of a small sort run concurrently, so the
+            // nearest inclusive prefix can be tens of tiles away: batching the polls keeps the chain short)
             int64_t t = (int64_t)tile - 1;
-            while (true) {
-                uint32_t sv;
-                do { sv = status[(size_t)t * RS_RADIX + d]; } while ((sv >> 30) == 0);
-                excl += sv & OS_VALUE_MASK;
-                if ((sv >> 30) == 2u) break;
-                --t;
+            bool done = false;
+            while (!done) {
+                uint32_t sv[OS_LOOK];
+#pragma unroll
+                for (int b = 0; b < OS_LOOK; ++b) sv[b] = (t - b >= 0) ? status[(size_t)(t - b) * RS_RADIX + d] : (uint32_t)(2u << 30);
+#pragma unroll
+                for (int b = 0; b < OS_LOOK; ++b) {
+                    if (done) break;
+                    const uint32_t f = sv[b] >> 30;
+                    if (f == 0) break;          // not published yet: poll again from this tile
+                    excl += sv[b] & OS_VALUE_MASK;
+                    --t;
+                    if (f == 2u) done = true;
+                }
             }
             *mine = OS_FLAG_INCL | (excl + run);
         }
@@ -202,7 +221,7 @@ __global__ void __launch_bounds__(OS_THREADS) k_os_pass(const uint64_t* __restri
             const unsigned d = (unsigned)((k[r] >> shift) & 0xff);
             const int64_t dst = (int64_t)dbase[d] + wcnt[wid][d] + rank[r];
             keys_out[dst] = k[r];
-            vals_out[dst] = vals_in[idx];
+            vals_out[dst] = v[r];
         }
     }
 }
