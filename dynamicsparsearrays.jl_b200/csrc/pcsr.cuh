@@ -277,6 +277,17 @@ __global__ void __launch_bounds__(256) k_clear_sems(int64_t* __restrict__ sem, c
 constexpr int SPMV_STEPS = 8;
 constexpr int SPMV_CHUNK = 32 * SPMV_STEPS;
 
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_sum_i32(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
 template <bool SPARSE_X>
 __global__ void __launch_bounds__(256) k_spmv_flat(const int64_t* __restrict__ keys, const double* __restrict__ vals, int64_t cap,
                                                     const double* __restrict__ x, const uint8_t* __restrict__ xmask, int64_t nx,
@@ -287,37 +298,64 @@ __global__ void __launch_bounds__(256) k_spmv_flat(const int64_t* __restrict__ k
     const int lane = threadIdx.x & 31;
     if (chunk >= nchunks) return;
     const unsigned lt = lanemask_lt();
-    int32_t cur_slot = -1;    // open partition (uniform across the warp)
-    double acc = 0.0;         // its partial so far
-    int32_t acc_cnt = 0;      // number of (x present) products folded into acc
-    bool prefix_open = true;  // no head seen yet in this chunk
     const int64_t base = chunk * SPMV_CHUNK;
-#pragma unroll 2
-    for (int step = 0; step < SPMV_STEPS; ++step) {
-        const int64_t p = base + step * 32 + lane;
-        int64_t k = GAP_KEY;
-        double v = 0.0;
+    // all loads of the chunk in flight together: 8 x (key, value), then 8 independent gathers of x
+    int64_t k[SPMV_STEPS];
+    double t[SPMV_STEPS];
+    int32_t tc[SPMV_STEPS];
+#pragma unroll
+    for (int s = 0; s < SPMV_STEPS; ++s) {
+        const int64_t p = base + s * 32 + lane;
+        k[s] = GAP_KEY;
+        t[s] = 0.0;
         if (p < cap) {
-            k = keys[p];
-            v = vals[p];
+            k[s] = keys[p];
+            t[s] = vals[p];
         }
-        const bool head = k == 0;
-        double t = 0.0;
-        int32_t tc = 0;
-        if (k > 0 && k <= nx) {
-            bool present = true;
-            if (SPARSE_X) present = xmask[k - 1] != 0;
+    }
+#pragma unroll
+    for (int s = 0; s < SPMV_STEPS; ++s) {
+        tc[s] = 0;
+        const int64_t kk = k[s];
+        if (kk > 0) {   // element: t = x[key] * value (separate rounding, operations.jl:101)
+            double xv = 0.0;
+            bool present = kk <= nx;
+            if (SPARSE_X) present = present && xmask[kk - 1] != 0;
             if (present) {
-                t = __dmul_rn(x[k - 1], v);
-                tc = 1;
+                xv = x[kk - 1];
+                tc[s] = 1;
             }
+            t[s] = present ? __dmul_rn(xv, t[s]) : 0.0;
+        } else if (kk != 0) {
+            t[s] = 0.0;   // gap
         }
+        // heads keep their value (partition id) in t[s]
+    }
+    int32_t cur_slot = -1;    // open partition (uniform across the warp)
+    double acc = 0.0;         // its partial up to the last head-carrying step
+    int32_t acc_cnt = 0;
+    double lacc = 0.0;        // per-lane partial of the open partition over head-less steps
+    int32_t lcnt = 0;
+    bool prefix_open = true;  // no head seen yet in this chunk
+#pragma unroll
+    for (int s = 0; s < SPMV_STEPS; ++s) {
+        const bool head = k[s] == 0;
         const unsigned hb = __ballot_sync(0xffffffffu, head);
-        // segmented inclusive scan (segments start at heads)
+        if (hb == 0) {   // common case (rows longer than a step): no shuffles at all
+            lacc = __dadd_rn(lacc, t[s]);
+            lcnt += tc[s];
+            continue;
+        }
+        // fold the lane partials into the open partition, then a segmented scan over this step
+        acc = __dadd_rn(acc, warp_sum_f64(lacc));
+        acc_cnt += warp_sum_i32(lcnt);
+        lacc = 0.0;
+        lcnt = 0;
+        const double tv = head ? 0.0 : t[s];
         const unsigned hle = hb & (lt | (1u << lane));
         const int seg_lo = hle ? 31 - __clz(hle) : 0;
-        double st = t;
-        int32_t sc = tc;
+        double st = tv;
+        int32_t sc = tc[s];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const double ot = __shfl_up_sync(0xffffffffu, st, o);
@@ -332,7 +370,7 @@ __global__ void __launch_bounds__(256) k_spmv_flat(const int64_t* __restrict__ k
         const int32_t prev_c = __shfl_up_sync(0xffffffffu, sc, 1);
         const unsigned hlt = hb & lt;
         const int prev_head_lane = hlt ? 31 - __clz(hlt) : -1;
-        const int32_t my_slot = head ? (int32_t)v - 1 : -1;
+        const int32_t my_slot = head ? (int32_t)t[s] - 1 : -1;
         const int32_t prev_head_slot = __shfl_sync(0xffffffffu, my_slot, prev_head_lane < 0 ? 0 : prev_head_lane);
         if (head) {
             double tot = lane > 0 ? prev_t : 0.0;
@@ -352,20 +390,15 @@ __global__ void __launch_bounds__(256) k_spmv_flat(const int64_t* __restrict__ k
                 ycnt[prev_head_slot] = totc;
             }
         }
-        // carry into the next step: the segment open at lane 31
-        const double last_t = __shfl_sync(0xffffffffu, st, 31);
-        const int32_t last_c = __shfl_sync(0xffffffffu, sc, 31);
-        if (hb) {
-            const int last_head_lane = 31 - __clz(hb);
-            cur_slot = __shfl_sync(0xffffffffu, my_slot, last_head_lane);
-            acc = last_t;
-            acc_cnt = last_c;
-            prefix_open = false;
-        } else {
-            acc = __dadd_rn(acc, last_t);
-            acc_cnt += last_c;
-        }
+        // the segment open at lane 31 carries into the next step
+        const int last_head_lane = 31 - __clz(hb);
+        cur_slot = __shfl_sync(0xffffffffu, my_slot, last_head_lane);
+        acc = __shfl_sync(0xffffffffu, st, 31);
+        acc_cnt = __shfl_sync(0xffffffffu, sc, 31);
+        prefix_open = false;
     }
+    acc = __dadd_rn(acc, warp_sum_f64(lacc));
+    acc_cnt += warp_sum_i32(lcnt);
     if (lane == 0) {
         if (cur_slot >= 0) {   // open partition at the end of the chunk: partial, completed by the fix-up
             yslot[cur_slot] = acc;

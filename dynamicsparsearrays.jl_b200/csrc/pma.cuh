@@ -27,7 +27,7 @@ struct Levels {
 constexpr int SMALL_CELLS = 2048;
 
 enum : uint8_t { FL_OVERWRITE = 1, FL_DELETE = 2, FL_INSERT = 4 };
-enum { ST_OVER = 0, ST_UNDER = 1, ST_NINS = 2, ST_ROOT = 3, ST_NHIGH = 4, ST_ANYBIG = 5, ST_ANYHIGH = 7, ST_WORDS = 16 };
+enum { ST_OVER = 0, ST_UNDER = 1, ST_NINS = 2, ST_ROOT = 3, ST_NHIGH = 4, ST_ANYBIG = 5, ST_NACT = 6, ST_ANYHIGH = 7, ST_WORDS = 16 };
 
 __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;
@@ -205,24 +205,35 @@ __global__ void __launch_bounds__(256) k_compact_inserts(const int64_t* __restri
     ins_pos[j] = op_pos[i];
 }
 // per-leaf bookkeeping of the compacted inserts: every new key belongs to the leaf of its predecessor cell; inserts are
-// sorted, so the inserts of one leaf are contiguous and ins_first[leaf] is the index of the first one
+// sorted, so the inserts of one leaf are contiguous.  The thread of the FIRST insert of a leaf counts the run and records
+// (leaf, first index, count) in the list of leaves that receive inserts (unordered: each entry is independent work).
+struct ActiveLeaf {
+    int32_t leaf, nins, i0, pad;
+};
 __global__ void __launch_bounds__(256) k_insert_leaf_info(const int64_t* __restrict__ ins_pos, const int64_t* __restrict__ nins_dev,
                                                            int32_t* __restrict__ inscnt, int32_t* __restrict__ ins_first,
-                                                           uint8_t* __restrict__ touched, int lgS) {
+                                                           uint8_t* __restrict__ touched, int lgS, ActiveLeaf* __restrict__ act,
+                                                           int64_t* __restrict__ nact_dev) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= *nins_dev) return;
+    const int64_t n = *nins_dev;
+    if (j >= n) return;
     const int64_t pos = ins_pos[j];
     const int64_t leaf = (pos < 0 ? 0 : pos) >> lgS;
-    atomicAdd(&inscnt[leaf], 1);
-    bool first = true;
     if (j > 0) {
         const int64_t pq = ins_pos[j - 1];
-        first = ((pq < 0 ? 0 : pq) >> lgS) != leaf;
+        if (((pq < 0 ? 0 : pq) >> lgS) == leaf) return;
     }
-    if (first) {
-        ins_first[leaf] = (int32_t)j;
-        touched[leaf] = 1;
+    int cnt = 1;
+    for (int64_t t = j + 1; t < n; ++t) {
+        const int64_t pt = ins_pos[t];
+        if (((pt < 0 ? 0 : pt) >> lgS) != leaf) break;
+        ++cnt;
     }
+    inscnt[leaf] = cnt;
+    ins_first[leaf] = (int32_t)j;
+    touched[leaf] = 1;
+    const unsigned long long slot = atomicAdd((unsigned long long*)nact_dev, 1ull);
+    act[slot] = ActiveLeaf{(int32_t)leaf, cnt, (int32_t)j, 0};
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -358,6 +369,8 @@ struct MergeArgs {
     int min_h;                 // dense path: only windows with outermost height >= min_h (the big ones)
     const uint8_t* cover;      // per leaf: 0 = not inside a window above leaf level
     const uint8_t* destpos;    // [33][32] spread! offset of rank r in a leaf holding m elements
+    const ActiveLeaf* act;     // leaves that receive inserts
+    const int64_t* nact_dev;
     const int32_t* hi_h;       // work list of windows above leaf level
     const int64_t* hi_w;
     const uint8_t* hi_max;
@@ -453,47 +466,43 @@ __global__ void __launch_bounds__(256) k_merge_scatter(MergeArgs A, Levels L) {
 // dense over the leaves with a two-load early exit.  The merged run is re-laid in place from registers; destinations
 // come from the precomputed spread! occupancy mask of (S cells, m elements) — no floating point on this path.
 // ---------------------------------------------------------------------------------------------
+// List-driven: one S-lane group per leaf that receives inserts (32/S leaves per warp), two dependent load rounds.
 __global__ void __launch_bounds__(256) k_leaf_merge(MergeArgs A, Levels L) {
     const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const int lgS = L.lgS, S = 1 << lgS;
     const int grp = lane >> lgS, q = lane & (S - 1), gshift = grp << lgS;
-    const int64_t l = gw * (32 >> lgS) + grp;
-    const bool valid = l < L.nsegs;
-    // round 1: two independent loads decide whether the leaf is merged here
-    int nins = 0;
-    uint8_t cov = 1;
-    if (valid) {
-        nins = A.inscnt[l];
-        cov = A.cover[l];
-    }
-    const bool active = valid && nins > 0 && cov == 0;
-    if (!__any_sync(0xffffffffu, active)) return;
-    // round 2: the leaf's cells and the index of its first insert, issued together
+    const unsigned gmask = S >= 32 ? 0xffffffffu : ((1u << S) - 1u);
+    const int64_t e = gw * (32 >> lgS) + grp;
+    const int64_t nact = *A.nact_dev;
+    if (gw * (32 >> lgS) >= nact) return;
+    // round 1: the work item
+    ActiveLeaf al = ActiveLeaf{0, 0, 0, 0};
+    const bool have = e < nact;
+    if (have) al = A.act[e];
+    const int64_t l = al.leaf;
+    const int nins = al.nins;
     const int64_t p0 = l << lgS, p = p0 + q;
-    int64_t key = GAP_KEY;
-    double val = 0.0;
-    int64_t i0 = 0;
-    if (active) {
+    // round 2: everything else, issued together
+    uint8_t cov = 1;
+    int64_t key = GAP_KEY, ik = 0;
+    double val = 0.0, iv = 0.0;
+    int qq = -2;
+    const bool has_ins = have && q < nins;
+    if (have) {
+        cov = A.cover[l];
         key = A.src_k[p];
         val = A.src_v[p];
-        i0 = A.ins_first[l];
+        if (has_ins) {
+            qq = (int)(A.ins_pos[al.i0 + q] - p0);   // predecessor cell inside the leaf, -1 = before the first cell
+            ik = A.ins_key[al.i0 + q];
+            iv = A.ins_val[al.i0 + q];
+        }
     }
+    const bool active = have && cov == 0;   // not inside a window above leaf level (those are re-laid by k_window_small)
     const bool live = key != GAP_KEY;
-    const unsigned lm_all = __ballot_sync(0xffffffffu, live);
-    const unsigned gmask = S >= 32 ? 0xffffffffu : ((1u << S) - 1u);
-    const unsigned lm = (lm_all >> gshift) & gmask;
+    const unsigned lm = (__ballot_sync(0xffffffffu, live) >> gshift) & gmask;
     const int srank = __popc(lm & ((1u << q) - 1u));
-    // round 3: lane q of the group holds insert q of the leaf (an accepted leaf has at most S items)
-    const bool has_ins = active && q < nins;
-    int qq = -2;
-    int64_t ik = 0;
-    double iv = 0.0;
-    if (has_ins) {
-        qq = (int)(A.ins_pos[i0 + q] - p0);   // predecessor cell inside the leaf, -1 = before the first cell
-        ik = A.ins_key[i0 + q];
-        iv = A.ins_val[i0 + q];
-    }
     // rank of insert q in the merged run = survivors up to its predecessor + the inserts before it
     int rj = 0;
     unsigned insbit = 0;
@@ -503,7 +512,7 @@ __global__ void __launch_bounds__(256) k_leaf_merge(MergeArgs A, Levels L) {
     }
     const unsigned insmask = __reduce_or_sync(gmask << gshift, insbit);   // merged ranks taken by the inserts
     const int m = __popc(lm) + nins;
-    const uint8_t* __restrict__ dtab = A.destpos + m * 32;                  // spread! offset of every rank for (S cells, m elements)
+    const uint8_t* __restrict__ dtab = A.destpos + m * 32;   // spread! offsets for (S cells, m elements)
     const unsigned mask = L.leafmask[m];
     __syncwarp();
     if (active) {
@@ -713,6 +722,7 @@ struct BatchWorkspace {   // per-handle scratch reused by every batch
     uint8_t* cover = nullptr;    // per leaf
     DBuf<int32_t> hi_h;
     DBuf<int64_t> hi_w;
+    DBuf<ActiveLeaf> act;
     DBuf<int64_t> shadow_k;
     DBuf<double> shadow_v;
     HPinned<int64_t> h_status;
@@ -818,6 +828,8 @@ struct PmaCore {
         A.cover = cover; A.hi_h = hi_h; A.hi_w = hi_w; A.hi_max = hi_max;
         ensure_destpos(st);
         A.destpos = destpos.p;
+        A.act = ws.act.p;
+        A.nact_dev = ws.status + ST_NACT;
         const unsigned warp_grid = grid_for(nsegs * 32, 256);
         if (hs[ST_OVER] || hs[ST_UNDER]) {
             // root failed: _extend!/_shrink! (pma.jl:132-139) until the root accepts, then one full spread into the new array
@@ -841,7 +853,11 @@ struct PmaCore {
                 DSA_LAUNCH("cover_windows", k_cover_windows, (unsigned)nhigh, 128, 0, st, hi_h, hi_w, mark, L, hi_max, cover);
             // leaves accepted at their own level (the common case), in place
             const int leaves_per_warp = 32 >> L.lgS;
-            DSA_LAUNCH("leaf_merge", k_leaf_merge, grid_for(((nsegs + leaves_per_warp - 1) / leaves_per_warp) * 32, 256), 256, 0, st, A, L);
+            const int64_t nact = hs[ST_NACT];
+            if (nact > 0) {
+                const int64_t lm_warps = (nact + leaves_per_warp - 1) / leaves_per_warp;
+                DSA_LAUNCH("leaf_merge", k_leaf_merge, grid_for(lm_warps * 32, 256), 256, 0, st, A, L);
+            }
             // outermost windows of <= SMALL_CELLS cells: one CTA each, through shared memory
             if (nhigh > 0) DSA_LAUNCH("window_small", k_window_small, (unsigned)nhigh, 256, 0, st, A, L);
             // bigger windows (rare: cascades): dense warp-per-leaf scatter into the shadow array + copy back
@@ -899,7 +915,7 @@ struct PmaCore {
             DSA_LAUNCH("compact_inserts", k_compact_inserts, gr, 256, 0, st, op_key, op_val, ws.op_pos.p, ws.op_flag.p, ws.ins_idx.p,
                        nops, ws.ins_key.p, ws.ins_val.p, ws.ins_pos.p, n_dev);
             DSA_LAUNCH("insert_leaf_info", k_insert_leaf_info, gr, 256, 0, st, ws.ins_pos.p, ws.status + ST_NINS, ws.inscnt,
-                       ws.ins_first.p, ws.touched, lgS);
+                       ws.ins_first.p, ws.touched, lgS, ws.act.ensure((size_t)std::min<int64_t>(nops, g.nb_segments) + 1), ws.status + ST_NACT);
         }
         rebalance_after(ws, nins, d_sem, st);
     }

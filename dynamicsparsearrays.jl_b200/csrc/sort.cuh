@@ -95,8 +95,8 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __res
 // that are already running).  6 launches for a 34-bit key instead of 25.
 // ---------------------------------------------------------------------------------------------
 constexpr int OS_THREADS = 256;
-constexpr int OS_ROUNDS = 8;                         // keys per thread
-constexpr int OS_TILE = OS_THREADS * OS_ROUNDS;      // 2048 keys per tile
+constexpr int OS_ROUNDS = 16;                        // keys per thread
+constexpr int OS_TILE = OS_THREADS * OS_ROUNDS;      // 4096 keys per tile: a 1M-key batch is ONE wave of 245 CTAs (2 per SM)
 constexpr int OS_WARPS = OS_THREADS / 32;
 constexpr int OS_MAX_PASS = 8;
 constexpr int OS_LOOK = 8;
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) k_os_scan_hist(uint32_t* __restrict__ ghi
     }
 }
 
-__global__ void __launch_bounds__(OS_THREADS) k_os_pass(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+__global__ void __launch_bounds__(OS_THREADS, 2) k_os_pass(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                                          uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n,
                                                          int shift, const uint32_t* __restrict__ gbase, volatile uint32_t* status,
                                                          unsigned* __restrict__ ticket) {
