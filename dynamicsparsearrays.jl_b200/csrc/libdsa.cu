@@ -20,28 +20,41 @@ struct BatchStats {
     int64_t missing, minkey, maxkey, maxpart_nz, maxkey_nz, minpart;
 };
 
-static BatchStats lookup_and_stats(Pcsr& P, PcsrWorkspace& ws, const int64_t* d_inkeys, const int64_t* d_partkeys, const double* d_vals,
-                                   int64_t n, cudaStream_t st) {
-    int32_t* op_slot = ws.op_slot.ensure((size_t)n);
+// One batched setindex! of one orientation, cut at its two host decisions so that the two orientations of a matrix can
+// share each stream synchronisation:
+//   phase1_launch  column lookup + batch statistics                     | sync |
+//   phase1_finish  validation (nothing mutated yet), new columns        (own syncs, only when columns are created)
+//   phase2_launch  sort, last-writer-wins, locate, apply hits, insert bookkeeping, density tree, window selection | sync |
+//   phase3         merges / redistribute / resize
+struct BatchCtx {
+    const int64_t* inkeys = nullptr;
+    const int64_t* partkeys = nullptr;
+    const double* vals = nullptr;
+    int64_t n = 0;
+    BatchStats bs{};
+    std::vector<int32_t> new_slots_h;
+};
+
+static void phase1_launch(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t st) {
+    int32_t* op_slot = ws.op_slot.ensure((size_t)c.n);
     int64_t* cs = ws.cs.ensure(CS_WORDS);
     int64_t* hcs = ws.h_cs.ensure(CS_WORDS);
     DSA_LAUNCH("colstat_init", k_colstat_init, 1, 1, 0, st, cs);
-    DSA_LAUNCH("col_lookup", k_col_lookup, grid_for(n, 256), 256, 0, st, d_partkeys, d_inkeys, d_vals, n, P.d_live_keys.p, P.d_live_slot.p,
-               P.nlive(), P.keymap(), P.keymap_min, P.keymap_len, op_slot, cs);
+    DSA_LAUNCH("col_lookup", k_col_lookup, grid_for(c.n, 256), 256, 0, st, c.partkeys, c.inkeys, c.vals, c.n, P.d_live_keys.p,
+               P.d_live_slot.p, P.nlive(), P.keymap(), P.keymap_min, P.keymap_len, op_slot, cs);
     DSA_CUDA(cudaMemcpyAsync(hcs, cs, CS_WORDS * 8, cudaMemcpyDeviceToHost, st));
-    DSA_CUDA(cudaStreamSynchronize(st));
-    return BatchStats{hcs[CS_MISSING], hcs[CS_MINKEY], hcs[CS_MAXKEY], hcs[CS_MAXPART_NZ], hcs[CS_MAXKEY_NZ], hcs[CS_MINPART]};
 }
 
-void Pcsr::set_batch_d(PcsrWorkspace& ws, const int64_t* d_inkeys, const int64_t* d_partkeys, const double* d_vals, int64_t n,
-                       int64_t* max_part_nz, int64_t* max_key_nz, cudaStream_t st) {
-    if (n <= 0) return;
-    BatchStats bs = lookup_and_stats(*this, ws, d_inkeys, d_partkeys, d_vals, n, st);
-    if (bs.minkey < 1) throw DsaError{DSA_ERR_ARGUMENT, "in-array keys must be >= 1 (key 0 is the semaphore key, pcsr.jl:23)"};
-    if (max_part_nz) *max_part_nz = bs.maxpart_nz;
-    if (max_key_nz) *max_key_nz = bs.maxkey_nz;
+static void phase1_read(PcsrWorkspace& ws, BatchCtx& c) {
+    const int64_t* hcs = ws.h_cs.p;
+    c.bs = BatchStats{hcs[CS_MISSING], hcs[CS_MINKEY], hcs[CS_MAXKEY], hcs[CS_MAXPART_NZ], hcs[CS_MAXKEY_NZ], hcs[CS_MINPART]};
+}
+
+static void phase1_finish(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t st) {
+    const BatchStats& bs = c.bs;
+    const int64_t n = c.n;
     const unsigned gr = grid_for(n, 256);
-    std::vector<int32_t> new_slots_h;
+    c.new_slots_h.clear();
     if (bs.missing > 0) {
         // absent columns: distinct keys in first-arrival order -> addcolumn! plan (pcsr.jl:148-169) on the host mirror
         int32_t* flag = ws.flag32.ensure((size_t)n);
@@ -49,7 +62,7 @@ void Pcsr::set_batch_d(PcsrWorkspace& ws, const int64_t* d_inkeys, const int64_t
         int64_t* mk = ws.miss_keys.ensure((size_t)bs.missing);
         DSA_LAUNCH("flag_missing", k_flag_missing, gr, 256, 0, st, ws.op_slot.p, n, flag);
         exclusive_scan_i32<int32_t>(ws.batch.scan, flag, idx, n, nullptr, st);
-        DSA_LAUNCH("compact_missing", k_compact_missing, gr, 256, 0, st, ws.op_slot.p, d_partkeys, idx, n, mk);
+        DSA_LAUNCH("compact_missing", k_compact_missing, gr, 256, 0, st, ws.op_slot.p, c.partkeys, idx, n, mk);
         ws.h_tmp.resize((size_t)bs.missing);
         DSA_CUDA(cudaMemcpyAsync(ws.h_tmp.data(), mk, (size_t)bs.missing * 8, cudaMemcpyDeviceToHost, st));
         DSA_CUDA(cudaStreamSynchronize(st));
@@ -62,14 +75,14 @@ void Pcsr::set_batch_d(PcsrWorkspace& ws, const int64_t* d_inkeys, const int64_t
         }
         std::vector<int64_t> out_key, out_old;
         std::vector<uint8_t> out_live;
-        const int64_t nold = nslots();
-        const int64_t nnew_slots = colmap_plan(slot_key.data(), slot_live.data(), nold, distinct.data(), (int64_t)distinct.size(), out_key,
-                                               out_live, out_old);
+        const int64_t nold = P.nslots();
+        const int64_t nnew_slots = colmap_plan(P.slot_key.data(), P.slot_live.data(), nold, distinct.data(), (int64_t)distinct.size(),
+                                               out_key, out_live, out_old);
         if (nnew_slots >= (int64_t(1) << 31)) throw DsaError{DSA_ERR_ARGUMENT, "too many partitions"};
         std::vector<int32_t> old2new((size_t)std::max<int64_t>(nold, 1), -1);
         for (int64_t t = 0; t < nnew_slots; ++t) {
             if (out_old[(size_t)t] > 0) old2new[(size_t)out_old[(size_t)t] - 1] = (int32_t)t;
-            else if (out_live[(size_t)t]) new_slots_h.push_back((int32_t)t);
+            else if (out_live[(size_t)t]) c.new_slots_h.push_back((int32_t)t);
         }
         DBuf<int64_t> new_sem;
         new_sem.ensure((size_t)nnew_slots + 1);
@@ -77,31 +90,35 @@ void Pcsr::set_batch_d(PcsrWorkspace& ws, const int64_t* d_inkeys, const int64_t
         if (nold > 0) {
             int32_t* d_o2n = ws.old2new.ensure((size_t)nold);
             DSA_CUDA(cudaMemcpyAsync(d_o2n, old2new.data(), (size_t)nold * 4, cudaMemcpyHostToDevice, st));
-            DSA_LAUNCH("renumber", k_renumber, grid_for(nold, 256), 256, 0, st, d_sem.p, d_o2n, nold, new_sem.p, pma.vals.p);
+            DSA_LAUNCH("renumber", k_renumber, grid_for(nold, 256), 256, 0, st, P.d_sem.p, d_o2n, nold, new_sem.p, P.pma.vals.p);
         }
         DSA_CUDA(cudaStreamSynchronize(st));
-        d_sem.swap(new_sem);
-        slot_key.swap(out_key);
-        slot_live.swap(out_live);
-        nb_partitions += (int64_t)distinct.size();
-        rebuild_live_and_upload(st, &new_slots_h);
+        P.d_sem.swap(new_sem);
+        P.slot_key.swap(out_key);
+        P.slot_live.swap(out_live);
+        P.nb_partitions += (int64_t)distinct.size();
+        P.rebuild_live_and_upload(st, &c.new_slots_h);
         // slots changed: look every op up again
         int64_t* cs = ws.cs.ensure(CS_WORDS);
         DSA_LAUNCH("colstat_init", k_colstat_init, 1, 1, 0, st, cs);
-        DSA_LAUNCH("col_lookup", k_col_lookup, gr, 256, 0, st, d_partkeys, (const int64_t*)nullptr, (const double*)nullptr, n, d_live_keys.p,
-                   d_live_slot.p, nlive(), keymap(), keymap_min, keymap_len, ws.op_slot.p, cs);
+        DSA_LAUNCH("col_lookup", k_col_lookup, gr, 256, 0, st, c.partkeys, (const int64_t*)nullptr, (const double*)nullptr, n,
+                   P.d_live_keys.p, P.d_live_slot.p, P.nlive(), P.keymap(), P.keymap_min, P.keymap_len, ws.op_slot.p, cs);
     }
-    const int64_t nnew = (int64_t)new_slots_h.size();
+}
+
+static void phase2_launch(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t st) {
+    const int64_t n = c.n;
+    const int64_t nnew = (int64_t)c.new_slots_h.size();
     const int64_t ntot = n + nnew;
     int32_t* d_new = ws.new_slots.ensure((size_t)nnew + 1);
-    if (nnew) DSA_CUDA(cudaMemcpyAsync(d_new, new_slots_h.data(), (size_t)nnew * 4, cudaMemcpyHostToDevice, st));
-    const int kb = std::max(1, bits_for((uint64_t)bs.maxkey));
-    const int pb = std::max(1, bits_for((uint64_t)std::max<int64_t>(nslots() - 1, 1)));
+    if (nnew) DSA_CUDA(cudaMemcpyAsync(d_new, c.new_slots_h.data(), (size_t)nnew * 4, cudaMemcpyHostToDevice, st));
+    const int kb = std::max(1, bits_for((uint64_t)c.bs.maxkey));
+    const int pb = std::max(1, bits_for((uint64_t)std::max<int64_t>(P.nslots() - 1, 1)));
     if (kb + pb > 64) throw DsaError{DSA_ERR_ARGUMENT, "key range too wide: bits(max in-array key) + bits(#partitions) must be <= 64"};
     uint64_t* sk = ws.sk.ensure((size_t)ntot);
     uint32_t* perm = ws.perm.ensure((size_t)ntot);
     const unsigned grt = grid_for(ntot, 256);
-    DSA_LAUNCH("make_sortkeys", k_make_sortkeys, grt, 256, 0, st, ws.op_slot.p, d_inkeys, n, d_new, nnew, kb, sk, perm);
+    DSA_LAUNCH("make_sortkeys", k_make_sortkeys, grt, 256, 0, st, ws.op_slot.p, c.inkeys, n, d_new, nnew, kb, sk, perm);
     radix_sort_pairs(ws.sort, sk, perm, ntot, kb + pb, st);
     int32_t* flag = ws.flag32.ensure((size_t)ntot);
     int32_t* uidx = ws.idx32.ensure((size_t)ntot);
@@ -111,12 +128,32 @@ void Pcsr::set_batch_d(PcsrWorkspace& ws, const int64_t* d_inkeys, const int64_t
     int32_t* u_pid = ws.u_pid.ensure((size_t)ntot);
     int64_t* u_key = ws.u_key.ensure((size_t)ntot);
     double* u_val = ws.u_val.ensure((size_t)ntot);
-    DSA_LAUNCH("gather_unique_ops", k_gather_unique_ops, grt, 256, 0, st, sk, perm, flag, uidx, ntot, n, kb, d_inkeys, d_vals, u_pid, u_key,
-               u_val);
-    if (nnew) DSA_CUDA(cudaStreamSynchronize(st));   // new_slots_h is read by the async copy above
-    pma.apply_sorted_ops(ws.batch, u_pid, u_key, u_val, ntot, d_sem.p, d_next_slot.p, st, false, nuniq_dev);
-    if (bs.maxkey > max_inkey) max_inkey = bs.maxkey;
-    if (nnew) rebuild_live_and_upload(st);   // the new partitions are placed now: they end the spans before them
+    DSA_LAUNCH("gather_unique_ops", k_gather_unique_ops, grt, 256, 0, st, sk, perm, flag, uidx, ntot, n, kb, c.inkeys, c.vals, u_pid,
+               u_key, u_val);
+    P.pma.apply_sorted_ops(ws.batch, u_pid, u_key, u_val, ntot, P.d_sem.p, P.d_next_slot.p, st, false, nuniq_dev, /*launch_only=*/true);
+}
+
+static void phase3(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t st) {
+    P.pma.rebalance_finish(ws.batch, P.d_sem.p, st);
+    if (c.bs.maxkey > P.max_inkey) P.max_inkey = c.bs.maxkey;
+    if (!c.new_slots_h.empty()) P.rebuild_live_and_upload(st);   // the new partitions are placed now: they end the spans before them
+}
+
+void Pcsr::set_batch_d(PcsrWorkspace& ws, const int64_t* d_inkeys, const int64_t* d_partkeys, const double* d_vals, int64_t n,
+                       int64_t* max_part_nz, int64_t* max_key_nz, cudaStream_t st) {
+    if (n <= 0) return;
+    BatchCtx c;
+    c.inkeys = d_inkeys; c.partkeys = d_partkeys; c.vals = d_vals; c.n = n;
+    phase1_launch(*this, ws, c, st);
+    DSA_CUDA(cudaStreamSynchronize(st));
+    phase1_read(ws, c);
+    if (c.bs.minkey < 1) throw DsaError{DSA_ERR_ARGUMENT, "in-array keys must be >= 1 (key 0 is the semaphore key, pcsr.jl:23)"};
+    if (max_part_nz) *max_part_nz = c.bs.maxpart_nz;
+    if (max_key_nz) *max_key_nz = c.bs.maxkey_nz;
+    phase1_finish(*this, ws, c, st);
+    phase2_launch(*this, ws, c, st);
+    DSA_CUDA(cudaStreamSynchronize(st));
+    phase3(*this, ws, c, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -160,7 +197,7 @@ struct dsa_vec {
 struct dsa_matrix {
     Pcsr colmajor, rowmajor;   // matrix.jl:6-7
     int64_t m = 0, n = 0;      // matrix.jl:2-3
-    PcsrWorkspace ws;
+    PcsrWorkspace ws, ws2;     // ws2: batch scratch of the row-major twin (both orientations are in flight together)
     Staging stg;
     StreamHolder sh;
     DBuf<int32_t> d_slots;
@@ -290,22 +327,26 @@ static void vec_set_batch_dev(dsa_vec* v, const int64_t* d_keys, const double* d
 static void matrix_set_batch_dev(dsa_matrix* A, const int64_t* d_rows, const int64_t* d_cols, const double* d_vals, int64_t n) {
     if (n <= 0) return;
     cudaStream_t st = A->sh.st;
-    // validate before mutate: both orientations need in-array keys >= 1 (rows for col-major, columns for row-major)
-    {
-        int64_t* mm = A->ws.cs.ensure(CS_WORDS);
-        int64_t* hmm = A->ws.h_cs.ensure(CS_WORDS);
-        minmax_i64(d_rows, n, mm, st);
-        minmax_i64(d_cols, n, mm + 2, st);
-        DSA_CUDA(cudaMemcpyAsync(hmm, mm, 32, cudaMemcpyDeviceToHost, st));
-        DSA_CUDA(cudaStreamSynchronize(st));
-        if (hmm[0] < 1 || hmm[2] < 1)
-            throw DsaError{DSA_ERR_ARGUMENT, "row and column keys must be >= 1 (each is an in-array key of one orientation; key 0 is the semaphore key, pcsr.jl:23)"};
-    }
-    int64_t maxcol_nz = INT64_MIN, maxrow_nz = INT64_MIN;
-    A->colmajor.set_batch_d(A->ws, d_rows, d_cols, d_vals, n, &maxcol_nz, &maxrow_nz, st);   // colmajor[row, col] = v  (matrix.jl:53-55)
-    A->rowmajor.set_batch_d(A->ws, d_cols, d_rows, d_vals, n, nullptr, nullptr, st);         // rowmajor[col, row] = v  (matrix.jl:57-59)
-    if (maxrow_nz != INT64_MIN && maxrow_nz > A->m) A->m = maxrow_nz;                        // matrix.jl:44-47
-    if (maxcol_nz != INT64_MIN && maxcol_nz > A->n) A->n = maxcol_nz;
+    BatchCtx cc, cr;
+    cc.inkeys = d_rows; cc.partkeys = d_cols; cc.vals = d_vals; cc.n = n;   // colmajor[row, col] = v  (matrix.jl:53-55)
+    cr.inkeys = d_cols; cr.partkeys = d_rows; cr.vals = d_vals; cr.n = n;   // rowmajor[col, row] = v  (matrix.jl:57-59)
+    phase1_launch(A->colmajor, A->ws, cc, st);
+    phase1_launch(A->rowmajor, A->ws2, cr, st);
+    DSA_CUDA(cudaStreamSynchronize(st));
+    phase1_read(A->ws, cc);
+    phase1_read(A->ws2, cr);
+    // validate before mutate: rows are the in-array keys of the col-major structure, columns those of the row-major one
+    if (cc.bs.minkey < 1 || cr.bs.minkey < 1)
+        throw DsaError{DSA_ERR_ARGUMENT, "row and column keys must be >= 1 (each is an in-array key of one orientation; key 0 is the semaphore key, pcsr.jl:23)"};
+    phase1_finish(A->colmajor, A->ws, cc, st);
+    phase1_finish(A->rowmajor, A->ws2, cr, st);
+    phase2_launch(A->colmajor, A->ws, cc, st);
+    phase2_launch(A->rowmajor, A->ws2, cr, st);
+    DSA_CUDA(cudaStreamSynchronize(st));
+    phase3(A->colmajor, A->ws, cc, st);
+    phase3(A->rowmajor, A->ws2, cr, st);
+    if (cc.bs.maxkey_nz != INT64_MIN && cc.bs.maxkey_nz > A->m) A->m = cc.bs.maxkey_nz;     // matrix.jl:44-47
+    if (cc.bs.maxpart_nz != INT64_MIN && cc.bs.maxpart_nz > A->n) A->n = cc.bs.maxpart_nz;
 }
 
 static void matrix_delete(dsa_matrix* A, bool rows, const int64_t* ids, int64_t n) {

@@ -801,15 +801,22 @@ struct PmaCore {
     // + touched.  Builds the density tree, selects windows, merges/redistributes, resizes when the root fails.
     // d_sem (nullable) = semaphore positions to refresh.  Returns through nnz.
     void rebalance_after(BatchWorkspace& ws, int64_t nins, int64_t* d_sem, cudaStream_t st) {
+        rebalance_launch(ws, st);
+        DSA_CUDA(cudaStreamSynchronize(st));
+        rebalance_finish(ws, d_sem, st);
+        (void)nins;
+    }
+
+    // first half: density tree + window selection + status read-back (enqueued; the caller synchronises the stream)
+    void rebalance_launch(BatchWorkspace& ws, cudaStream_t st) {
         Levels L = levels();
         const int64_t nsegs = g.nb_segments;
         int32_t* post = ws.post.ensure((size_t)tree_size());
         uint8_t* mark = ws.mark;
         int64_t* status = ws.status;
-        uint8_t* cover = ws.cover;
         int32_t* hi_h = ws.hi_h.ensure((size_t)nsegs + 1);
         int64_t* hi_w = ws.hi_w.ensure((size_t)nsegs + 1);
-        uint8_t* hi_max = ws.hi_max.ensure((size_t)nsegs + 1);
+        ws.hi_max.ensure((size_t)nsegs + 1);
         DSA_LAUNCH("tree_low", k_tree_low, grid_for(nsegs, 1024), 1024, 0, st, leafcnt.p, ws.inscnt, post, L);
         if (L.H > 10) DSA_LAUNCH("tree_high", k_tree_high, 1, 1024, 0, st, post, L);
         DSA_LAUNCH("select_windows", k_select_windows, grid_for(nsegs, 256), 256, 0, st, ws.touched, post, mark, L, status, hi_h, hi_w);
@@ -817,7 +824,19 @@ struct PmaCore {
         DSA_CUDA(cudaMemcpyAsync(status + ST_ROOT, post + L.off[L.H], sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
         int64_t* hs = ws.h_status.ensure(ST_WORDS);
         DSA_CUDA(cudaMemcpyAsync(hs, status, ST_WORDS * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-        DSA_CUDA(cudaStreamSynchronize(st));
+    }
+
+    // second half (after the stream was synchronised): merges / redistributes, resizes when the root failed
+    void rebalance_finish(BatchWorkspace& ws, int64_t* d_sem, cudaStream_t st) {
+        Levels L = levels();
+        const int64_t nsegs = g.nb_segments;
+        int32_t* post = ws.post.p;
+        uint8_t* mark = ws.mark;
+        uint8_t* cover = ws.cover;
+        int32_t* hi_h = ws.hi_h.p;
+        int64_t* hi_w = ws.hi_w.p;
+        uint8_t* hi_max = ws.hi_max.p;
+        int64_t* hs = ws.h_status.p;
         const int64_t N = (int64_t)(int32_t)(hs[ST_ROOT] & 0xffffffff);
         MergeArgs A;
         memset(&A, 0, sizeof(A));
@@ -871,7 +890,6 @@ struct PmaCore {
             }
         }
         nnz = N;
-        (void)nins;
     }
 
     void prepare_batch_scratch(BatchWorkspace& ws, int64_t nops, cudaStream_t st) {
@@ -898,10 +916,9 @@ struct PmaCore {
     // sorted unique ops -> located, applied, merged.  op_pid/sem/next_sem nullable (plain PMA).
     void apply_sorted_ops(BatchWorkspace& ws, const int32_t* op_pid, const int64_t* op_key, const double* op_val, int64_t nops,
                           int64_t* d_sem, const int32_t* d_next_slot, cudaStream_t st, bool scratch_ready = false,
-                          const int64_t* n_dev = nullptr) {
+                          const int64_t* n_dev = nullptr, bool launch_only = false) {
         if (!scratch_ready) prepare_batch_scratch(ws, nops, st);
         const int lgS = ilog2_i64(g.segment_capacity);
-        int64_t nins = 0;
         if (nops > 0) {
             const unsigned gr = grid_for(nops, 256);
             DSA_LAUNCH("locate", k_locate, gr, 256, 0, st, keys.p, g.capacity, op_pid, op_key, op_val, nops, d_sem, d_next_slot,
@@ -917,7 +934,11 @@ struct PmaCore {
             DSA_LAUNCH("insert_leaf_info", k_insert_leaf_info, gr, 256, 0, st, ws.ins_pos.p, ws.status + ST_NINS, ws.inscnt,
                        ws.ins_first.p, ws.touched, lgS, ws.act.ensure((size_t)std::min<int64_t>(nops, g.nb_segments) + 1), ws.status + ST_NACT);
         }
-        rebalance_after(ws, nins, d_sem, st);
+        rebalance_launch(ws, st);
+        if (!launch_only) {
+            DSA_CUDA(cudaStreamSynchronize(st));
+            rebalance_finish(ws, d_sem, st);
+        }
     }
 };
 
