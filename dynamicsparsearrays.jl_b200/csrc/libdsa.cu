@@ -17,8 +17,9 @@ static thread_local std::string g_last_error;
 // Pcsr::set_batch_d — batched setindex! of one orientation (pcsr.jl:341-347 per op), DESIGN.md §4
 // ---------------------------------------------------------------------------------------------
 struct BatchStats {
-    int64_t missing, minkey, maxkey, maxpart_nz, maxkey_nz, minpart;
+    int64_t missing, minkey, maxkey, maxpart_nz, maxkey_nz, minpart, maxbucket;
 };
+constexpr int64_t BUCKET_MAX = 256;   // largest per-partition bucket the quadratic in-bucket ranking is used for
 
 // One batched setindex! of one orientation, cut at its two host decisions so that the two orientations of a matrix can
 // share each stream synchronisation:
@@ -40,14 +41,18 @@ static void phase1_launch(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t 
     int64_t* cs = ws.cs.ensure(CS_WORDS);
     int64_t* hcs = ws.h_cs.ensure(CS_WORDS);
     DSA_LAUNCH("colstat_init", k_colstat_init, 1, 1, 0, st, cs);
+    const int64_t ns = P.nslots();
+    int32_t* bcnt = ws.bcnt.ensure((size_t)ns + 1);
+    int32_t* lidx = ws.lidx.ensure((size_t)c.n);
+    DSA_CUDA(cudaMemsetAsync(bcnt, 0, ((size_t)ns + 1) * 4, st));
     DSA_LAUNCH("col_lookup", k_col_lookup, grid_for(c.n, 256), 256, 0, st, c.partkeys, c.inkeys, c.vals, c.n, P.d_live_keys.p,
-               P.d_live_slot.p, P.nlive(), P.keymap(), P.keymap_min, P.keymap_len, op_slot, cs);
+               P.d_live_slot.p, P.nlive(), P.keymap(), P.keymap_min, P.keymap_len, op_slot, cs, bcnt, lidx);
     DSA_CUDA(cudaMemcpyAsync(hcs, cs, CS_WORDS * 8, cudaMemcpyDeviceToHost, st));
 }
 
 static void phase1_read(PcsrWorkspace& ws, BatchCtx& c) {
     const int64_t* hcs = ws.h_cs.p;
-    c.bs = BatchStats{hcs[CS_MISSING], hcs[CS_MINKEY], hcs[CS_MAXKEY], hcs[CS_MAXPART_NZ], hcs[CS_MAXKEY_NZ], hcs[CS_MINPART]};
+    c.bs = BatchStats{hcs[CS_MISSING], hcs[CS_MINKEY], hcs[CS_MAXKEY], hcs[CS_MAXPART_NZ], hcs[CS_MAXKEY_NZ], hcs[CS_MINPART], hcs[CS_MAXBUCKET]};
 }
 
 static void phase1_finish(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t st) {
@@ -102,7 +107,8 @@ static void phase1_finish(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t 
         int64_t* cs = ws.cs.ensure(CS_WORDS);
         DSA_LAUNCH("colstat_init", k_colstat_init, 1, 1, 0, st, cs);
         DSA_LAUNCH("col_lookup", k_col_lookup, gr, 256, 0, st, c.partkeys, (const int64_t*)nullptr, (const double*)nullptr, n,
-                   P.d_live_keys.p, P.d_live_slot.p, P.nlive(), P.keymap(), P.keymap_min, P.keymap_len, ws.op_slot.p, cs);
+                   P.d_live_keys.p, P.d_live_slot.p, P.nlive(), P.keymap(), P.keymap_min, P.keymap_len, ws.op_slot.p, cs,
+                   (int32_t*)nullptr, (int32_t*)nullptr);
     }
 }
 
@@ -118,8 +124,20 @@ static void phase2_launch(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t 
     uint64_t* sk = ws.sk.ensure((size_t)ntot);
     uint32_t* perm = ws.perm.ensure((size_t)ntot);
     const unsigned grt = grid_for(ntot, 256);
-    DSA_LAUNCH("make_sortkeys", k_make_sortkeys, grt, 256, 0, st, ws.op_slot.p, c.inkeys, n, d_new, nnew, kb, sk, perm);
-    radix_sort_pairs(ws.sort, sk, perm, ntot, kb + pb, st);
+    if (nnew == 0 && c.bs.missing == 0 && c.bs.maxbucket <= BUCKET_MAX) {
+        // every partition receives few ops: bucket by partition, rank inside the bucket
+        const int64_t ns = P.nslots();
+        int32_t* boff = ws.boff.ensure((size_t)ns + 1);
+        int64_t* bkey = ws.tmp_k.ensure((size_t)n);
+        uint32_t* barr = ws.barr.ensure((size_t)n);
+        int32_t* bslot = ws.bslot.ensure((size_t)n);
+        exclusive_scan_i32<int32_t>(ws.batch.scan, ws.bcnt.p, boff, ns, nullptr, st);
+        DSA_LAUNCH("bucket_scatter", k_bucket_scatter, grt, 256, 0, st, ws.op_slot.p, ws.lidx.p, c.inkeys, n, boff, bkey, barr, bslot);
+        DSA_LAUNCH("bucket_rank", k_bucket_rank, grt, 256, 0, st, bkey, barr, bslot, boff, ws.bcnt.p, n, kb, sk, perm);
+    } else {
+        DSA_LAUNCH("make_sortkeys", k_make_sortkeys, grt, 256, 0, st, ws.op_slot.p, c.inkeys, n, d_new, nnew, kb, sk, perm);
+        radix_sort_pairs(ws.sort, sk, perm, ntot, kb + pb, st);
+    }
     int32_t* flag = ws.flag32.ensure((size_t)ntot);
     int32_t* uidx = ws.idx32.ensure((size_t)ntot);
     int64_t* nuniq_dev = ws.nuniq.ensure(4) + 2;

@@ -13,7 +13,7 @@ namespace dsa {
 // (find(mpcsc.col_keys, col), pcsr.jl:342 — tombstones are kept out of the searched list instead of being skipped)
 // also reduces: #ops whose column is absent, min/max in-array key, max partition key / in-array key of non-zero writes
 // ---------------------------------------------------------------------------------------------
-enum { CS_MISSING = 0, CS_MINKEY = 1, CS_MAXKEY = 2, CS_MAXPART_NZ = 3, CS_MAXKEY_NZ = 4, CS_MINPART = 5, CS_WORDS = 8 };
+enum { CS_MISSING = 0, CS_MINKEY = 1, CS_MAXKEY = 2, CS_MAXPART_NZ = 3, CS_MAXKEY_NZ = 4, CS_MINPART = 5, CS_MAXBUCKET = 6, CS_WORDS = 8 };
 
 __global__ void k_colstat_init(int64_t* cs) {
     cs[CS_MISSING] = 0;
@@ -22,6 +22,7 @@ __global__ void k_colstat_init(int64_t* cs) {
     cs[CS_MAXPART_NZ] = INT64_MIN;
     cs[CS_MAXKEY_NZ] = INT64_MIN;
     cs[CS_MINPART] = INT64_MAX;
+    cs[CS_MAXBUCKET] = 0;
 }
 
 __device__ __forceinline__ int32_t live_lookup(const int64_t* __restrict__ live_keys, const int32_t* __restrict__ live_slot,
@@ -39,10 +40,12 @@ __global__ void __launch_bounds__(256) k_col_lookup(const int64_t* __restrict__ 
                                                      const double* __restrict__ vals, int64_t n,
                                                      const int64_t* __restrict__ live_keys, const int32_t* __restrict__ live_slot,
                                                      int64_t nlive, const int32_t* __restrict__ keymap, int64_t keymap_min,
-                                                     int64_t keymap_len, int32_t* __restrict__ op_slot, int64_t* __restrict__ cs) {
+                                                     int64_t keymap_len, int32_t* __restrict__ op_slot, int64_t* __restrict__ cs,
+                                                     int32_t* __restrict__ bcnt, int32_t* __restrict__ lidx) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t mink = INT64_MAX, maxk = INT64_MIN, maxp = INT64_MIN, maxknz = INT64_MIN, minp = INT64_MAX;
     int miss = 0;
+    int bmax = 0;
     if (i < n) {
         const int64_t pk = partkeys[i];
         minp = pk;
@@ -55,6 +58,11 @@ __global__ void __launch_bounds__(256) k_col_lookup(const int64_t* __restrict__ 
         }
         op_slot[i] = s;
         miss = s < 0;
+        if (bcnt && s >= 0) {   // bucket-sort bookkeeping: arrival-independent local index inside the partition's bucket
+            const int li = atomicAdd(&bcnt[s], 1);
+            lidx[i] = li;
+            bmax = li + 1;
+        }
         if (inkeys) {
             const int64_t k = inkeys[i];
             mink = maxk = k;
@@ -69,14 +77,17 @@ __global__ void __launch_bounds__(256) k_col_lookup(const int64_t* __restrict__ 
         a = __shfl_xor_sync(0xffffffffu, maxknz, o); maxknz = a > maxknz ? a : maxknz;
         a = __shfl_xor_sync(0xffffffffu, minp, o); minp = a < minp ? a : minp;
         miss += __shfl_xor_sync(0xffffffffu, miss, o);
+        const int b2 = __shfl_xor_sync(0xffffffffu, bmax, o);
+        bmax = b2 > bmax ? b2 : bmax;
     }
     // block-level combine, then one set of atomics per CTA
     __shared__ int64_t sh[5][8];
-    __shared__ int shm[8];
+    __shared__ int shm[8], shb[8];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane == 0) {
         sh[0][wid] = mink; sh[1][wid] = maxk; sh[2][wid] = maxp; sh[3][wid] = maxknz; sh[4][wid] = minp;
         shm[wid] = miss;
+        shb[wid] = bmax;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -87,7 +98,9 @@ __global__ void __launch_bounds__(256) k_col_lookup(const int64_t* __restrict__ 
             maxknz = sh[3][w] > maxknz ? sh[3][w] : maxknz;
             minp = sh[4][w] < minp ? sh[4][w] : minp;
             miss += shm[w];
+            bmax = shb[w] > bmax ? shb[w] : bmax;
         }
+        if (bmax) atomicMax((long long*)&cs[CS_MAXBUCKET], (long long)bmax);
         if (miss) atomicAdd((unsigned long long*)&cs[CS_MISSING], (unsigned long long)miss);
         if (mink != INT64_MAX) atomicMin((long long*)&cs[CS_MINKEY], (long long)mink);
         if (maxk != INT64_MIN) atomicMax((long long*)&cs[CS_MAXKEY], (long long)maxk);
@@ -138,6 +151,42 @@ __global__ void __launch_bounds__(256) k_make_sortkeys(const int32_t* __restrict
         idx[i] = (uint32_t)i;
     }
 }
+// ---------------------------------------------------------------------------------------------
+// Bucket path of K1 (batches whose partitions each receive few ops): ops are dropped into their partition's bucket
+// (offsets = exclusive scan of the per-partition counts taken during the column lookup), then every op ranks itself
+// inside its bucket by (key, arrival).  Same output as the radix sort — ops ordered by (partition, key), equal keys in
+// arrival order — in 3 small kernels instead of 5 passes over 64-bit keys.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bucket_scatter(const int32_t* __restrict__ op_slot, const int32_t* __restrict__ lidx,
+                                                         const int64_t* __restrict__ inkeys, int64_t n, const int32_t* __restrict__ boff,
+                                                         int64_t* __restrict__ bkey, uint32_t* __restrict__ barr, int32_t* __restrict__ bslot) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t s = op_slot[i];
+    const int64_t pos = (int64_t)boff[s] + lidx[i];
+    bkey[pos] = inkeys[i];
+    barr[pos] = (uint32_t)i;
+    bslot[pos] = s;
+}
+__global__ void __launch_bounds__(256) k_bucket_rank(const int64_t* __restrict__ bkey, const uint32_t* __restrict__ barr,
+                                                      const int32_t* __restrict__ bslot, const int32_t* __restrict__ boff,
+                                                      const int32_t* __restrict__ bcnt, int64_t n, int kb, uint64_t* __restrict__ sk,
+                                                      uint32_t* __restrict__ perm) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int32_t s = bslot[p];
+    const int64_t lo = boff[s], hi = lo + bcnt[s];
+    const int64_t key = bkey[p];
+    const uint32_t arr = barr[p];
+    int64_t r = lo;
+    for (int64_t q = lo; q < hi; ++q) {
+        const int64_t kq = bkey[q];
+        r += (kq < key) || (kq == key && barr[q] < arr);
+    }
+    sk[r] = ((uint64_t)(uint32_t)s << kb) | (uint64_t)key;
+    perm[r] = arr;
+}
+
 // plain PMA: sort key = key - min
 __global__ void __launch_bounds__(256) k_make_sortkeys_vec(const int64_t* __restrict__ keys, int64_t n, int64_t mink,
                                                             uint64_t* __restrict__ sk, uint32_t* __restrict__ idx) {
@@ -471,7 +520,8 @@ __global__ void __launch_bounds__(256) k_scatter_x(const int64_t* __restrict__ x
 struct PcsrWorkspace {
     BatchWorkspace batch;
     SortWorkspace sort;
-    DBuf<int32_t> op_slot, flag32, idx32, u_pid, new_slots, old2new, rank32, del_slots, cnt32;
+    DBuf<int32_t> op_slot, flag32, idx32, u_pid, new_slots, old2new, rank32, del_slots, cnt32, bcnt, boff, lidx, bslot;
+    DBuf<uint32_t> barr;
     DBuf<int64_t> miss_keys, cs, u_key, live_pos, nuniq, tmp_k, tmp_owner, del_keys;
     DBuf<double> u_val, tmp_v, yslot, carry, xdense;
     DBuf<uint64_t> sk;
@@ -580,7 +630,7 @@ struct Pcsr {
         int64_t* cs = ws.cs.ensure(CS_WORDS);
         DSA_LAUNCH("colstat_init", k_colstat_init, 1, 1, 0, st, cs);
         DSA_LAUNCH("col_lookup", k_col_lookup, grid_for(n, 256), 256, 0, st, d_partkeys, (const int64_t*)nullptr, (const double*)nullptr, n,
-                   d_live_keys.p, d_live_slot.p, nlive(), keymap(), keymap_min, keymap_len, op_slot, cs);
+                   d_live_keys.p, d_live_slot.p, nlive(), keymap(), keymap_min, keymap_len, op_slot, cs, (int32_t*)nullptr, (int32_t*)nullptr);
         DSA_LAUNCH("get", k_get, grid_for(n, 256), 256, 0, st, pma.keys.p, pma.vals.p, pma.g.capacity, op_slot, d_inkeys, n, d_sem.p,
                    d_next_slot.p, d_out);
     }

@@ -286,6 +286,26 @@ def test_matrix_batches(seed):
         assert np.array_equal(gm.get_batch(rq, cq), seq.get_many(rq, cq))
 
 
+def test_matrix_batch_duplicates_last_writer_wins():
+    """many writes to the same (i, j) inside one batch, on both sort paths: per-partition buckets (all columns exist, small
+    buckets) and radix sort (a hot column overflows the bucket limit / new columns appear)"""
+    rng = np.random.default_rng(31)
+    m, n = 60, 50
+    I, J, V = _rand_coo(rng, m, n, 1500)
+    for hot in (False, True):
+        gm, pol, seq = D.dynamicsparse(I, J, V), O.Matrix(I, J, V), O.Matrix(I, J, V)
+        for rnd in range(3):
+            nb = 6000
+            I2 = rng.integers(1, m + 1, nb)
+            J2 = rng.integers(1, n + 1, nb) if not hot else np.where(rng.random(nb) < 0.5, 7, rng.integers(1, n + 1, nb))
+            V2 = np.where(rng.random(nb) < 0.4, 0.0, rng.integers(1, 9, nb).astype(float))
+            gm.set_batch(I2, J2, V2)
+            pol.set_batch_policy(I2, J2, V2)
+            seq.set_many(I2, J2, V2)
+            assert_matrix_equal(gm, pol)
+            assert_matrix_equal(gm, seq, layout=False)
+
+
 def test_matrix_delete_columns_and_rows_bulk():
     rng = np.random.default_rng(11)
     I, J, V = _rand_coo(rng, 300, 400, 8000)
