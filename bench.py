@@ -206,7 +206,7 @@ def main():
 
     def step_dev(s):
         bi, bj, bv = d_batches[s]
-        D._lib.check(L.dsa_matrix_set_batch_d(A._h, vp(bi), vp(bj), vp(bv), C.c_int64(BATCH), C.c_int64(0), C.c_int64(0)))
+        D._lib.check(L.dsa_matrix_set_batch_d(A._h, vp(bi), vp(bj), vp(bv), C.c_int64(BATCH)))
         D._lib.check(L.dsa_matrix_spmv_dense_d(A._h, C.c_int(0), vp(d_x), C.c_int64(N_COLS), vp(d_y), C.c_int64(M_ROWS)))
 
     for s in range(W):
@@ -238,7 +238,7 @@ def main():
     # the extra batches delete the inserts of the batch generated before them, which was never applied: harmless no-ops
     for bi, bj, bv in extra:
         tb = (torch.from_numpy(bi).to(dev), torch.from_numpy(bj).to(dev), torch.from_numpy(bv).to(dev))
-        D._lib.check(L.dsa_matrix_set_batch_d(A._h, vp(tb[0]), vp(tb[1]), vp(tb[2]), C.c_int64(BATCH), C.c_int64(0), C.c_int64(0)))
+        D._lib.check(L.dsa_matrix_set_batch_d(A._h, vp(tb[0]), vp(tb[1]), vp(tb[2]), C.c_int64(BATCH)))
         D._lib.check(L.dsa_matrix_spmv_dense_d(A._h, C.c_int(0), vp(d_x), C.c_int64(N_COLS), vp(d_y), C.c_int64(M_ROWS)))
     torch.cuda.synchronize()
     L.dsa_prof_enable(C.c_int(0))

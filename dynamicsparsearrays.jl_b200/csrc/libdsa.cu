@@ -700,7 +700,7 @@ int dsa_matrix_set_batch(dsa_matrix_t* A, const int64_t* rows, const int64_t* co
     return DSA_OK;
     DSA_CATCH
 }
-int dsa_matrix_set_batch_d(dsa_matrix_t* A, const int64_t* d_rows, const int64_t* d_cols, const double* d_vals, int64_t n, int64_t, int64_t) {
+int dsa_matrix_set_batch_d(dsa_matrix_t* A, const int64_t* d_rows, const int64_t* d_cols, const double* d_vals, int64_t n) {
     DSA_TRY
     matrix_set_batch_dev(A, d_rows, d_cols, d_vals, n);
     return DSA_OK;
@@ -845,6 +845,55 @@ int dsa_matrix_export(dsa_matrix_t* A, int which, uint8_t* occupied, int64_t* ke
             col_live[s] = P.slot_live[(size_t)s];
         }
     }
+    return DSA_OK;
+    DSA_CATCH
+}
+
+// ---- sharded use ------------------------------------------------------------------------------------------------------
+int dsa_matrix_build_one(dsa_matrix_t* A, int which, const int64_t* inkeys, const int64_t* partkeys, const double* vals, int64_t n,
+                         int combine) {
+    DSA_TRY
+    cudaStream_t st = A->sh.st;
+    Pcsr& P = which == DSA_COLMAJOR ? A->colmajor : A->rowmajor;
+    int64_t* dk = h2d(A->stg.a, inkeys, n, st);
+    int64_t* dp = h2d(A->stg.b, partkeys, n, st);
+    double* dv = h2d(A->stg.v, vals, n, st);
+    P.build_coo_d(A->ws, dk, dp, dv, n, combine, st);
+    DSA_CUDA(cudaStreamSynchronize(st));
+    return DSA_OK;
+    DSA_CATCH
+}
+int dsa_matrix_set_batch_one_d(dsa_matrix_t* A, int which, const int64_t* d_inkeys, const int64_t* d_partkeys, const double* d_vals,
+                               int64_t n) {
+    DSA_TRY
+    Pcsr& P = which == DSA_COLMAJOR ? A->colmajor : A->rowmajor;
+    P.set_batch_d(which == DSA_COLMAJOR ? A->ws : A->ws2, d_inkeys, d_partkeys, d_vals, n, nullptr, nullptr, A->sh.st);
+    return DSA_OK;
+    DSA_CATCH
+}
+}  // extern "C"
+namespace dsa {
+__global__ void __launch_bounds__(256) k_spmv_to_dense_range(const double* __restrict__ yslot, const int64_t* __restrict__ sem,
+                                                              const int64_t* __restrict__ slot_key, int64_t nslots, double* __restrict__ y,
+                                                              int64_t key_lo, int64_t key_hi) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nslots || sem[s] < 0) return;
+    const int64_t k = slot_key[s];
+    if (k >= key_lo && k < key_hi) y[k - key_lo] = yslot[s];
+}
+}  // namespace dsa
+extern "C" {
+int dsa_matrix_spmv_dense_range_d(dsa_matrix_t* A, int trans, const double* d_x, int64_t nx, double* d_y, int64_t key_lo,
+                                  int64_t key_hi) {
+    DSA_TRY
+    cudaStream_t st = A->sh.st;
+    Pcsr& P = trans ? A->colmajor : A->rowmajor;
+    if (key_hi > key_lo) DSA_CUDA(cudaMemsetAsync(d_y, 0, (size_t)(key_hi - key_lo) * 8, st));
+    matrix_spmv_slots(A, trans, d_x, nullptr, nx);
+    const int64_t ns = P.nslots();
+    if (ns > 0)
+        DSA_LAUNCH("spmv_to_dense", k_spmv_to_dense_range, grid_for(ns, 256), 256, 0, st, A->ws.yslot.p, P.d_sem.p, P.d_slot_key.p, ns, d_y,
+                   key_lo, key_hi);
     return DSA_OK;
     DSA_CATCH
 }

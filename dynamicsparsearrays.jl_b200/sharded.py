@@ -1,0 +1,150 @@
+"""Column-range sharding of a DynamicSparseMatrix across the GPUs of one box.
+
+One process per GPU.  Rank r owns the column-major PCSR of the columns in ``col_split[r] .. col_split[r+1]-1`` and the
+row-major PCSR of the rows in ``row_split[r] .. row_split[r+1]-1``.  A batch of logical updates ``A[i, j] = v`` is therefore
+routed twice — to owner(j) for the column-major structure, to owner(i) for the row-major one — with one stable partition
+by owner (``dsa_route_batch_d``, on the device) and one ``all_to_all_single`` per array over NCCL.  ``A * x`` is computed
+from the row-major shards (each rank produces its own slice of y, written straight into the all-gather buffer);
+``transpose(A) * x`` uses the column-major shards.  No other collective exists on the path.
+
+The local structure is a ``LocalBackend`` (libdsa on the GPU).  The routing / exchange logic is backend-agnostic so that
+``tests/test_sharded_gloo.py`` can drive it on CPU tensors over gloo with the oracle as the per-rank checker.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import check, lib
+
+
+def even_splitters(n_keys, world):
+    """split[r] = first key owned by rank r (keys are 1-based); split[world] = n_keys + 1."""
+    per = -(-n_keys // world)
+    return [1 + r * per for r in range(world)] + [max(n_keys, per * world) + 1]
+
+
+def owner_of(keys, split):
+    """owner(key) = number of interior splitters <= key."""
+    inner = np.asarray(split[1:-1], dtype=np.int64)
+    return np.searchsorted(inner, np.asarray(keys, dtype=np.int64), side="right")
+
+
+class LibdsaBackend:
+    """The per-rank structure on the GPU: one dsa_matrix handle whose two orientations are updated independently."""
+
+    def __init__(self, device):
+        self.device = device
+        self.h = C.c_void_p()
+        check(lib().dsa_matrix_create(C.byref(self.h)))
+        check(lib().dsa_matrix_set_stream(self.h, C.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().dsa_matrix_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def build(self, which, inkeys, partkeys, vals):
+        inkeys, partkeys, vals = (np.ascontiguousarray(a) for a in (inkeys, partkeys, vals))
+        check(lib().dsa_matrix_build_one(self.h, C.c_int(which), C.c_void_p(inkeys.ctypes.data), C.c_void_p(partkeys.ctypes.data),
+                                         C.c_void_p(vals.ctypes.data), C.c_int64(len(vals)), C.c_int(0)))
+
+    def set_batch(self, which, inkeys, partkeys, vals):
+        n = inkeys.numel()
+        if n:
+            check(lib().dsa_matrix_set_batch_one_d(self.h, C.c_int(which), C.c_void_p(inkeys.data_ptr()), C.c_void_p(partkeys.data_ptr()),
+                                                   C.c_void_p(vals.data_ptr()), C.c_int64(n)))
+
+    def spmv_range(self, trans, x, y_slice, key_lo, key_hi):
+        check(lib().dsa_matrix_spmv_dense_range_d(self.h, C.c_int(1 if trans else 0), C.c_void_p(x.data_ptr()), C.c_int64(x.numel()),
+                                                  C.c_void_p(y_slice.data_ptr()), C.c_int64(key_lo), C.c_int64(key_hi)))
+
+    def info(self, which):
+        out = np.zeros(10, np.int64)
+        check(lib().dsa_matrix_info(self.h, C.c_int(which), C.c_void_p(out.ctypes.data)))
+        return dict(capacity=int(out[0]), nb_elements=int(out[3]), nb_partitions=int(out[5]), nnz=int(out[9]))
+
+
+def route(route_keys, rows, cols, vals, split, world):
+    """Stable partition of a batch by owner(route_keys).  Returns (rows, cols, vals) in rank order + per-rank counts."""
+    n = rows.numel()
+    if rows.is_cuda:
+        orows, ocols, ovals = torch.empty_like(rows), torch.empty_like(cols), torch.empty_like(vals)
+        counts = np.zeros(world, np.int64)
+        inner = np.asarray(split[1:-1], dtype=np.int64)
+        check(lib().dsa_route_batch_d(C.c_void_p(route_keys.data_ptr()), C.c_void_p(rows.data_ptr()), C.c_void_p(cols.data_ptr()),
+                                      C.c_void_p(vals.data_ptr()), C.c_int64(n), C.c_void_p(inner.ctypes.data), C.c_int(world),
+                                      C.c_void_p(orows.data_ptr()), C.c_void_p(ocols.data_ptr()), C.c_void_p(ovals.data_ptr()),
+                                      C.c_void_p(counts.ctypes.data), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return orows, ocols, ovals, counts.tolist()
+    own = owner_of(route_keys.numpy(), split)
+    order = np.argsort(own, kind="stable")
+    counts = np.bincount(own, minlength=world).tolist()
+    idx = torch.from_numpy(order)
+    return rows[idx], cols[idx], vals[idx], counts
+
+
+def exchange(arrays, send_counts, group=None):
+    """all-to-all of the routed arrays: counts first (one small all_to_all), then one all_to_all_single per array."""
+    world = dist.get_world_size(group)
+    dev = arrays[0].device
+    sc = torch.tensor(send_counts, dtype=torch.int64, device=dev)
+    rc = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_to_all_single(rc, sc, group=group)
+    recv_counts = rc.tolist()
+    out = []
+    for a in arrays:
+        r = torch.empty(int(sum(recv_counts)), dtype=a.dtype, device=dev)
+        dist.all_to_all_single(r, a.contiguous(), output_split_sizes=recv_counts, input_split_sizes=list(send_counts), group=group)
+        out.append(r)
+    return out, recv_counts
+
+
+class ShardedMatrix:
+    def __init__(self, m, n, backend, group=None):
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.m, self.n = int(m), int(n)
+        self.row_split = even_splitters(self.m, self.world)
+        self.col_split = even_splitters(self.n, self.world)
+        self.local = backend
+        self.rows_per = self.row_split[1] - self.row_split[0]
+        self.cols_per = self.col_split[1] - self.col_split[0]
+
+    # rank-local key ranges
+    def my_rows(self):
+        return self.row_split[self.rank], min(self.row_split[self.rank + 1], self.m + 1)
+
+    def my_cols(self):
+        return self.col_split[self.rank], min(self.col_split[self.rank + 1], self.n + 1)
+
+    def set_batch(self, rows, cols, vals):
+        """rows/cols/vals: this rank's share of the global batch (tensors on the shard's device)."""
+        # column-major structure lives with owner(col)
+        r1, c1, v1, cnt = route(cols, rows, cols, vals, self.col_split, self.world)
+        (r1, c1, v1), _ = exchange([r1, c1, v1], cnt, self.group)
+        self.local.set_batch(_lib.COLMAJOR, r1, c1, v1)          # in-array key = row, partition key = col
+        # row-major structure lives with owner(row)
+        r2, c2, v2, cnt = route(rows, rows, cols, vals, self.row_split, self.world)
+        (r2, c2, v2), _ = exchange([r2, c2, v2], cnt, self.group)
+        self.local.set_batch(_lib.ROWMAJOR, c2, r2, v2)          # in-array key = col, partition key = row
+
+    def spmv(self, x, trans=False):
+        """y = A * x (trans=False, x of length n) or transpose(A) * x; x replicated on every rank, y returned replicated."""
+        per = self.cols_per if trans else self.rows_per
+        lo = (self.col_split if trans else self.row_split)[self.rank]
+        y = torch.zeros(per * self.world, dtype=torch.float64, device=x.device)
+        y_slice = y[self.rank * per:(self.rank + 1) * per]
+        self.local.spmv_range(trans, x, y_slice, lo, lo + per)   # epilogue writes this rank's slice of the gather buffer
+        if y.is_cuda:
+            dist.all_gather_into_tensor(y, y_slice, group=self.group)      # in place: the slice already sits at its offset
+        else:                                                              # gloo (CPU tests)
+            parts = [torch.empty(per, dtype=torch.float64) for _ in range(self.world)]
+            dist.all_gather(parts, y_slice.clone(), group=self.group)
+            y = torch.cat(parts)
+        return y[: (self.n if trans else self.m)]

@@ -110,8 +110,7 @@ int dsa_matrix_set_stream(dsa_matrix_t* A, void* cuda_stream);
 /* batched setindex! (matrix.jl:43-62 -> pcsr.jl:341-347 twice): LWW, 0.0 deletes, absent rows/columns are created
  * (addcolumn!, pcsr.jl:148-169), m/n grow on non-zeros. In-array keys must be >= 1 (key 0 is the semaphore key, pcsr.jl:23). */
 int dsa_matrix_set_batch(dsa_matrix_t* A, const int64_t* rows, const int64_t* cols, const double* vals, int64_t n);
-int dsa_matrix_set_batch_d(dsa_matrix_t* A, const int64_t* d_rows, const int64_t* d_cols, const double* d_vals, int64_t n,
-                           int64_t max_row, int64_t max_col);
+int dsa_matrix_set_batch_d(dsa_matrix_t* A, const int64_t* d_rows, const int64_t* d_cols, const double* d_vals, int64_t n);
 /* batched getindex (matrix.jl:64-68 -> pcsr.jl:261-267); which = orientation to read (both hold the same values) */
 int dsa_matrix_get_batch(dsa_matrix_t* A, int which, const int64_t* rows, const int64_t* cols, int64_t n, double* out);
 /* deletecolumn! / deleterow! for a list (matrix.jl:95-111 -> pcsr.jl:188-212, writes.jl:80-92); DSA_ERR_ARGUMENT if one is absent */
@@ -133,6 +132,18 @@ int dsa_matrix_info(const dsa_matrix_t* A, int which, int64_t* out10);
 /* raw layout dump: occupied/keys/vals[capacity], semaphores[len] (1-based position, 0 = nothing), col_keys[len], col_live[len] */
 int dsa_matrix_export(dsa_matrix_t* A, int which, uint8_t* occupied, int64_t* keys, double* vals, int64_t* semaphores,
                       int64_t* col_keys, uint8_t* col_live);
+
+/* ---------------------------------------------------------------- sharded use (one orientation at a time) ---- */
+/* A rank of a column-range-sharded matrix owns the col-major structure of ITS columns and the row-major structure of ITS rows
+ * (SURVEY.md §8e), so the two orientations of its handle receive different op sets.  in-array keys / partition keys are
+ * (rows, cols) for DSA_COLMAJOR and (cols, rows) for DSA_ROWMAJOR. */
+int dsa_matrix_build_one(dsa_matrix_t* A, int which, const int64_t* inkeys, const int64_t* partkeys, const double* vals, int64_t n,
+                         int combine);
+int dsa_matrix_set_batch_one_d(dsa_matrix_t* A, int which, const int64_t* d_inkeys, const int64_t* d_partkeys, const double* d_vals,
+                               int64_t n);
+/* y[k - key_lo] = (row-major if trans == 0, else col-major) partition k times x, for key_lo <= k < key_hi; other entries 0 */
+int dsa_matrix_spmv_dense_range_d(dsa_matrix_t* A, int trans, const double* d_x, int64_t nx, double* d_y, int64_t key_lo,
+                                  int64_t key_hi);
 
 /* ---------------------------------------------------------------- multi-GPU routing ---- */
 /* owner(key) = number of splitters <= key (rank r owns keys in [splitter[r-1], splitter[r])). Stable partition of a device batch by
