@@ -27,6 +27,9 @@ def main_dist(args, rank, world, local_rank):
     import dsa_b200 as D
     from dsa_b200.sharded import LibdsaBackend, ShardedMatrix
 
+    # stdout carries exactly ONE JSON line: everything else (NCCL banners, warnings) goes to stderr
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     D.lib().dsa_set_device(C.c_int(local_rank))
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -62,13 +65,13 @@ def main_dist(args, rank, world, local_rank):
         A.set_batch(*d_sh[s])
         return A.spmv(d_x)
 
+    sampler = B.ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()   # samples every 100 ms from the warm-up to the end of the e2e loop (the timed regions are ~10 ms each)
     for s in range(W):
         y = step_dev(s)
     torch.cuda.synchronize()
     dist.barrier()
-    sampler = B.ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
     launches0 = L.dsa_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -82,7 +85,6 @@ def main_dist(args, rank, world, local_rank):
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     launches = L.dsa_launch_count() - launches0
-    clocks = sampler.stop() if sampler else None
     ms_step = float(ms.item()) / K
     value = B.BATCH * world / (ms_step * 1e-3) / 1e6
     checksum = float(y.sum().item())
@@ -109,6 +111,7 @@ def main_dist(args, rank, world, local_rank):
     wall = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     dist.all_reduce(wall, op=dist.ReduceOp.MAX)
     ms_e2e = 1e3 * float(wall.item()) / K
+    clocks = sampler.stop() if sampler else None
     e2e = {"value": B.BATCH * world / (ms_e2e * 1e-3) / 1e6, "unit": "Mupdates/s", "h2d_bytes_per_step": (24 * B.BATCH + 8 * n) * world,
            "d2h_bytes_per_step": 8 * m * world, "ms_per_step": ms_e2e, "checksum": float(yh.sum().item())}
 
@@ -138,10 +141,12 @@ def main_dist(args, rank, world, local_rank):
         cfg["workload"] = (f"C4-style weak scaling: PCSR {m} x {n}, {nnz_block * world * world} nnz sharded by column range over {world} GPUs; "
                            f"step = {B.BATCH * world} updates routed to both orientations (NCCL all-to-all) + SpMV with all-gather")
         cfg.update(rows=m, cols=n, nnz=nnz_block * world * world, batch=B.BATCH * world)
+        os.dup2(saved_stdout, 1)
         print(json.dumps({
             "metric": "batched PCSR insert/delete Mupdates/s", "value": value, "unit": "Mupdates/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int64 keys / f64 values", "data": "synthetic", "config": cfg, "clocks": clocks, "e2e": e2e,
             "gpu_launches": int(launches), "roofline": spmv, "spmv": spmv, "cpu_baseline": None, "checksum": checksum,
-            "shard_nnz_rank0": inf["nnz"]}))
+            "shard_nnz_rank0": inf["nnz"]}), flush=True)
+        os.dup2(2, 1)
     dist.destroy_process_group()

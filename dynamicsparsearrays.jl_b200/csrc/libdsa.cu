@@ -342,29 +342,38 @@ static void vec_set_batch_dev(dsa_vec* v, const int64_t* d_keys, const double* d
 }
 
 // ---- matrix helpers -----------------------------------------------------------------------------------------------
-static void matrix_set_batch_dev(dsa_matrix* A, const int64_t* d_rows, const int64_t* d_cols, const double* d_vals, int64_t n) {
-    if (n <= 0) return;
+// The two orientations go through the batch phases together so that they share each stream synchronisation.  A plain matrix
+// batch feeds both with the same triples; a shard of a distributed matrix feeds them different ones.
+static void matrix_set_batch_two(dsa_matrix* A, const int64_t* rows_c, const int64_t* cols_c, const double* vals_c, int64_t nc,
+                                 const int64_t* rows_r, const int64_t* cols_r, const double* vals_r, int64_t nr) {
     cudaStream_t st = A->sh.st;
     BatchCtx cc, cr;
-    cc.inkeys = d_rows; cc.partkeys = d_cols; cc.vals = d_vals; cc.n = n;   // colmajor[row, col] = v  (matrix.jl:53-55)
-    cr.inkeys = d_cols; cr.partkeys = d_rows; cr.vals = d_vals; cr.n = n;   // rowmajor[col, row] = v  (matrix.jl:57-59)
-    phase1_launch(A->colmajor, A->ws, cc, st);
-    phase1_launch(A->rowmajor, A->ws2, cr, st);
+    cc.inkeys = rows_c; cc.partkeys = cols_c; cc.vals = vals_c; cc.n = nc;   // colmajor[row, col] = v  (matrix.jl:53-55)
+    cr.inkeys = cols_r; cr.partkeys = rows_r; cr.vals = vals_r; cr.n = nr;   // rowmajor[col, row] = v  (matrix.jl:57-59)
+    if (nc > 0) phase1_launch(A->colmajor, A->ws, cc, st);
+    if (nr > 0) phase1_launch(A->rowmajor, A->ws2, cr, st);
     DSA_CUDA(cudaStreamSynchronize(st));
-    phase1_read(A->ws, cc);
-    phase1_read(A->ws2, cr);
+    if (nc > 0) phase1_read(A->ws, cc);
+    if (nr > 0) phase1_read(A->ws2, cr);
     // validate before mutate: rows are the in-array keys of the col-major structure, columns those of the row-major one
-    if (cc.bs.minkey < 1 || cr.bs.minkey < 1)
+    if ((nc > 0 && cc.bs.minkey < 1) || (nr > 0 && cr.bs.minkey < 1))
         throw DsaError{DSA_ERR_ARGUMENT, "row and column keys must be >= 1 (each is an in-array key of one orientation; key 0 is the semaphore key, pcsr.jl:23)"};
-    phase1_finish(A->colmajor, A->ws, cc, st);
-    phase1_finish(A->rowmajor, A->ws2, cr, st);
-    phase2_launch(A->colmajor, A->ws, cc, st);
-    phase2_launch(A->rowmajor, A->ws2, cr, st);
+    if (nc > 0) phase1_finish(A->colmajor, A->ws, cc, st);
+    if (nr > 0) phase1_finish(A->rowmajor, A->ws2, cr, st);
+    if (nc > 0) phase2_launch(A->colmajor, A->ws, cc, st);
+    if (nr > 0) phase2_launch(A->rowmajor, A->ws2, cr, st);
     DSA_CUDA(cudaStreamSynchronize(st));
-    phase3(A->colmajor, A->ws, cc, st);
-    phase3(A->rowmajor, A->ws2, cr, st);
-    if (cc.bs.maxkey_nz != INT64_MIN && cc.bs.maxkey_nz > A->m) A->m = cc.bs.maxkey_nz;     // matrix.jl:44-47
-    if (cc.bs.maxpart_nz != INT64_MIN && cc.bs.maxpart_nz > A->n) A->n = cc.bs.maxpart_nz;
+    if (nc > 0) phase3(A->colmajor, A->ws, cc, st);
+    if (nr > 0) phase3(A->rowmajor, A->ws2, cr, st);
+    // matrix.jl:44-47: dimensions grow on non-zero writes
+    if (nc > 0 && cc.bs.maxkey_nz != INT64_MIN && cc.bs.maxkey_nz > A->m) A->m = cc.bs.maxkey_nz;
+    if (nc > 0 && cc.bs.maxpart_nz != INT64_MIN && cc.bs.maxpart_nz > A->n) A->n = cc.bs.maxpart_nz;
+    if (nr > 0 && cr.bs.maxpart_nz != INT64_MIN && cr.bs.maxpart_nz > A->m) A->m = cr.bs.maxpart_nz;
+    if (nr > 0 && cr.bs.maxkey_nz != INT64_MIN && cr.bs.maxkey_nz > A->n) A->n = cr.bs.maxkey_nz;
+}
+static void matrix_set_batch_dev(dsa_matrix* A, const int64_t* d_rows, const int64_t* d_cols, const double* d_vals, int64_t n) {
+    if (n <= 0) return;
+    matrix_set_batch_two(A, d_rows, d_cols, d_vals, n, d_rows, d_cols, d_vals, n);
 }
 
 static void matrix_delete(dsa_matrix* A, bool rows, const int64_t* ids, int64_t n) {
@@ -868,6 +877,14 @@ int dsa_matrix_set_batch_one_d(dsa_matrix_t* A, int which, const int64_t* d_inke
     DSA_TRY
     Pcsr& P = which == DSA_COLMAJOR ? A->colmajor : A->rowmajor;
     P.set_batch_d(which == DSA_COLMAJOR ? A->ws : A->ws2, d_inkeys, d_partkeys, d_vals, n, nullptr, nullptr, A->sh.st);
+    return DSA_OK;
+    DSA_CATCH
+}
+int dsa_matrix_set_batch_two_d(dsa_matrix_t* A, const int64_t* d_rows_c, const int64_t* d_cols_c, const double* d_vals_c, int64_t nc,
+                               const int64_t* d_rows_r, const int64_t* d_cols_r, const double* d_vals_r, int64_t nr) {
+    DSA_TRY
+    if (nc <= 0 && nr <= 0) return DSA_OK;
+    matrix_set_batch_two(A, d_rows_c, d_cols_c, d_vals_c, nc, d_rows_r, d_cols_r, d_vals_r, nr);
     return DSA_OK;
     DSA_CATCH
 }

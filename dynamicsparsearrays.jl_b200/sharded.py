@@ -60,6 +60,13 @@ class LibdsaBackend:
             check(lib().dsa_matrix_set_batch_one_d(self.h, C.c_int(which), C.c_void_p(inkeys.data_ptr()), C.c_void_p(partkeys.data_ptr()),
                                                    C.c_void_p(vals.data_ptr()), C.c_int64(n)))
 
+    def set_batch_two(self, col_triple, row_triple):
+        """col_triple / row_triple = (rows, cols, vals) for the column-major / row-major structure; one call, shared syncs."""
+        (rc, cc, vc), (rr, cr, vr) = col_triple, row_triple
+        check(lib().dsa_matrix_set_batch_two_d(self.h, C.c_void_p(rc.data_ptr()), C.c_void_p(cc.data_ptr()), C.c_void_p(vc.data_ptr()),
+                                               C.c_int64(rc.numel()), C.c_void_p(rr.data_ptr()), C.c_void_p(cr.data_ptr()),
+                                               C.c_void_p(vr.data_ptr()), C.c_int64(rr.numel())))
+
     def spmv_range(self, trans, x, y_slice, key_lo, key_hi):
         check(lib().dsa_matrix_spmv_dense_range_d(self.h, C.c_int(1 if trans else 0), C.c_void_p(x.data_ptr()), C.c_int64(x.numel()),
                                                   C.c_void_p(y_slice.data_ptr()), C.c_int64(key_lo), C.c_int64(key_hi)))
@@ -125,11 +132,32 @@ class ShardedMatrix:
 
     def set_batch(self, rows, cols, vals):
         """rows/cols/vals: this rank's share of the global batch (tensors on the shard's device)."""
-        # column-major structure lives with owner(col)
+        if not rows.is_cuda:
+            return self._set_batch_simple(rows, cols, vals)
+        W = self.world
+        # the column-major structure lives with owner(col), the row-major one with owner(row)
+        r1, c1, v1, cnt_c = route(cols, rows, cols, vals, self.col_split, W)
+        r2, c2, v2, cnt_r = route(rows, rows, cols, vals, self.row_split, W)
+        # one small all-to-all carries both count vectors
+        sc = torch.tensor([x for pair in zip(cnt_c, cnt_r) for x in pair], dtype=torch.int64, device=rows.device)
+        rc = torch.empty_like(sc)
+        dist.all_to_all_single(rc, sc, group=self.group)
+        rc = rc.view(W, 2).tolist()
+        rcv_c, rcv_r = [p[0] for p in rc], [p[1] for p in rc]
+        # triples travel packed as (n, 3) int64 rows: one all-to-all per orientation
+        out = []
+        for (r, c, v, snd, rcv) in ((r1, c1, v1, cnt_c, rcv_c), (r2, c2, v2, cnt_r, rcv_r)):
+            packed = torch.stack((r, c, v.view(torch.int64)), dim=1)
+            recv = torch.empty((int(sum(rcv)), 3), dtype=torch.int64, device=rows.device)
+            dist.all_to_all_single(recv, packed, output_split_sizes=rcv, input_split_sizes=list(snd), group=self.group)
+            cols3 = recv.t().contiguous()
+            out.append((cols3[0], cols3[1], cols3[2].view(torch.float64)))
+        self.local.set_batch_two(out[0], out[1])
+
+    def _set_batch_simple(self, rows, cols, vals):
         r1, c1, v1, cnt = route(cols, rows, cols, vals, self.col_split, self.world)
         (r1, c1, v1), _ = exchange([r1, c1, v1], cnt, self.group)
         self.local.set_batch(_lib.COLMAJOR, r1, c1, v1)          # in-array key = row, partition key = col
-        # row-major structure lives with owner(row)
         r2, c2, v2, cnt = route(rows, rows, cols, vals, self.row_split, self.world)
         (r2, c2, v2), _ = exchange([r2, c2, v2], cnt, self.group)
         self.local.set_batch(_lib.ROWMAJOR, c2, r2, v2)          # in-array key = col, partition key = row

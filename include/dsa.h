@@ -141,6 +141,10 @@ int dsa_matrix_build_one(dsa_matrix_t* A, int which, const int64_t* inkeys, cons
                          int combine);
 int dsa_matrix_set_batch_one_d(dsa_matrix_t* A, int which, const int64_t* d_inkeys, const int64_t* d_partkeys, const double* d_vals,
                                int64_t n);
+/* both orientations in one call (they share the two host synchronisations of a batch): the col-major structure receives
+ * (rows_c, cols_c, vals_c), the row-major one (rows_r, cols_r, vals_r) */
+int dsa_matrix_set_batch_two_d(dsa_matrix_t* A, const int64_t* d_rows_c, const int64_t* d_cols_c, const double* d_vals_c, int64_t nc,
+                               const int64_t* d_rows_r, const int64_t* d_cols_r, const double* d_vals_r, int64_t nr);
 /* y[k - key_lo] = (row-major if trans == 0, else col-major) partition k times x, for key_lo <= k < key_hi; other entries 0 */
 int dsa_matrix_spmv_dense_range_d(dsa_matrix_t* A, int trans, const double* d_x, int64_t nx, double* d_y, int64_t key_lo,
                                   int64_t key_hi);
