@@ -102,6 +102,14 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu --set full capture."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["kernels"][kernel]["dram_bytes"]
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -258,7 +266,7 @@ def main():
         a = spmv_alg_bytes / (spmv_us * 1e-6) / 1e9
         spmv = {"kernel": "spmv_flat", "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak,
                 "frac_of_8TBs": a / 8000.0, "physical_gbs": spmv_phys_bytes / (spmv_us * 1e-6) / 1e9, "avg_us": spmv_us,
-                "algorithmic_bytes": spmv_alg_bytes, "traffic": None, "peak_source": peak_src}
+                "algorithmic_bytes": spmv_alg_bytes, "traffic": ncu_traffic("spmv_flat"), "peak_source": peak_src}
     dom = max(kernels.items(), key=lambda kv: kv[1]["ms_per_step"]) if kernels else (None, None)
     roofline = None
     if dom[0]:
@@ -268,7 +276,7 @@ def main():
         else:   # a kernel of the update pipeline processes one orientation's share of the batch per launch
             alg = BYTES_PER_UPDATE_ONE * BATCH
         a = alg / (k["avg_us"] * 1e-6) / 1e9
-        roofline = {"kernel": name, "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "traffic": None,
+        roofline = {"kernel": name, "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "traffic": ncu_traffic(name),
                     "avg_us": k["avg_us"], "algorithmic_bytes": alg, "share_of_step": k["ms_per_step"] / sum(v["ms_per_step"] for v in kernels.values()),
                     "peak_source": peak_src}
 

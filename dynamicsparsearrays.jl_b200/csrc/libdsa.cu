@@ -128,12 +128,10 @@ static void phase2_launch(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t 
         // every partition receives few ops: bucket by partition, rank inside the bucket
         const int64_t ns = P.nslots();
         int32_t* boff = ws.boff.ensure((size_t)ns + 1);
-        int64_t* bkey = ws.tmp_k.ensure((size_t)n);
-        uint32_t* barr = ws.barr.ensure((size_t)n);
-        int32_t* bslot = ws.bslot.ensure((size_t)n);
+        BucketRec* rec = ws.brec.ensure((size_t)n);
         exclusive_scan_i32<int32_t>(ws.batch.scan, ws.bcnt.p, boff, ns, nullptr, st);
-        DSA_LAUNCH("bucket_scatter", k_bucket_scatter, grt, 256, 0, st, ws.op_slot.p, ws.lidx.p, c.inkeys, n, boff, bkey, barr, bslot);
-        DSA_LAUNCH("bucket_rank", k_bucket_rank, grt, 256, 0, st, bkey, barr, bslot, boff, ws.bcnt.p, n, kb, sk, perm);
+        DSA_LAUNCH("bucket_scatter", k_bucket_scatter, grt, 256, 0, st, ws.op_slot.p, ws.lidx.p, c.inkeys, n, boff, rec);
+        DSA_LAUNCH("bucket_rank", k_bucket_rank, grt, 256, 0, st, rec, boff, ws.bcnt.p, n, kb, sk, perm);
     } else {
         DSA_LAUNCH("make_sortkeys", k_make_sortkeys, grt, 256, 0, st, ws.op_slot.p, c.inkeys, n, d_new, nnew, kb, sk, perm);
         radix_sort_pairs(ws.sort, sk, perm, ntot, kb + pb, st);
@@ -981,6 +979,69 @@ int dsa_route_batch_d(const int64_t* d_route_keys, const int64_t* d_rows, const 
         if (e < 0) e = prev;
         counts_out[r] = e - prev;
         prev = e;
+    }
+    return DSA_OK;
+    DSA_CATCH
+}
+
+}  // extern "C"
+namespace dsa {
+__global__ void __launch_bounds__(256) k_route_gather_packed(const uint64_t* __restrict__ sk, const uint32_t* __restrict__ perm, int64_t n,
+                                                              const int64_t* __restrict__ rows, const int64_t* __restrict__ cols,
+                                                              const double* __restrict__ vals, int64_t* __restrict__ packed,
+                                                              int64_t* __restrict__ ends) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t s = perm[i];
+    packed[3 * i + 0] = rows[s];
+    packed[3 * i + 1] = cols[s];
+    packed[3 * i + 2] = __double_as_longlong(vals[s]);
+    if (i == n - 1 || sk[i] != sk[i + 1]) ends[(int)sk[i] + 1] = i + 1;   // end offset of this owner's run
+}
+}  // namespace dsa
+extern "C" {
+int dsa_route_batch2_d(const int64_t* d_rows, const int64_t* d_cols, const double* d_vals, int64_t n, const int64_t* col_splitters,
+                       const int64_t* row_splitters, int nranks, int64_t* d_packed_by_col, int64_t* d_packed_by_row,
+                       int64_t* counts_by_col, int64_t* counts_by_row, void* cuda_stream) {
+    DSA_TRY
+    static SortWorkspace sws[2];
+    static DBuf<uint64_t> sk[2];
+    static DBuf<uint32_t> perm[2];
+    static DBuf<int64_t> d_split, d_ends;
+    static HPinned<int64_t> h_ends;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    for (int r = 0; r < nranks; ++r) counts_by_col[r] = counts_by_row[r] = 0;
+    if (n <= 0) return DSA_OK;
+    const int ns = std::max(nranks - 1, 0);
+    d_split.ensure((size_t)2 * ns + 2);
+    d_ends.ensure((size_t)2 * (nranks + 1));
+    int64_t* he = h_ends.ensure((size_t)2 * (nranks + 1));
+    if (ns) {
+        DSA_CUDA(cudaMemcpyAsync(d_split.p, col_splitters, (size_t)ns * 8, cudaMemcpyHostToDevice, st));
+        DSA_CUDA(cudaMemcpyAsync(d_split.p + ns, row_splitters, (size_t)ns * 8, cudaMemcpyHostToDevice, st));
+    }
+    DSA_CUDA(cudaMemsetAsync(d_ends.p, 0xff, (size_t)2 * (nranks + 1) * 8, st));   // -1 = owner absent
+    const unsigned gr = grid_for(n, 256);
+    const int bits = std::max(1, bits_for((uint64_t)std::max(nranks - 1, 1)));
+    for (int o = 0; o < 2; ++o) {
+        sk[o].ensure((size_t)n);
+        perm[o].ensure((size_t)n);
+        DSA_LAUNCH("route_owner", k_route_owner, gr, 256, 0, st, o == 0 ? d_cols : d_rows, n, d_split.p + o * ns, nranks, sk[o].p, perm[o].p);
+        radix_sort_pairs(sws[o], sk[o].p, perm[o].p, n, bits, st);
+        DSA_LAUNCH("route_gather", k_route_gather_packed, gr, 256, 0, st, sk[o].p, perm[o].p, n, d_rows, d_cols, d_vals,
+                   o == 0 ? d_packed_by_col : d_packed_by_row, d_ends.p + o * (nranks + 1));
+    }
+    DSA_CUDA(cudaMemcpyAsync(he, d_ends.p, (size_t)2 * (nranks + 1) * 8, cudaMemcpyDeviceToHost, st));
+    DSA_CUDA(cudaStreamSynchronize(st));
+    for (int o = 0; o < 2; ++o) {
+        int64_t prev = 0;
+        int64_t* out = o == 0 ? counts_by_col : counts_by_row;
+        for (int r = 0; r < nranks; ++r) {
+            int64_t e = he[o * (nranks + 1) + r + 1];
+            if (e < 0) e = prev;
+            out[r] = e - prev;
+            prev = e;
+        }
     }
     return DSA_OK;
     DSA_CATCH

@@ -157,34 +157,34 @@ __global__ void __launch_bounds__(256) k_make_sortkeys(const int32_t* __restrict
 // inside its bucket by (key, arrival).  Same output as the radix sort — ops ordered by (partition, key), equal keys in
 // arrival order — in 3 small kernels instead of 5 passes over 64-bit keys.
 // ---------------------------------------------------------------------------------------------
+struct __align__(16) BucketRec {
+    int64_t key;
+    uint32_t arr;
+    int32_t slot;
+};
 __global__ void __launch_bounds__(256) k_bucket_scatter(const int32_t* __restrict__ op_slot, const int32_t* __restrict__ lidx,
                                                          const int64_t* __restrict__ inkeys, int64_t n, const int32_t* __restrict__ boff,
-                                                         int64_t* __restrict__ bkey, uint32_t* __restrict__ barr, int32_t* __restrict__ bslot) {
+                                                         BucketRec* __restrict__ rec) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int32_t s = op_slot[i];
     const int64_t pos = (int64_t)boff[s] + lidx[i];
-    bkey[pos] = inkeys[i];
-    barr[pos] = (uint32_t)i;
-    bslot[pos] = s;
+    rec[pos] = BucketRec{inkeys[i], (uint32_t)i, s};   // one 16 B store per op
 }
-__global__ void __launch_bounds__(256) k_bucket_rank(const int64_t* __restrict__ bkey, const uint32_t* __restrict__ barr,
-                                                      const int32_t* __restrict__ bslot, const int32_t* __restrict__ boff,
+__global__ void __launch_bounds__(256) k_bucket_rank(const BucketRec* __restrict__ rec, const int32_t* __restrict__ boff,
                                                       const int32_t* __restrict__ bcnt, int64_t n, int kb, uint64_t* __restrict__ sk,
                                                       uint32_t* __restrict__ perm) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
-    const int32_t s = bslot[p];
-    const int64_t lo = boff[s], hi = lo + bcnt[s];
-    const int64_t key = bkey[p];
-    const uint32_t arr = barr[p];
+    const BucketRec me = rec[p];
+    const int64_t lo = boff[me.slot], hi = lo + bcnt[me.slot];
     int64_t r = lo;
     for (int64_t q = lo; q < hi; ++q) {
-        const int64_t kq = bkey[q];
-        r += (kq < key) || (kq == key && barr[q] < arr);
+        const BucketRec o = rec[q];
+        r += (o.key < me.key) || (o.key == me.key && o.arr < me.arr);
     }
-    sk[r] = ((uint64_t)(uint32_t)s << kb) | (uint64_t)key;
-    perm[r] = arr;
+    sk[r] = ((uint64_t)(uint32_t)me.slot << kb) | (uint64_t)me.key;
+    perm[r] = me.arr;
 }
 
 // plain PMA: sort key = key - min
@@ -323,8 +323,7 @@ __global__ void __launch_bounds__(256) k_clear_sems(int64_t* __restrict__ sem, c
 // k_spmv_fixup then adds, per chunk with a head, the carries of the following head-less chunks in chunk order.
 // No atomics: the result is bit-reproducible.  mul and add are separate roundings (no FMA), as in the reference.
 // ---------------------------------------------------------------------------------------------
-constexpr int SPMV_STEPS = 8;
-constexpr int SPMV_CHUNK = 32 * SPMV_STEPS;
+constexpr int SPMV_STEPS_DEFAULT = 4;   // 32-cell steps per warp chunk (4 keeps the kernel at 48 warps/SM; see profiles/)
 
 __device__ __forceinline__ double warp_sum_f64(double v) {
 #pragma unroll
@@ -337,7 +336,7 @@ __device__ __forceinline__ int warp_sum_i32(int v) {
     return v;
 }
 
-template <bool SPARSE_X>
+template <bool SPARSE_X, int SPMV_STEPS>
 __global__ void __launch_bounds__(256) k_spmv_flat(const int64_t* __restrict__ keys, const double* __restrict__ vals, int64_t cap,
                                                     const double* __restrict__ x, const uint8_t* __restrict__ xmask, int64_t nx,
                                                     double* __restrict__ yslot, int32_t* __restrict__ ycnt,
@@ -347,6 +346,7 @@ __global__ void __launch_bounds__(256) k_spmv_flat(const int64_t* __restrict__ k
     const int lane = threadIdx.x & 31;
     if (chunk >= nchunks) return;
     const unsigned lt = lanemask_lt();
+    constexpr int SPMV_CHUNK = 32 * SPMV_STEPS;
     const int64_t base = chunk * SPMV_CHUNK;
     // all loads of the chunk in flight together: 8 x (key, value), then 8 independent gathers of x
     int64_t k[SPMV_STEPS];
@@ -357,9 +357,9 @@ __global__ void __launch_bounds__(256) k_spmv_flat(const int64_t* __restrict__ k
         const int64_t p = base + s * 32 + lane;
         k[s] = GAP_KEY;
         t[s] = 0.0;
-        if (p < cap) {
-            k[s] = keys[p];
-            t[s] = vals[p];
+        if (p < cap) {   // streamed once: evict-first, so the array does not push x out of L1/L2
+            k[s] = __ldcs(keys + p);
+            t[s] = __ldcs(vals + p);
         }
     }
 #pragma unroll
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(256) k_spmv_flat(const int64_t* __restrict__ k
             bool present = kk <= nx;
             if (SPARSE_X) present = present && xmask[kk - 1] != 0;
             if (present) {
-                xv = x[kk - 1];
+                xv = __ldg(x + (kk - 1));
                 tc[s] = 1;
             }
             t[s] = present ? __dmul_rn(xv, t[s]) : 0.0;
@@ -521,7 +521,7 @@ struct PcsrWorkspace {
     BatchWorkspace batch;
     SortWorkspace sort;
     DBuf<int32_t> op_slot, flag32, idx32, u_pid, new_slots, old2new, rank32, del_slots, cnt32, bcnt, boff, lidx, bslot;
-    DBuf<uint32_t> barr;
+    DBuf<BucketRec> brec;
     DBuf<int64_t> miss_keys, cs, u_key, live_pos, nuniq, tmp_k, tmp_owner, del_keys;
     DBuf<double> u_val, tmp_v, yslot, carry, xdense;
     DBuf<uint64_t> sk;
@@ -671,9 +671,10 @@ struct Pcsr {
     }
 
     // flat SpMV; results by slot in ws.yslot / ws.ycnt
-    void spmv_slots(PcsrWorkspace& ws, const double* d_x, const uint8_t* d_xmask, int64_t nx, cudaStream_t st) {
+    template <int STEPS>
+    void spmv_launch(PcsrWorkspace& ws, const double* d_x, const uint8_t* d_xmask, int64_t nx, cudaStream_t st) {
         const int64_t cap = pma.g.capacity;
-        const int64_t nchunks = (cap + SPMV_CHUNK - 1) / SPMV_CHUNK;
+        const int64_t nchunks = (cap + 32 * STEPS - 1) / (32 * STEPS);
         const int64_t ns = nslots();
         double* yslot = ws.yslot.ensure((size_t)ns + 1);
         int32_t* ycnt = ws.ycnt.ensure((size_t)ns + 1);
@@ -682,12 +683,22 @@ struct Pcsr {
         int32_t* clast = ws.chunk_last.ensure((size_t)nchunks);
         const unsigned gr = grid_for(nchunks * 32, 256);
         if (d_xmask)
-            DSA_LAUNCH("spmv_flat", (k_spmv_flat<true>), gr, 256, 0, st, pma.keys.p, pma.vals.p, cap, d_x, d_xmask, nx, yslot, ycnt, carry,
-                       ccnt, clast, nchunks);
+            DSA_LAUNCH("spmv_flat", (k_spmv_flat<true, STEPS>), gr, 256, 0, st, pma.keys.p, pma.vals.p, cap, d_x, d_xmask, nx, yslot, ycnt,
+                       carry, ccnt, clast, nchunks);
         else
-            DSA_LAUNCH("spmv_flat", (k_spmv_flat<false>), gr, 256, 0, st, pma.keys.p, pma.vals.p, cap, d_x, d_xmask, nx, yslot, ycnt, carry,
-                       ccnt, clast, nchunks);
+            DSA_LAUNCH("spmv_flat", (k_spmv_flat<false, STEPS>), gr, 256, 0, st, pma.keys.p, pma.vals.p, cap, d_x, d_xmask, nx, yslot, ycnt,
+                       carry, ccnt, clast, nchunks);
         DSA_LAUNCH("spmv_fixup", k_spmv_fixup, grid_for(nchunks, 256), 256, 0, st, yslot, ycnt, carry, ccnt, clast, nchunks);
+    }
+    // flat SpMV; results by slot in ws.yslot / ws.ycnt
+    void spmv_slots(PcsrWorkspace& ws, const double* d_x, const uint8_t* d_xmask, int64_t nx, cudaStream_t st) {
+        static const int steps = [] {
+            const char* e = getenv("DSA_SPMV_STEPS");
+            return e ? atoi(e) : SPMV_STEPS_DEFAULT;
+        }();
+        if (steps == 8) spmv_launch<8>(ws, d_x, d_xmask, nx, st);
+        else if (steps == 2) spmv_launch<2>(ws, d_x, d_xmask, nx, st);
+        else spmv_launch<4>(ws, d_x, d_xmask, nx, st);
     }
 
     void clone_from(const Pcsr& o, cudaStream_t st) {

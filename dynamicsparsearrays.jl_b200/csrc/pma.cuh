@@ -178,8 +178,7 @@ __global__ void __launch_bounds__(256) k_apply_hits(int64_t* __restrict__ keys, 
         vals[op_pos[i]] = op_val[i];
     } else if (f == FL_DELETE) {
         const int64_t p = op_pos[i];
-        keys[p] = GAP_KEY;
-        vals[p] = 0.0;
+        keys[p] = GAP_KEY;   // the value of a gap cell is never read (exports and SpMV mask by the key)
         atomicSub(&leafcnt[p >> lgS], 1);
         touched[p >> lgS] = 1;
     }

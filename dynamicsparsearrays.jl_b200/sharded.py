@@ -135,9 +135,19 @@ class ShardedMatrix:
         if not rows.is_cuda:
             return self._set_batch_simple(rows, cols, vals)
         W = self.world
-        # the column-major structure lives with owner(col), the row-major one with owner(row)
-        r1, c1, v1, cnt_c = route(cols, rows, cols, vals, self.col_split, W)
-        r2, c2, v2, cnt_r = route(rows, rows, cols, vals, self.row_split, W)
+        n = rows.numel()
+        # the column-major structure lives with owner(col), the row-major one with owner(row): both stable partitions, packed as
+        # (n, 3) int64 rows, in one library call (one host sync for the 2 x W send counts)
+        pk_c = torch.empty((n, 3), dtype=torch.int64, device=rows.device)
+        pk_r = torch.empty((n, 3), dtype=torch.int64, device=rows.device)
+        cc, cr = np.zeros(W, np.int64), np.zeros(W, np.int64)
+        isc = np.asarray(self.col_split[1:-1], dtype=np.int64)
+        isr = np.asarray(self.row_split[1:-1], dtype=np.int64)
+        check(lib().dsa_route_batch2_d(C.c_void_p(rows.data_ptr()), C.c_void_p(cols.data_ptr()), C.c_void_p(vals.data_ptr()), C.c_int64(n),
+                                       C.c_void_p(isc.ctypes.data), C.c_void_p(isr.ctypes.data), C.c_int(W), C.c_void_p(pk_c.data_ptr()),
+                                       C.c_void_p(pk_r.data_ptr()), C.c_void_p(cc.ctypes.data), C.c_void_p(cr.ctypes.data),
+                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        cnt_c, cnt_r = cc.tolist(), cr.tolist()
         # one small all-to-all carries both count vectors
         sc = torch.tensor([x for pair in zip(cnt_c, cnt_r) for x in pair], dtype=torch.int64, device=rows.device)
         rc = torch.empty_like(sc)
@@ -146,8 +156,7 @@ class ShardedMatrix:
         rcv_c, rcv_r = [p[0] for p in rc], [p[1] for p in rc]
         # triples travel packed as (n, 3) int64 rows: one all-to-all per orientation
         out = []
-        for (r, c, v, snd, rcv) in ((r1, c1, v1, cnt_c, rcv_c), (r2, c2, v2, cnt_r, rcv_r)):
-            packed = torch.stack((r, c, v.view(torch.int64)), dim=1)
+        for (packed, snd, rcv) in ((pk_c, cnt_c, rcv_c), (pk_r, cnt_r, rcv_r)):
             recv = torch.empty((int(sum(rcv)), 3), dtype=torch.int64, device=rows.device)
             dist.all_to_all_single(recv, packed, output_split_sizes=rcv, input_split_sizes=list(snd), group=self.group)
             cols3 = recv.t().contiguous()

@@ -156,6 +156,12 @@ int dsa_route_batch_d(const int64_t* d_route_keys, const int64_t* d_rows, const 
                       const int64_t* splitters, int nranks, int64_t* d_rows_out, int64_t* d_cols_out, double* d_vals_out,
                       int64_t* counts_out, void* cuda_stream);
 
+/* both routings of a matrix batch in one call: by owner(col) for the col-major shards and by owner(row) for the row-major ones.
+ * Outputs are packed (n, 3) int64 rows {row, col, bits(val)} in rank order, ready for one all-to-all each; one host sync. */
+int dsa_route_batch2_d(const int64_t* d_rows, const int64_t* d_cols, const double* d_vals, int64_t n, const int64_t* col_splitters,
+                       const int64_t* row_splitters, int nranks, int64_t* d_packed_by_col, int64_t* d_packed_by_row,
+                       int64_t* counts_by_col, int64_t* counts_by_row, void* cuda_stream);
+
 /* ---------------------------------------------------------------- measurement ---------- */
 /* kernel launches issued by this library since load (bench.py's gpu_launches) */
 int64_t dsa_launch_count(void);
