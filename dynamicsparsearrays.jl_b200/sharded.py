@@ -11,6 +11,8 @@ The local structure is a ``LocalBackend`` (libdsa on the GPU).  The routing / ex
 ``tests/test_sharded_gloo.py`` can drive it on CPU tensors over gloo with the oracle as the per-rank checker.
 """
 import ctypes as C
+import queue
+import threading
 
 import numpy as np
 import torch
@@ -113,8 +115,14 @@ def exchange(arrays, send_counts, group=None):
 
 
 class ShardedMatrix:
+    """set_batch(rows, cols, vals) routes + exchanges + applies one batch.  For streams of batches, submit(...) hands the
+    routing and the NCCL exchange of a batch to a background router (own CUDA stream, own communicator) so that they overlap
+    with the application of the previous batch; apply_next() applies the oldest submitted batch.  Every rank must submit
+    and apply in the same order."""
+
     def __init__(self, m, n, backend, group=None):
         self.group = group
+        self._router = None
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.m, self.n = int(m), int(n)
         self.row_split = even_splitters(self.m, self.world)
@@ -134,12 +142,20 @@ class ShardedMatrix:
         """rows/cols/vals: this rank's share of the global batch (tensors on the shard's device)."""
         if not rows.is_cuda:
             return self._set_batch_simple(rows, cols, vals)
+        # the column-major structure lives with owner(col), the row-major one with owner(row): both stable partitions (packed
+        # (n, 3) int64 rows, one library call, one host sync for the 2 x W send counts), one small all-to-all for the counts,
+        # one all-to-all per orientation for the triples
+        out = self._route_exchange(rows, cols, vals, self.group)
+        self.local.set_batch_two(out[0], out[1])
+
+    # ---- pipelined use -------------------------------------------------------------------------------------------
+    def _route_exchange(self, rows, cols, vals, group):
+        """route both orientations, exchange counts and packed triples; returns the two received (rows, cols, vals) triples"""
         W = self.world
         n = rows.numel()
-        # the column-major structure lives with owner(col), the row-major one with owner(row): both stable partitions, packed as
-        # (n, 3) int64 rows, in one library call (one host sync for the 2 x W send counts)
-        pk_c = torch.empty((n, 3), dtype=torch.int64, device=rows.device)
-        pk_r = torch.empty((n, 3), dtype=torch.int64, device=rows.device)
+        dev = rows.device
+        pk_c = torch.empty((n, 3), dtype=torch.int64, device=dev)
+        pk_r = torch.empty((n, 3), dtype=torch.int64, device=dev)
         cc, cr = np.zeros(W, np.int64), np.zeros(W, np.int64)
         isc = np.asarray(self.col_split[1:-1], dtype=np.int64)
         isr = np.asarray(self.row_split[1:-1], dtype=np.int64)
@@ -148,20 +164,65 @@ class ShardedMatrix:
                                        C.c_void_p(pk_r.data_ptr()), C.c_void_p(cc.ctypes.data), C.c_void_p(cr.ctypes.data),
                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         cnt_c, cnt_r = cc.tolist(), cr.tolist()
-        # one small all-to-all carries both count vectors
-        sc = torch.tensor([x for pair in zip(cnt_c, cnt_r) for x in pair], dtype=torch.int64, device=rows.device)
+        sc = torch.tensor([x for pair in zip(cnt_c, cnt_r) for x in pair], dtype=torch.int64, device=dev)
         rc = torch.empty_like(sc)
-        dist.all_to_all_single(rc, sc, group=self.group)
+        dist.all_to_all_single(rc, sc, group=group)
         rc = rc.view(W, 2).tolist()
-        rcv_c, rcv_r = [p[0] for p in rc], [p[1] for p in rc]
-        # triples travel packed as (n, 3) int64 rows: one all-to-all per orientation
         out = []
-        for (packed, snd, rcv) in ((pk_c, cnt_c, rcv_c), (pk_r, cnt_r, rcv_r)):
-            recv = torch.empty((int(sum(rcv)), 3), dtype=torch.int64, device=rows.device)
-            dist.all_to_all_single(recv, packed, output_split_sizes=rcv, input_split_sizes=list(snd), group=self.group)
+        for (packed, snd, rcv) in ((pk_c, cnt_c, [p[0] for p in rc]), (pk_r, cnt_r, [p[1] for p in rc])):
+            recv = torch.empty((int(sum(rcv)), 3), dtype=torch.int64, device=dev)
+            dist.all_to_all_single(recv, packed, output_split_sizes=rcv, input_split_sizes=list(snd), group=group)
             cols3 = recv.t().contiguous()
             out.append((cols3[0], cols3[1], cols3[2].view(torch.float64)))
+        return out
+
+    def _start_router(self, device):
+        self._tasks, self._routed = queue.Queue(), queue.Queue()
+        self._comm_group = dist.new_group(ranks=list(range(self.world)))   # own communicator: never shared with the main thread
+        self._comm_stream = torch.cuda.Stream(device=device)
+
+        def loop():
+            torch.cuda.set_device(device)
+            lib().dsa_set_device(C.c_int(device.index))
+            while True:
+                task = self._tasks.get()
+                if task is None:
+                    return
+                try:
+                    with torch.cuda.stream(self._comm_stream):
+                        rows, cols, vals = (t.to(device, non_blocking=True) for t in task)   # host shares are copied here, overlapped too
+                        out = self._route_exchange(rows, cols, vals, self._comm_group)
+                        ev = torch.cuda.Event()
+                        ev.record(self._comm_stream)
+                    self._routed.put((out, ev, None))
+                except Exception as ex:   # surfaced by apply_next
+                    self._routed.put((None, None, ex))
+
+        self._router = threading.Thread(target=loop, daemon=True)
+        self._router.start()
+
+    def submit(self, rows, cols, vals):
+        """enqueue this rank's share of the next global batch (device tensors, or pinned host tensors)"""
+        if self._router is None:
+            self._start_router(self.local.device)
+        self._tasks.put((rows, cols, vals))
+
+    def apply_next(self):
+        """apply the oldest submitted batch to the local shards (blocks until its routing has been issued)"""
+        out, ev, ex = self._routed.get()
+        if ex is not None:
+            raise ex
+        torch.cuda.current_stream().wait_event(ev)
         self.local.set_batch_two(out[0], out[1])
+        for triple in out:   # the tensors were allocated on the router's stream
+            for t in triple:
+                t.record_stream(torch.cuda.current_stream())
+
+    def close(self):
+        if self._router is not None:
+            self._tasks.put(None)
+            self._router.join(timeout=10)
+            self._router = None
 
     def _set_batch_simple(self, rows, cols, vals):
         r1, c1, v1, cnt = route(cols, rows, cols, vals, self.col_split, self.world)
