@@ -365,6 +365,22 @@ class DynamicSparseMatrix:
             self._pending.clear()
             check(lib().dsa_matrix_set_batch(self._h, _p(r), _p(c), _p(v), C.c_int64(len(r))))
 
+    def stage_batch(self, rows, cols, vals):
+        """Start the host->device copy of a batch and return at once; apply_staged() applies it (double-buffered flush).
+        The arrays must stay alive (and should be pinned) until the matching apply_staged() returns."""
+        self._not_fillmode("Cannot apply a batch in fill mode")
+        self.flush()
+        rows, cols, vals = _i64(rows), _i64(cols), _f64(vals)
+        if not (len(rows) == len(cols) == len(vals)):
+            raise ArgumentError(_lib.DSA_ERR_ARGUMENT, "rows, columns, and nonzeros do not have same length.")
+        self._staged = getattr(self, "_staged", [])
+        self._staged.append((rows, cols, vals))
+        check(lib().dsa_matrix_stage_batch(self._h, _p(rows), _p(cols), _p(vals), C.c_int64(len(rows))))
+
+    def apply_staged(self):
+        check(lib().dsa_matrix_apply_staged(self._h))
+        self._staged.pop(0)
+
     def _not_fillmode(self, msg):
         if self.fillmode:
             raise ErrorException(_lib.DSA_ERR_ERROR, msg)

@@ -216,6 +216,20 @@ struct dsa_matrix {
     PcsrWorkspace ws, ws2;     // ws2: batch scratch of the row-major twin (both orientations are in flight together)
     Staging stg;
     StreamHolder sh;
+    // double-buffered staging of host batches (dsa_matrix_stage_batch / dsa_matrix_apply_staged)
+    struct Slot {
+        DBuf<int64_t> r, c;
+        DBuf<double> v;
+        cudaEvent_t ev = nullptr;
+        int64_t n = 0;
+    } slot[2];
+    cudaStream_t copy_st = nullptr;
+    int staged_head = 0, staged_count = 0;
+    ~dsa_matrix() {
+        for (auto& s : slot)
+            if (s.ev) cudaEventDestroy(s.ev);
+        if (copy_st) cudaStreamDestroy(copy_st);
+    }
     DBuf<int32_t> d_slots;
     DBuf<int64_t> d_ids;
 };
@@ -704,6 +718,39 @@ int dsa_matrix_set_batch(dsa_matrix_t* A, const int64_t* rows, const int64_t* co
     double* dv = h2d(A->stg.v, vals, n, st);
     matrix_set_batch_dev(A, dr, dc, dv, n);
     DSA_CUDA(cudaStreamSynchronize(st));
+    return DSA_OK;
+    DSA_CATCH
+}
+int dsa_matrix_stage_batch(dsa_matrix_t* A, const int64_t* rows, const int64_t* cols, const double* vals, int64_t n) {
+    DSA_TRY
+    if (A->staged_count >= 2) throw DsaError{DSA_ERR_ERROR, "two batches are already staged: call dsa_matrix_apply_staged first"};
+    if (n < 0) throw DsaError{DSA_ERR_ARGUMENT, "negative length"};
+    if (!A->copy_st) DSA_CUDA(cudaStreamCreateWithFlags(&A->copy_st, cudaStreamNonBlocking));
+    dsa_matrix::Slot& s = A->slot[(A->staged_head + A->staged_count) & 1];
+    if (!s.ev) DSA_CUDA(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+    s.n = n;
+    int64_t* dr = s.r.ensure((size_t)std::max<int64_t>(n, 1));
+    int64_t* dc = s.c.ensure((size_t)std::max<int64_t>(n, 1));
+    double* dv = s.v.ensure((size_t)std::max<int64_t>(n, 1));
+    if (n > 0) {
+        DSA_CUDA(cudaMemcpyAsync(dr, rows, (size_t)n * 8, cudaMemcpyHostToDevice, A->copy_st));
+        DSA_CUDA(cudaMemcpyAsync(dc, cols, (size_t)n * 8, cudaMemcpyHostToDevice, A->copy_st));
+        DSA_CUDA(cudaMemcpyAsync(dv, vals, (size_t)n * 8, cudaMemcpyHostToDevice, A->copy_st));
+    }
+    DSA_CUDA(cudaEventRecord(s.ev, A->copy_st));
+    A->staged_count += 1;
+    return DSA_OK;
+    DSA_CATCH
+}
+int dsa_matrix_apply_staged(dsa_matrix_t* A) {
+    DSA_TRY
+    if (A->staged_count <= 0) throw DsaError{DSA_ERR_ERROR, "no staged batch"};
+    dsa_matrix::Slot& s = A->slot[A->staged_head & 1];
+    A->staged_head ^= 1;
+    A->staged_count -= 1;
+    DSA_CUDA(cudaStreamWaitEvent(A->sh.st, s.ev, 0));
+    matrix_set_batch_dev(A, s.r.p, s.c.p, s.v.p, s.n);
+    DSA_CUDA(cudaStreamSynchronize(A->sh.st));
     return DSA_OK;
     DSA_CATCH
 }

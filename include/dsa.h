@@ -111,6 +111,12 @@ int dsa_matrix_set_stream(dsa_matrix_t* A, void* cuda_stream);
  * (addcolumn!, pcsr.jl:148-169), m/n grow on non-zeros. In-array keys must be >= 1 (key 0 is the semaphore key, pcsr.jl:23). */
 int dsa_matrix_set_batch(dsa_matrix_t* A, const int64_t* rows, const int64_t* cols, const double* vals, int64_t n);
 int dsa_matrix_set_batch_d(dsa_matrix_t* A, const int64_t* d_rows, const int64_t* d_cols, const double* d_vals, int64_t n);
+/* The buffered-write flush, double-buffered: dsa_matrix_stage_batch starts the host->device copy of a batch on the handle's
+ * copy stream and returns at once (the host buffers must stay valid, and should be pinned, until the matching
+ * dsa_matrix_apply_staged returns); dsa_matrix_apply_staged applies the oldest staged batch exactly like dsa_matrix_set_batch.
+ * Staging batch k+1 before applying batch k overlaps its PCIe transfer with the kernels of batch k.  At most 2 batches staged. */
+int dsa_matrix_stage_batch(dsa_matrix_t* A, const int64_t* rows, const int64_t* cols, const double* vals, int64_t n);
+int dsa_matrix_apply_staged(dsa_matrix_t* A);
 /* batched getindex (matrix.jl:64-68 -> pcsr.jl:261-267); which = orientation to read (both hold the same values) */
 int dsa_matrix_get_batch(dsa_matrix_t* A, int which, const int64_t* rows, const int64_t* cols, int64_t n, double* out);
 /* deletecolumn! / deleterow! for a list (matrix.jl:95-111 -> pcsr.jl:188-212, writes.jl:80-92); DSA_ERR_ARGUMENT if one is absent */
