@@ -373,13 +373,14 @@ class DynamicSparseMatrix:
         rows, cols, vals = _i64(rows), _i64(cols), _f64(vals)
         if not (len(rows) == len(cols) == len(vals)):
             raise ArgumentError(_lib.DSA_ERR_ARGUMENT, "rows, columns, and nonzeros do not have same length.")
-        self._staged = getattr(self, "_staged", [])
-        self._staged.append((rows, cols, vals))
         check(lib().dsa_matrix_stage_batch(self._h, _p(rows), _p(cols), _p(vals), C.c_int64(len(rows))))
+        self._staged = getattr(self, "_staged", [])
+        self._staged.append((rows, cols, vals))   # keep the host arrays alive until the copy has been consumed
 
     def apply_staged(self):
         check(lib().dsa_matrix_apply_staged(self._h))
-        self._staged.pop(0)
+        if getattr(self, "_staged", None):
+            self._staged.pop(0)
 
     def _not_fillmode(self, msg):
         if self.fillmode:

@@ -121,29 +121,31 @@ static void phase2_launch(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t 
     const int kb = std::max(1, bits_for((uint64_t)c.bs.maxkey));
     const int pb = std::max(1, bits_for((uint64_t)std::max<int64_t>(P.nslots() - 1, 1)));
     if (kb + pb > 64) throw DsaError{DSA_ERR_ARGUMENT, "key range too wide: bits(max in-array key) + bits(#partitions) must be <= 64"};
-    uint64_t* sk = ws.sk.ensure((size_t)ntot);
-    uint32_t* perm = ws.perm.ensure((size_t)ntot);
     const unsigned grt = grid_for(ntot, 256);
+    int32_t* u_pid = ws.u_pid.ensure((size_t)ntot);
+    int64_t* u_key = ws.u_key.ensure((size_t)ntot);
+    double* u_val = ws.u_val.ensure((size_t)ntot);
     if (nnew == 0 && c.bs.missing == 0 && c.bs.maxbucket <= BUCKET_MAX) {
-        // every partition receives few ops: bucket by partition, rank inside the bucket
+        // every partition receives few ops: bucket by partition, rank inside the bucket; superseded writes are flagged dead
         const int64_t ns = P.nslots();
         int32_t* boff = ws.boff.ensure((size_t)ns + 1);
         BucketRec* rec = ws.brec.ensure((size_t)n);
+        uint8_t* dead = ws.u_dead.ensure((size_t)n);
         exclusive_scan_i32<int32_t>(ws.batch.scan, ws.bcnt.p, boff, ns, nullptr, st);
         DSA_LAUNCH("bucket_scatter", k_bucket_scatter, grt, 256, 0, st, ws.op_slot.p, ws.lidx.p, c.inkeys, n, boff, rec);
-        DSA_LAUNCH("bucket_rank", k_bucket_rank, grt, 256, 0, st, rec, boff, ws.bcnt.p, n, kb, sk, perm);
-    } else {
-        DSA_LAUNCH("make_sortkeys", k_make_sortkeys, grt, 256, 0, st, ws.op_slot.p, c.inkeys, n, d_new, nnew, kb, sk, perm);
-        radix_sort_pairs(ws.sort, sk, perm, ntot, kb + pb, st);
+        DSA_LAUNCH("bucket_rank", k_bucket_rank, grt, 256, 0, st, rec, boff, ws.bcnt.p, n, c.vals, u_pid, u_key, u_val, dead);
+        P.pma.apply_sorted_ops(ws.batch, u_pid, u_key, u_val, n, P.d_sem.p, P.d_next_slot.p, st, false, nullptr, /*launch_only=*/true, dead);
+        return;
     }
+    uint64_t* sk = ws.sk.ensure((size_t)ntot);
+    uint32_t* perm = ws.perm.ensure((size_t)ntot);
+    DSA_LAUNCH("make_sortkeys", k_make_sortkeys, grt, 256, 0, st, ws.op_slot.p, c.inkeys, n, d_new, nnew, kb, sk, perm);
+    radix_sort_pairs(ws.sort, sk, perm, ntot, kb + pb, st);
     int32_t* flag = ws.flag32.ensure((size_t)ntot);
     int32_t* uidx = ws.idx32.ensure((size_t)ntot);
     int64_t* nuniq_dev = ws.nuniq.ensure(4) + 2;
     DSA_LAUNCH("flag_run_last", k_flag_run_last, grt, 256, 0, st, sk, ntot, flag);
     exclusive_scan_i32<int32_t>(ws.batch.scan, flag, uidx, ntot, nuniq_dev, st);
-    int32_t* u_pid = ws.u_pid.ensure((size_t)ntot);
-    int64_t* u_key = ws.u_key.ensure((size_t)ntot);
-    double* u_val = ws.u_val.ensure((size_t)ntot);
     DSA_LAUNCH("gather_unique_ops", k_gather_unique_ops, grt, 256, 0, st, sk, perm, flag, uidx, ntot, n, kb, c.inkeys, c.vals, u_pid,
                u_key, u_val);
     P.pma.apply_sorted_ops(ws.batch, u_pid, u_key, u_val, ntot, P.d_sem.p, P.d_next_slot.p, st, false, nuniq_dev, /*launch_only=*/true);

@@ -171,20 +171,27 @@ __global__ void __launch_bounds__(256) k_bucket_scatter(const int32_t* __restric
     const int64_t pos = (int64_t)boff[s] + lidx[i];
     rec[pos] = BucketRec{inkeys[i], (uint32_t)i, s};   // one 16 B store per op
 }
+// Every op ranks itself inside its bucket by (key, arrival) and lands, fully formed, at its sorted position; an op that is
+// followed by a later write to the same (partition, key) is marked dead (last writer wins) instead of being compacted away.
 __global__ void __launch_bounds__(256) k_bucket_rank(const BucketRec* __restrict__ rec, const int32_t* __restrict__ boff,
-                                                      const int32_t* __restrict__ bcnt, int64_t n, int kb, uint64_t* __restrict__ sk,
-                                                      uint32_t* __restrict__ perm) {
+                                                      const int32_t* __restrict__ bcnt, int64_t n, const double* __restrict__ vals,
+                                                      int32_t* __restrict__ u_pid, int64_t* __restrict__ u_key, double* __restrict__ u_val,
+                                                      uint8_t* __restrict__ u_dead) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const BucketRec me = rec[p];
     const int64_t lo = boff[me.slot], hi = lo + bcnt[me.slot];
     int64_t r = lo;
+    bool dead = false;
     for (int64_t q = lo; q < hi; ++q) {
         const BucketRec o = rec[q];
         r += (o.key < me.key) || (o.key == me.key && o.arr < me.arr);
+        dead |= (o.key == me.key && o.arr > me.arr);
     }
-    sk[r] = ((uint64_t)(uint32_t)me.slot << kb) | (uint64_t)me.key;
-    perm[r] = me.arr;
+    u_pid[r] = me.slot;
+    u_key[r] = me.key;
+    u_val[r] = vals[me.arr];
+    u_dead[r] = dead ? 1 : 0;
 }
 
 // plain PMA: sort key = key - min
@@ -522,6 +529,7 @@ struct PcsrWorkspace {
     SortWorkspace sort;
     DBuf<int32_t> op_slot, flag32, idx32, u_pid, new_slots, old2new, rank32, del_slots, cnt32, bcnt, boff, lidx, bslot;
     DBuf<BucketRec> brec;
+    DBuf<uint8_t> u_dead;
     DBuf<int64_t> miss_keys, cs, u_key, live_pos, nuniq, tmp_k, tmp_owner, del_keys;
     DBuf<double> u_val, tmp_v, yslot, carry, xdense;
     DBuf<uint64_t> sk;

@@ -125,9 +125,13 @@ __global__ void __launch_bounds__(256) k_locate(const int64_t* __restrict__ keys
                                                  const int64_t* __restrict__ op_key, const double* __restrict__ op_val, int64_t nops,
                                                  const int64_t* __restrict__ sem, const int32_t* __restrict__ next_slot,
                                                  int64_t* __restrict__ op_pos, uint8_t* __restrict__ op_flag,
-                                                 const int64_t* __restrict__ n_dev) {
+                                                 const int64_t* __restrict__ n_dev, const uint8_t* __restrict__ op_dead) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (n_dev ? *n_dev : nops)) return;
+    if (op_dead && op_dead[i]) {   // overwritten by a later op of the same batch (last writer wins)
+        op_flag[i] = 0;
+        return;
+    }
     const int64_t key = op_key[i];
     const bool is_set = op_val[i] != 0.0;   // pma.jl:197, pcsr.jl:301
     int64_t pos;
@@ -170,10 +174,16 @@ __global__ void __launch_bounds__(256) k_get(const int64_t* __restrict__ keys, c
 __global__ void __launch_bounds__(256) k_apply_hits(int64_t* __restrict__ keys, double* __restrict__ vals,
                                                      const int64_t* __restrict__ op_pos, const uint8_t* __restrict__ op_flag,
                                                      const double* __restrict__ op_val, int64_t nops, int32_t* __restrict__ leafcnt,
-                                                     uint8_t* __restrict__ touched, int lgS, const int64_t* __restrict__ n_dev) {
+                                                     uint8_t* __restrict__ touched, int lgS, const int64_t* __restrict__ n_dev,
+                                                     int32_t* __restrict__ ins_flag) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (n_dev ? *n_dev : nops)) return;
+    if (i >= nops) return;
+    if (i >= (n_dev ? *n_dev : nops)) {
+        ins_flag[i] = 0;
+        return;
+    }
     const uint8_t f = op_flag[i];
+    ins_flag[i] = f == FL_INSERT ? 1 : 0;
     if (f == FL_OVERWRITE) {
         vals[op_pos[i]] = op_val[i];
     } else if (f == FL_DELETE) {
@@ -915,18 +925,17 @@ struct PmaCore {
     // sorted unique ops -> located, applied, merged.  op_pid/sem/next_sem nullable (plain PMA).
     void apply_sorted_ops(BatchWorkspace& ws, const int32_t* op_pid, const int64_t* op_key, const double* op_val, int64_t nops,
                           int64_t* d_sem, const int32_t* d_next_slot, cudaStream_t st, bool scratch_ready = false,
-                          const int64_t* n_dev = nullptr, bool launch_only = false) {
+                          const int64_t* n_dev = nullptr, bool launch_only = false, const uint8_t* op_dead = nullptr) {
         if (!scratch_ready) prepare_batch_scratch(ws, nops, st);
         const int lgS = ilog2_i64(g.segment_capacity);
         if (nops > 0) {
             const unsigned gr = grid_for(nops, 256);
             DSA_LAUNCH("locate", k_locate, gr, 256, 0, st, keys.p, g.capacity, op_pid, op_key, op_val, nops, d_sem, d_next_slot,
-                       ws.op_pos.p, ws.op_flag.p, n_dev);
-            DSA_LAUNCH("apply_hits", k_apply_hits, gr, 256, 0, st, keys.p, vals.p, ws.op_pos.p, ws.op_flag.p, op_val, nops,
-                       leafcnt.p, ws.touched, lgS, n_dev);
-            // ins_idx = exclusive scan of (flag == FL_INSERT)
+                       ws.op_pos.p, ws.op_flag.p, n_dev, op_dead);
+            // hits are applied; ins_idx = exclusive scan of the insert flags written by the same kernel
             int32_t* f32 = ws.flag32.ensure((size_t)nops);
-            DSA_LAUNCH("flag_inserts", k_flag_eq, gr, 256, 0, st, ws.op_flag.p, nops, (uint8_t)FL_INSERT, f32, n_dev);
+            DSA_LAUNCH("apply_hits", k_apply_hits, gr, 256, 0, st, keys.p, vals.p, ws.op_pos.p, ws.op_flag.p, op_val, nops,
+                       leafcnt.p, ws.touched, lgS, n_dev, f32);
             exclusive_scan_i32<int32_t>(ws.scan, f32, ws.ins_idx.p, nops, ws.status + ST_NINS, st);
             DSA_LAUNCH("compact_inserts", k_compact_inserts, gr, 256, 0, st, op_key, op_val, ws.op_pos.p, ws.op_flag.p, ws.ins_idx.p,
                        nops, ws.ins_key.p, ws.ins_val.p, ws.ins_pos.p, n_dev);

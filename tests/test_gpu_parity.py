@@ -306,6 +306,33 @@ def test_matrix_batch_duplicates_last_writer_wins():
             assert_matrix_equal(gm, seq, layout=False)
 
 
+def test_staged_flush_equals_synchronous_flush():
+    """dsa_matrix_stage_batch / dsa_matrix_apply_staged (double-buffered H2D) must be indistinguishable from set_batch"""
+    rng = np.random.default_rng(41)
+    I, J, V = _rand_coo(rng, 400, 300, 9000)
+    a, b = D.dynamicsparse(I, J, V), D.dynamicsparse(I, J, V)
+    batches = []
+    for _ in range(4):
+        nb = 5000
+        batches.append((rng.integers(1, 450, nb), rng.integers(1, 350, nb), np.where(rng.random(nb) < 0.3, 0.0, rng.random(nb) + 0.5)))
+    a.stage_batch(*batches[0])
+    for s in range(4):
+        if s + 1 < 4:
+            a.stage_batch(*batches[s + 1])       # copy of the next batch overlaps the kernels of this one
+        a.apply_staged()
+        b.set_batch(*batches[s])
+        for which in (0, 1):
+            ea, eb = a.export(which), b.export(which)
+            assert np.array_equal(ea["tag"], eb["tag"]) and np.array_equal(ea["key"], eb["key"]) and np.array_equal(ea["val"], eb["val"])
+            assert np.array_equal(ea["semaphores"], eb["semaphores"])
+    with pytest.raises(D.ErrorException):
+        a.apply_staged()
+    a.stage_batch(*batches[0])
+    a.stage_batch(*batches[1])
+    with pytest.raises(D.ErrorException):
+        a.stage_batch(*batches[2])
+
+
 def test_matrix_delete_columns_and_rows_bulk():
     rng = np.random.default_rng(11)
     I, J, V = _rand_coo(rng, 300, 400, 8000)
