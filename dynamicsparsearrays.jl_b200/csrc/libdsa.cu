@@ -65,11 +65,15 @@ static void phase1_finish(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t 
         int32_t* flag = ws.flag32.ensure((size_t)n);
         int32_t* idx = ws.idx32.ensure((size_t)n);
         int64_t* mk = ws.miss_keys.ensure((size_t)bs.missing);
-        DSA_LAUNCH("flag_missing", k_flag_missing, gr, 256, 0, st, ws.op_slot.p, n, flag);
-        exclusive_scan_i32<int32_t>(ws.batch.scan, flag, idx, n, nullptr, st);
+        int64_t* nheads_dev = ws.nuniq.ensure(4) + 3;
+        int64_t nheads = 0;
+        DSA_LAUNCH("flag_missing", k_flag_missing, gr, 256, 0, st, ws.op_slot.p, c.partkeys, n, flag);
+        exclusive_scan_i32<int32_t>(ws.batch.scan, flag, idx, n, nheads_dev, st);
         DSA_LAUNCH("compact_missing", k_compact_missing, gr, 256, 0, st, ws.op_slot.p, c.partkeys, idx, n, mk);
-        ws.h_tmp.resize((size_t)bs.missing);
-        DSA_CUDA(cudaMemcpyAsync(ws.h_tmp.data(), mk, (size_t)bs.missing * 8, cudaMemcpyDeviceToHost, st));
+        DSA_CUDA(cudaMemcpyAsync(&nheads, nheads_dev, 8, cudaMemcpyDeviceToHost, st));
+        DSA_CUDA(cudaStreamSynchronize(st));
+        ws.h_tmp.resize((size_t)nheads);
+        DSA_CUDA(cudaMemcpyAsync(ws.h_tmp.data(), mk, (size_t)nheads * 8, cudaMemcpyDeviceToHost, st));
         DSA_CUDA(cudaStreamSynchronize(st));
         std::vector<int64_t> distinct;
         {

@@ -110,14 +110,20 @@ __global__ void __launch_bounds__(256) k_col_lookup(const int64_t* __restrict__ 
     }
 }
 
-__global__ void __launch_bounds__(256) k_flag_missing(const int32_t* __restrict__ op_slot, int64_t n, int32_t* __restrict__ flag) {
+// ops whose column is absent, minus immediate repeats of the same key (columns usually arrive as runs of entries): the
+// host only needs every distinct absent key once, in first-arrival order
+__device__ __forceinline__ bool missing_head(const int32_t* __restrict__ op_slot, const int64_t* __restrict__ partkeys, int64_t i) {
+    return op_slot[i] < 0 && (i == 0 || partkeys[i - 1] != partkeys[i]);
+}
+__global__ void __launch_bounds__(256) k_flag_missing(const int32_t* __restrict__ op_slot, const int64_t* __restrict__ partkeys, int64_t n,
+                                                       int32_t* __restrict__ flag) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) flag[i] = op_slot[i] < 0 ? 1 : 0;
+    if (i < n) flag[i] = missing_head(op_slot, partkeys, i) ? 1 : 0;
 }
 __global__ void __launch_bounds__(256) k_compact_missing(const int32_t* __restrict__ op_slot, const int64_t* __restrict__ partkeys,
                                                           const int32_t* __restrict__ idx, int64_t n, int64_t* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && op_slot[i] < 0) out[idx[i]] = partkeys[i];
+    if (i < n && missing_head(op_slot, partkeys, i)) out[idx[i]] = partkeys[i];
 }
 
 // renumbering after new columns: partition ids are slot indices; moved semaphore cells get their new id (pcsr.jl:128-134)

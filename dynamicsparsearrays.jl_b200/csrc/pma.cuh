@@ -232,12 +232,15 @@ __global__ void __launch_bounds__(256) k_insert_leaf_info(const int64_t* __restr
         const int64_t pq = ins_pos[j - 1];
         if (((pq < 0 ? 0 : pq) >> lgS) == leaf) return;
     }
-    int cnt = 1;
-    for (int64_t t = j + 1; t < n; ++t) {
-        const int64_t pt = ins_pos[t];
-        if (((pt < 0 ? 0 : pt) >> lgS) != leaf) break;
-        ++cnt;
+    // the run of this leaf ends at the first insert whose predecessor lies in a later leaf (positions are sorted)
+    int64_t lo = j + 1, hi = n;
+    const int64_t leaf_end = (leaf + 1) << lgS;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (ins_pos[mid] < leaf_end) lo = mid + 1;
+        else hi = mid;
     }
+    const int cnt = (int)(lo - j);
     inscnt[leaf] = cnt;
     ins_first[leaf] = (int32_t)j;
     touched[leaf] = 1;
@@ -456,17 +459,7 @@ __global__ void __launch_bounds__(256) k_merge_scatter(MergeArgs A, Levels L) {
         dv[d] = val;
         if (A.sem && key == 0) A.sem[(int64_t)val - 1] = d;   // moves.jl:160-166
     }
-    for (int j = lane; j < nins; j += 32) {
-        const int64_t ipos = A.ins_pos[i0 + j];
-        const int q = (int)(ipos - p0);   // -1 .. S-1
-        const int surv_le = q < 0 ? 0 : __popc(lm & (q >= 31 ? 0xffffffffu : ((2u << q) - 1u)));
-        const int64_t d = wbase + spread_dest(sp, base + surv_le + j);
-        const int64_t ik = A.ins_key[i0 + j];
-        const double iv = A.ins_val[i0 + j];
-        dk[d] = ik;
-        dv[d] = iv;
-        if (A.sem && ik == 0) A.sem[(int64_t)iv - 1] = d;
-    }
+    // the leaf's inserts are placed by k_scatter_inserts (one thread per insert: a hot leaf may receive millions)
     if (!A.root_mode && h == 0 && lane == 0) A.leafcnt[l] = (int32_t)m;
 }
 
@@ -637,6 +630,40 @@ __global__ void __launch_bounds__(256) k_window_small(MergeArgs A, Levels L) {
             A.leafcnt[(ws_cell + t) >> lgS] = __popc((b >> lane) & mm);
         }
     }
+}
+
+// Inserts of the big windows / of a resize: one thread per insert (appends and skewed batches pile up to millions of inserts
+// on one leaf, so they cannot be left to the leaf's warp).  rank = prefix of post over the window's preceding leaves
+// + survivors of the leaf up to the predecessor cell + index among the leaf's inserts.
+__global__ void __launch_bounds__(256) k_scatter_inserts(MergeArgs A, Levels L, const int64_t* __restrict__ nins_dev) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= *nins_dev) return;
+    const int64_t ipos = A.ins_pos[j];
+    const int64_t l = (ipos < 0 ? 0 : ipos) >> L.lgS;
+    int h;
+    if (A.root_mode) h = L.H;
+    else {
+        h = (int)A.cover[l] - 1;          // height of the outermost window covering the leaf (k_cover_windows)
+        if (h < A.min_h) return;          // leaf-level or small window: placed by k_leaf_merge / k_window_small
+    }
+    const int S = 1 << L.lgS;
+    const int64_t first_leaf = (l >> h) << h;
+    const int64_t c = A.root_mode ? A.root_c : ((int64_t)S << h);
+    const int64_t m = A.root_mode ? A.root_m : (int64_t)A.post[L.off[h] + (l >> h)];
+    int64_t base = 0;
+    for (int k = 0; k < h; ++k)
+        if ((l >> k) & 1) base += A.post[L.off[k] + ((l >> k) - 1)];
+    const int64_t p0 = l << L.lgS;
+    int surv_le = 0;
+    for (int64_t p = p0; p <= ipos; ++p) surv_le += A.src_k[p] != GAP_KEY;
+    const int64_t r = base + surv_le + (j - A.ins_first[l]);
+    const int64_t wbase = A.root_mode ? 0 : (first_leaf << L.lgS);
+    const int64_t d = wbase + spread_dest(spread_make(c, m), r);
+    const int64_t ik = A.ins_key[j];
+    const double iv = A.ins_val[j];
+    A.dst_k[d] = ik;
+    A.dst_v[d] = iv;
+    if (A.sem && ik == 0) A.sem[(int64_t)iv - 1] = d;
 }
 
 // windows of height >= 1: copy the shadow back, writing the analytic gaps and the new leaf counts
@@ -868,6 +895,8 @@ struct PmaCore {
             nv.ensure((size_t)ng.capacity);
             A.dst_k = nk.p; A.dst_v = nv.p; A.root_mode = 1; A.root_c = ng.capacity; A.root_m = N;
             DSA_LAUNCH("merge_scatter_root", k_merge_scatter, warp_grid, 256, 0, st, A, L);
+            if (hs[ST_NINS] > 0)
+                DSA_LAUNCH("scatter_inserts_root", k_scatter_inserts, grid_for(hs[ST_NINS], 256), 256, 0, st, A, L, ws.status + ST_NINS);
             g = ng;
             leafcnt.ensure((size_t)g.nb_segments);
             DSA_LAUNCH("layout_gaps", k_layout, grid_for(g.capacity, 256), 256, 0, st, nk.p, nv.p, g.capacity, N,
@@ -894,6 +923,8 @@ struct PmaCore {
                 A.dst_v = ws.shadow_v.ensure((size_t)g.capacity);
                 A.min_h = L.hsmall + 1;
                 DSA_LAUNCH("merge_scatter_big", k_merge_scatter, warp_grid, 256, 0, st, A, L);
+                if (hs[ST_NINS] > 0)
+                    DSA_LAUNCH("scatter_inserts_big", k_scatter_inserts, grid_for(hs[ST_NINS], 256), 256, 0, st, A, L, ws.status + ST_NINS);
                 DSA_LAUNCH("copyback_big", k_copyback, warp_grid, 256, 0, st, keys.p, vals.p, A.dst_k, A.dst_v, post, mark, leafcnt.p, L,
                            L.hsmall + 1);
             }
@@ -939,8 +970,9 @@ struct PmaCore {
             exclusive_scan_i32<int32_t>(ws.scan, f32, ws.ins_idx.p, nops, ws.status + ST_NINS, st);
             DSA_LAUNCH("compact_inserts", k_compact_inserts, gr, 256, 0, st, op_key, op_val, ws.op_pos.p, ws.op_flag.p, ws.ins_idx.p,
                        nops, ws.ins_key.p, ws.ins_val.p, ws.ins_pos.p, n_dev);
+            ActiveLeaf* act = ws.act.ensure((size_t)std::min<int64_t>(nops, g.nb_segments) + 1);
             DSA_LAUNCH("insert_leaf_info", k_insert_leaf_info, gr, 256, 0, st, ws.ins_pos.p, ws.status + ST_NINS, ws.inscnt,
-                       ws.ins_first.p, ws.touched, lgS, ws.act.ensure((size_t)std::min<int64_t>(nops, g.nb_segments) + 1), ws.status + ST_NACT);
+                       ws.ins_first.p, ws.touched, lgS, act, ws.status + ST_NACT);
         }
         rebalance_launch(ws, st);
         if (!launch_only) {

@@ -1,0 +1,127 @@
+#!/usr/bin/env python
+"""Secondary measurements for BASELINE.md §5 (not the bench.py contract line): BASELINE.json configs C1, C3 and C5 on one B200,
+each next to the CPU oracle (C++ restatement of the reference, 1 core) on the same inputs.  Prints one JSON object per config.
+    python profiles/bench_configs.py            (run under gpurun)"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import dsa_b200 as D  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+
+def timed(f, reps=1):
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        r = f()
+    return (time.perf_counter() - t0) / reps, r
+
+
+def c1():
+    rng = np.random.default_rng(0xD5A00001)
+    keys = np.unique(rng.integers(1, 10_000_000_000, 1_000_000))
+    vals = rng.integers(10, 100001, len(keys)) / 10.0
+    t_build_g, gv = timed(lambda: D.dynamicsparsevec(keys, vals))
+    t_build_o, ov = timed(lambda: O.Vec(keys, vals))
+    nb, rounds = 100_000, 10
+    tg = to = 0.0
+    live = keys
+    for r in range(rounds):
+        ins_k = rng.integers(1, 10_000_000_000, nb // 2)
+        del_k = rng.choice(live, nb // 2, replace=False)
+        bk = np.concatenate([ins_k, del_k])
+        bv = np.concatenate([rng.integers(10, 100001, nb // 2) / 10.0, np.zeros(nb // 2)])
+        p = rng.permutation(nb)
+        bk, bv = bk[p], bv[p]
+        dt, _ = timed(lambda: gv.set_batch(bk, bv))
+        tg += dt
+        dt, _ = timed(lambda: ov.set_many(bk, bv))
+        to += dt
+        live = np.setdiff1d(np.union1d(live, ins_k), del_k)
+    q = rng.choice(live, 1_000_000)
+    t_get_g, a = timed(lambda: gv.get_batch(q))
+    t_get_o, b = timed(lambda: ov.get_many(q))
+    assert np.array_equal(a, b)
+    return {"config": "C1 dynamicsparsevec PMA, 1M keys, 100k mixed ops per flush (host buffers, synchronous call)",
+            "gpu_Mupdates_s": nb * rounds / tg / 1e6, "cpu_Mupdates_s": nb * rounds / to / 1e6,
+            "gpu_build_s": t_build_g, "cpu_build_s": t_build_o, "gpu_Mfinds_s": 1.0 / t_get_g, "cpu_Mfinds_s": 1.0 / t_get_o}
+
+
+def c3():
+    rng = np.random.default_rng(0xD5A00003)
+    m, cols_per_round, nnz_per_col, rounds = 100_000, 10_000, 50, 10
+
+    def new_columns(first_id):
+        J = np.repeat(np.arange(first_id, first_id + cols_per_round), nnz_per_col)
+        I = rng.integers(1, m + 1, len(J))
+        return I, J, rng.random(len(I)) + 0.01
+
+    I, J, V = new_columns(1)
+    tg, gm = timed(lambda: D.dynamicsparse(I, J, V, m=m))
+    to, om = timed(lambda: O.Matrix(I, J, V, m=m))
+    live = list(range(1, cols_per_round + 1))
+    nxt = cols_per_round + 1
+    upd = len(I)
+    t_spmv_g = t_spmv_o = 0.0
+    for r in range(1, rounds):
+        I, J, V = new_columns(nxt)
+        dt, _ = timed(lambda: gm.set_batch(I, J, V)); tg += dt
+        dt, _ = timed(lambda: om.set_many(I, J, V)); to += dt
+        live += list(range(nxt, nxt + cols_per_round))
+        nxt += cols_per_round
+        dead = rng.choice(np.array(live[:-1]), len(live) // 20, replace=False)
+        dt, _ = timed(lambda: D.deletecolumn(gm, dead)); tg += dt
+
+        def seqdel():
+            for c in dead:
+                om.deletecolumn(int(c))
+        dt, _ = timed(seqdel); to += dt
+        ds = set(dead.tolist())
+        live = [c for c in live if c not in ds]
+        upd += len(I) + len(dead) * nnz_per_col
+        mm, nn = gm.size
+        x, pi = rng.random(nn), rng.random(mm)
+        dt, y1 = timed(lambda: (gm.mul_dense(x), gm.mul_dense(pi, trans=True))); t_spmv_g += dt
+        dt, y2 = timed(lambda: (om.mul_dense(x, mm), om.mul_dense(pi, nn, trans=True))); t_spmv_o += dt
+        assert np.allclose(y1[0], y2[0], rtol=1e-12) and np.allclose(y1[1], y2[1], rtol=1e-12)
+    return {"config": "C3 column generation: 10 rounds x (append 10k cols x 50 nnz, deletecolumn! 5%, A*x and A'*pi), host buffers",
+            "gpu_Mupdates_s": upd / tg / 1e6, "cpu_Mupdates_s": upd / to / 1e6, "gpu_total_s": tg + t_spmv_g, "cpu_total_s": to + t_spmv_o,
+            "gpu_spmv_pair_ms": 1e3 * t_spmv_g / (rounds - 1), "cpu_spmv_pair_ms": 1e3 * t_spmv_o / (rounds - 1),
+            "live_columns": len(live), "nnz": D.nnz(gm)}
+
+
+def c5():
+    rng = np.random.default_rng(0xD5A00005)
+    m = n = 100_000
+    nnz = 10_000_000
+    I, J = rng.integers(1, m + 1, nnz), rng.integers(1, n + 1, nnz)
+    V = rng.random(nnz) + 1e-3
+    gm = D.dynamicsparse(I, J, V, m=m, n=n)
+    om = O.Matrix(I, J, V, m=m, n=n)
+    w = 1.0 / np.arange(1, m + 1)
+    cdf = np.cumsum(w) / w.sum()
+    nb = 1_000_000
+    I2, J2 = np.searchsorted(cdf, rng.random(nb)) + 1, np.searchsorted(cdf, rng.random(nb)) + 1
+    V2 = rng.random(nb) + 1e-3
+    tg, _ = timed(lambda: gm.set_batch(I2, J2, V2))
+    sample = 200_000
+    to, _ = timed(lambda: om.set_many(I2[:sample], J2[:sample], V2[:sample]))
+    hot = rng.choice(n, 100, replace=False) + 1
+    I3 = np.concatenate([np.arange(m + 1, m + 1 + 10_000) for _ in hot])
+    J3 = np.repeat(hot, 10_000)
+    V3 = rng.random(len(I3)) + 1e-3
+    tg2, _ = timed(lambda: gm.set_batch(I3, J3, V3))
+    to2, _ = timed(lambda: om.set_many(I3[:sample], J3[:sample], V3[:sample]))
+    return {"config": "C5 skew on the C2 matrix: 1M Zipf(1.0) x Zipf(1.0) inserts; 1M monotone inserts into 100 hot columns (host buffers)",
+            "gpu_zipf_Mupdates_s": nb / tg / 1e6, "cpu_zipf_Mupdates_s": sample / to / 1e6, "gpu_monotone_Mupdates_s": len(I3) / tg2 / 1e6,
+            "cpu_monotone_Mupdates_s": sample / to2 / 1e6, "cpu_sample": sample, "capacity_after": gm.info(0)["capacity"]}
+
+
+if __name__ == "__main__":
+    D.require_gpu()
+    for f in (c1, c3, c5):
+        print(json.dumps(f()), flush=True)
