@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <ctime>
 #include <map>
 #include <string>
 #include <vector>
@@ -75,6 +76,78 @@ struct LaunchScope {   // brackets ONE kernel launch
         DSA_CUDA(cudaGetLastError());                                              \
     } while (0)
 
+// host-timed allocator calls show up in the profile dump as "(cudaMalloc)" / "(cudaFree)"
+struct AllocTimer {
+    const char* name;
+    double t0;
+    static double now() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    }
+    explicit AllocTimer(const char* n) : name(n), t0(prof().enabled ? now() : 0.0) {}
+    ~AllocTimer() {
+        if (prof().enabled) {
+            ProfEntry& e = prof().entries[name];
+            e.count += 1;
+            e.ms += now() - t0;
+        }
+    }
+};
+
+// ---- caching device allocator ---------------------------------------------------------------------
+// cudaMalloc / cudaFree of the 100 MB-class buffers of a growing structure cost milliseconds each (measured: 230 ms per batch
+// while a matrix doubles, profiles/prof_c5.py).  Blocks are therefore recycled: sizes are rounded to 4 classes per octave,
+// a released block goes back to a free list after a device synchronisation (the same guarantee cudaFree gives: nobody is
+// still using it), and is handed out again to the next request of a compatible size.  dsa_trim_memory() returns the cached
+// blocks to the driver.
+struct DevicePool {
+    std::multimap<size_t, void*> free_blocks;
+    size_t cached_bytes = 0;
+    static size_t size_class(size_t bytes) {
+        if (bytes < 4096) return 4096;
+        int lg = 63 - __builtin_clzll((unsigned long long)bytes);
+        const size_t step = size_t(1) << (lg - 2);
+        return (bytes + step - 1) / step * step;
+    }
+    void* get(size_t bytes) {
+        const size_t want = size_class(bytes);
+        auto it = free_blocks.lower_bound(want);
+        if (it != free_blocks.end() && it->first <= want + want / 2) {
+            void* p = it->second;
+            cached_bytes -= it->first;
+            free_blocks.erase(it);
+            return p;
+        }
+        void* p = nullptr;
+        AllocTimer t("(cudaMalloc)");
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {   // give the cache back to the driver and retry once
+            cudaGetLastError();
+            trim();
+            e = cudaMalloc(&p, want);
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            throw DsaError{DSA_ERR_OOM, "cudaMalloc(" + std::to_string(want) + " bytes): " + cudaGetErrorString(e)};
+        }
+        return p;
+    }
+    void put(void* p, size_t bytes) {
+        cudaDeviceSynchronize();   // what cudaFree would have guaranteed: no queued work still touches the block
+        const size_t c = size_class(bytes);
+        free_blocks.emplace(c, p);
+        cached_bytes += c;
+    }
+    void trim() {
+        AllocTimer t("(cudaFree)");
+        for (auto& kv : free_blocks) cudaFree(kv.second);
+        free_blocks.clear();
+        cached_bytes = 0;
+    }
+};
+DevicePool& device_pool();
+
 // ---- device buffer that only grows ------------------------------------------------------------
 template <typename T>
 struct DBuf {
@@ -85,7 +158,7 @@ struct DBuf {
     DBuf& operator=(const DBuf&) = delete;
     ~DBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (p) device_pool().put(p, cap * sizeof(T));
         p = nullptr;
         cap = 0;
     }
@@ -93,23 +166,9 @@ struct DBuf {
     T* ensure(size_t n) {
         if (n > cap) {
             release();
-            size_t want = n + n / 4 + 64;
-            DSA_CUDA(cudaMalloc(&p, want * sizeof(T)));
-            cap = want;
-        }
-        return p;
-    }
-    // contents preserved (copy on stream)
-    T* grow_keep(size_t n, size_t keep, cudaStream_t st) {
-        if (n > cap) {
-            size_t want = n + n / 2 + 64;
-            T* q = nullptr;
-            DSA_CUDA(cudaMalloc(&q, want * sizeof(T)));
-            if (p && keep) DSA_CUDA(cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st));
-            DSA_CUDA(cudaStreamSynchronize(st));
-            if (p) cudaFree(p);
-            p = q;
-            cap = want;
+            const size_t bytes = DevicePool::size_class((n + 64) * sizeof(T));
+            p = (T*)device_pool().get(bytes);
+            cap = bytes / sizeof(T);
         }
         return p;
     }

@@ -10,6 +10,10 @@ Prof& prof() {
     static Prof p;
     return p;
 }
+DevicePool& device_pool() {
+    static DevicePool* p = new DevicePool();   // never destroyed: handles may be released during interpreter shutdown
+    return *p;
+}
 
 static thread_local std::string g_last_error;
 
@@ -1101,6 +1105,14 @@ int dsa_route_batch2_d(const int64_t* d_rows, const int64_t* d_cols, const doubl
 }
 
 // ---- measurement ------------------------------------------------------------------------------------------------------
+int dsa_trim_memory(void) {
+    DSA_TRY
+    cudaDeviceSynchronize();
+    device_pool().trim();
+    return DSA_OK;
+    DSA_CATCH
+}
+int64_t dsa_cached_bytes(void) { return (int64_t)device_pool().cached_bytes; }
 int64_t dsa_launch_count(void) { return prof().launches; }
 int dsa_prof_enable(int on) {
     prof().enabled = on != 0;

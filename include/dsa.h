@@ -168,6 +168,12 @@ int dsa_route_batch2_d(const int64_t* d_rows, const int64_t* d_cols, const doubl
                        const int64_t* row_splitters, int nranks, int64_t* d_packed_by_col, int64_t* d_packed_by_row,
                        int64_t* counts_by_col, int64_t* counts_by_row, void* cuda_stream);
 
+/* ---------------------------------------------------------------- memory --------------- */
+/* device buffers are recycled through a size-class cache (growth of a structure would otherwise pay cudaMalloc/cudaFree of
+ * 100 MB-class blocks per batch); dsa_trim_memory returns the cached blocks to the driver */
+int dsa_trim_memory(void);
+int64_t dsa_cached_bytes(void);
+
 /* ---------------------------------------------------------------- measurement ---------- */
 /* kernel launches issued by this library since load (bench.py's gpu_launches) */
 int64_t dsa_launch_count(void);
