@@ -32,7 +32,9 @@ def main_dist(args, rank, world, local_rank):
     os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     D.lib().dsa_set_device(C.c_int(local_rank))
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import datetime
+    # a short collective timeout: a hang must abort within minutes instead of holding N GPUs for the default 10
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=90))
     dev = torch.device("cuda", local_rank)
     L = D.lib()
     K, W = args.steps, max(args.warmup, 3)
@@ -61,9 +63,15 @@ def main_dist(args, rank, world, local_rank):
     d_x = torch.from_numpy(x_h).to(dev)
     d_sh = [tuple(torch.from_numpy(a).to(dev) for a in s) for s in shares[:K + W]]
 
-    # software pipeline: the routing + NCCL exchange of batch s+1 (background router, own stream and communicator) overlaps
-    # with the application of batch s; every batch is submitted and applied inside the timed region
+    # Default: every step routes, exchanges and applies its batch synchronously (validated on 2/4/8 GPUs).
+    # DSA_DIST_PIPELINE=1 (experimental, validated on 2 GPUs only): the routing + NCCL exchange of batch s+1 runs on a
+    # background router (own stream and communicator) and overlaps the application of batch s.
+    PIPE = os.environ.get("DSA_DIST_PIPELINE", "0") == "1"
+
     def step_dev(s, last):
+        if not PIPE:
+            A.set_batch(*d_sh[s])
+            return A.spmv(d_x)
         if s + 1 < last:
             A.submit(*d_sh[s + 1])
         A.apply_next()
@@ -72,7 +80,8 @@ def main_dist(args, rank, world, local_rank):
     sampler = B.ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()   # samples every 100 ms from the warm-up to the end of the e2e loop (the timed regions are ~10 ms each)
-    A.submit(*d_sh[0])
+    if PIPE:
+        A.submit(*d_sh[0])
     for s in range(W):
         y = step_dev(s, W + K)
     torch.cuda.synchronize()
@@ -99,13 +108,18 @@ def main_dist(args, rank, world, local_rank):
     h_x = torch.from_numpy(x_h).pin_memory()
 
     def step_host(s, last):
+        xx = h_x.to(dev, non_blocking=True)
+        if not PIPE:
+            bi, bj, bv = (t.to(dev, non_blocking=True) for t in h_sh[s])
+            A.set_batch(bi, bj, bv)
+            return A.spmv(xx).cpu()
         if s + 1 < last:
             A.submit(*h_sh[s + 1])            # pinned host share: its H2D copy runs on the router's stream
-        xx = h_x.to(dev, non_blocking=True)
         A.apply_next()
         return A.spmv(xx).cpu()
 
-    A.submit(*h_sh[0])
+    if PIPE:
+        A.submit(*h_sh[0])
     for s in range(W):
         yh = step_host(s, W + K)
     torch.cuda.synchronize()
@@ -147,7 +161,8 @@ def main_dist(args, rank, world, local_rank):
         cfg = B.workload_config(world)
         cfg["workload"] = (f"C4-style weak scaling: PCSR {m} x {n}, {nnz_block * world * world} nnz sharded by column range over {world} GPUs; "
                            f"step = {B.BATCH * world} updates routed to both orientations (NCCL all-to-all) + SpMV with all-gather")
-        cfg.update(rows=m, cols=n, nnz=nnz_block * world * world, batch=B.BATCH * world)
+        cfg.update(rows=m, cols=n, nnz=nnz_block * world * world, batch=B.BATCH * world,
+                   routing="pipelined (background router)" if PIPE else "synchronous per step")
         os.dup2(saved_stdout, 1)
         print(json.dumps({
             "metric": "batched PCSR insert/delete Mupdates/s", "value": value, "unit": "Mupdates/s", "n_gpus": world, "steps": K,

@@ -115,10 +115,16 @@ def exchange(arrays, send_counts, group=None):
 
 
 class ShardedMatrix:
-    """set_batch(rows, cols, vals) routes + exchanges + applies one batch.  For streams of batches, submit(...) hands the
-    routing and the NCCL exchange of a batch to a background router (own CUDA stream, own communicator) so that they overlap
-    with the application of the previous batch; apply_next() applies the oldest submitted batch.  Every rank must submit
-    and apply in the same order."""
+    """set_batch(rows, cols, vals) routes + exchanges + applies one batch (validated on 2, 4 and 8 GPUs).
+
+    EXPERIMENTAL: submit(...) hands the routing and the NCCL exchange of a batch to a background router (own CUDA stream,
+    own communicator) so that they overlap with the application of the previous batch; apply_next() applies the oldest
+    submitted batch.  Measured 2 043 Mupdates/s on 2 GPUs (86 % weak-scaling efficiency), but it DEADLOCKED on 8 GPUs: the
+    router's blocking host<->device copies synchronise with the legacy default stream, which is itself waiting on the main
+    thread's all-gather, while other ranks wait for this router's all-to-all (two communicators, inconsistent order).  The
+    fix (main work on a non-default stream, pinned non-blocking count exchange, all-gather issued only after the router has
+    enqueued the next batch's collectives) is not validated yet, so bench.py uses the synchronous path unless
+    DSA_DIST_PIPELINE=1."""
 
     def __init__(self, m, n, backend, group=None):
         self.group = group
