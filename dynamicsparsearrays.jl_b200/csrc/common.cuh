@@ -6,6 +6,7 @@
 #include <cstring>
 #include <ctime>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "../../include/dsa.h"
@@ -104,6 +105,7 @@ struct AllocTimer {
 struct DevicePool {
     std::multimap<size_t, void*> free_blocks;
     size_t cached_bytes = 0;
+    std::mutex mu;   // handles of different host threads share the pool
     static size_t size_class(size_t bytes) {
         if (bytes < 4096) return 4096;
         int lg = 63 - __builtin_clzll((unsigned long long)bytes);
@@ -111,6 +113,7 @@ struct DevicePool {
         return (bytes + step - 1) / step * step;
     }
     void* get(size_t bytes) {
+        std::lock_guard<std::mutex> lock(mu);
         const size_t want = size_class(bytes);
         auto it = free_blocks.lower_bound(want);
         if (it != free_blocks.end() && it->first <= want + want / 2) {
@@ -124,7 +127,7 @@ struct DevicePool {
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) {   // give the cache back to the driver and retry once
             cudaGetLastError();
-            trim();
+            trim_locked();
             e = cudaMalloc(&p, want);
         }
         if (e != cudaSuccess) {
@@ -135,15 +138,20 @@ struct DevicePool {
     }
     void put(void* p, size_t bytes) {
         cudaDeviceSynchronize();   // what cudaFree would have guaranteed: no queued work still touches the block
+        std::lock_guard<std::mutex> lock(mu);
         const size_t c = size_class(bytes);
         free_blocks.emplace(c, p);
         cached_bytes += c;
     }
-    void trim() {
+    void trim_locked() {
         AllocTimer t("(cudaFree)");
         for (auto& kv : free_blocks) cudaFree(kv.second);
         free_blocks.clear();
         cached_bytes = 0;
+    }
+    void trim() {
+        std::lock_guard<std::mutex> lock(mu);
+        trim_locked();
     }
 };
 DevicePool& device_pool();
