@@ -36,6 +36,13 @@ def main_dist(args, rank, world, local_rank):
     # a short collective timeout: a hang must abort within minutes instead of holding N GPUs for the default 10
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=90))
     dev = torch.device("cuda", local_rank)
+    # Default: every step routes, exchanges and applies its batch synchronously (validated on 2/4/8 GPUs).
+    # DSA_DIST_PIPELINE=1 (experimental): the routing + NCCL exchange of batch s+1 runs on a background router (own stream and
+    # communicator) and overlaps the application of batch s; the main work then runs on a non-default stream so that nothing
+    # the router does can synchronise with it implicitly.
+    PIPE = os.environ.get("DSA_DIST_PIPELINE", "0") == "1"
+    if PIPE:
+        torch.cuda.set_stream(torch.cuda.Stream(device=dev))
     L = D.lib()
     K, W = args.steps, max(args.warmup, 3)
     per = B.M_ROWS                       # rows / cols per rank
@@ -62,11 +69,6 @@ def main_dist(args, rank, world, local_rank):
     x_h = np.random.default_rng([B.SEED, 9]).random(n)
     d_x = torch.from_numpy(x_h).to(dev)
     d_sh = [tuple(torch.from_numpy(a).to(dev) for a in s) for s in shares[:K + W]]
-
-    # Default: every step routes, exchanges and applies its batch synchronously (validated on 2/4/8 GPUs).
-    # DSA_DIST_PIPELINE=1 (experimental, validated on 2 GPUs only): the routing + NCCL exchange of batch s+1 runs on a
-    # background router (own stream and communicator) and overlaps the application of batch s.
-    PIPE = os.environ.get("DSA_DIST_PIPELINE", "0") == "1"
 
     def step_dev(s, last):
         if not PIPE:

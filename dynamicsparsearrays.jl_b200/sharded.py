@@ -119,12 +119,12 @@ class ShardedMatrix:
 
     EXPERIMENTAL: submit(...) hands the routing and the NCCL exchange of a batch to a background router (own CUDA stream,
     own communicator) so that they overlap with the application of the previous batch; apply_next() applies the oldest
-    submitted batch.  Measured 2 043 Mupdates/s on 2 GPUs (86 % weak-scaling efficiency), but it DEADLOCKED on 8 GPUs: the
-    router's blocking host<->device copies synchronise with the legacy default stream, which is itself waiting on the main
-    thread's all-gather, while other ranks wait for this router's all-to-all (two communicators, inconsistent order).  The
-    fix (main work on a non-default stream, pinned non-blocking count exchange, all-gather issued only after the router has
-    enqueued the next batch's collectives) is not validated yet, so bench.py uses the synchronous path unless
-    DSA_DIST_PIPELINE=1."""
+    submitted batch.  The first version measured 2 043 Mupdates/s on 2 GPUs (86 % weak-scaling efficiency) but DEADLOCKED
+    on 8 GPUs: the router's blocking host<->device copies synchronised with the legacy default stream, which was itself
+    waiting on the main thread's all-gather, while other ranks waited for this router's all-to-all (two communicators,
+    inconsistent order).  This version (pinned non-blocking count exchange, all-gather issued only after the router has
+    enqueued the collectives of every submitted batch; the caller should also run its main work on a non-default stream)
+    passes the gloo test but has not run on GPUs yet, so bench.py uses the synchronous path unless DSA_DIST_PIPELINE=1."""
 
     def __init__(self, m, n, backend, group=None):
         self.group = group
@@ -182,27 +182,89 @@ class ShardedMatrix:
             out.append((cols3[0], cols3[1], cols3[2].view(torch.float64)))
         return out
 
+    def _route_exchange_router(self, rows, cols, vals, group):
+        """_route_exchange as issued by the router thread.  Differences that matter for deadlock freedom: no blocking
+        pageable copy (those synchronise with the legacy default stream, which may be waiting on the main thread's
+        all-gather): the counts travel through pinned buffers with non-blocking copies and a *stream* synchronisation."""
+        W = self.world
+        dev = rows.device
+        if dev.type != "cuda":   # gloo / CPU tensors (tests): same protocol, host routing
+            r1, c1, v1, cnt_c = route(cols, rows, cols, vals, self.col_split, W)
+            r2, c2, v2, cnt_r = route(rows, rows, cols, vals, self.row_split, W)
+            sc = torch.tensor([x for pair in zip(cnt_c, cnt_r) for x in pair], dtype=torch.int64)
+            rc = torch.empty_like(sc)
+            dist.all_to_all_single(rc, sc, group=group)
+            rc = rc.view(W, 2).tolist()
+            out = []
+            for (r, c, v, snd, rcv) in ((r1, c1, v1, cnt_c, [p[0] for p in rc]), (r2, c2, v2, cnt_r, [p[1] for p in rc])):
+                packed = torch.stack((r, c, v.view(torch.int64)), dim=1).contiguous()
+                recv = torch.empty((int(sum(rcv)), 3), dtype=torch.int64)
+                dist.all_to_all_single(recv, packed, output_split_sizes=rcv, input_split_sizes=list(snd), group=group)
+                cols3 = recv.t().contiguous()
+                out.append((cols3[0], cols3[1], cols3[2].view(torch.float64)))
+            return out
+        n = rows.numel()
+        st = torch.cuda.current_stream()
+        pk_c = torch.empty((n, 3), dtype=torch.int64, device=dev)
+        pk_r = torch.empty((n, 3), dtype=torch.int64, device=dev)
+        cc, cr = np.zeros(W, np.int64), np.zeros(W, np.int64)
+        isc = np.asarray(self.col_split[1:-1], dtype=np.int64)
+        isr = np.asarray(self.row_split[1:-1], dtype=np.int64)
+        check(lib().dsa_route_batch2_d(C.c_void_p(rows.data_ptr()), C.c_void_p(cols.data_ptr()), C.c_void_p(vals.data_ptr()), C.c_int64(n),
+                                       C.c_void_p(isc.ctypes.data), C.c_void_p(isr.ctypes.data), C.c_int(W), C.c_void_p(pk_c.data_ptr()),
+                                       C.c_void_p(pk_r.data_ptr()), C.c_void_p(cc.ctypes.data), C.c_void_p(cr.ctypes.data),
+                                       C.c_void_p(st.cuda_stream)))
+        cnt_c, cnt_r = cc.tolist(), cr.tolist()
+        h_sc = torch.tensor([x for pair in zip(cnt_c, cnt_r) for x in pair], dtype=torch.int64).pin_memory()
+        sc = h_sc.to(dev, non_blocking=True)
+        rc = torch.empty_like(sc)
+        dist.all_to_all_single(rc, sc, group=group)
+        h_rc = torch.empty(2 * W, dtype=torch.int64).pin_memory()
+        h_rc.copy_(rc, non_blocking=True)
+        st.synchronize()
+        rcl = h_rc.view(W, 2).tolist()
+        out = []
+        for (packed, snd, rcv) in ((pk_c, cnt_c, [p[0] for p in rcl]), (pk_r, cnt_r, [p[1] for p in rcl])):
+            recv = torch.empty((int(sum(rcv)), 3), dtype=torch.int64, device=dev)
+            dist.all_to_all_single(recv, packed, output_split_sizes=rcv, input_split_sizes=list(snd), group=group)
+            cols3 = recv.t().contiguous()
+            out.append((cols3[0], cols3[1], cols3[2].view(torch.float64)))
+        return out
+
     def _start_router(self, device):
         self._tasks, self._routed = queue.Queue(), queue.Queue()
         self._comm_group = dist.new_group(ranks=list(range(self.world)))   # own communicator: never shared with the main thread
-        self._comm_stream = torch.cuda.Stream(device=device)
+        self._cuda = device is not None and device.type == "cuda"
+        self._comm_stream = torch.cuda.Stream(device=device) if self._cuda else None
+        # collectives of the two communicators must be enqueued in the same order on every rank: the main thread's
+        # all-gather waits until the router has enqueued the collectives of every batch submitted so far
+        self._order = threading.Condition()
+        self._unissued = 0
 
         def loop():
-            torch.cuda.set_device(device)
-            lib().dsa_set_device(C.c_int(device.index))
+            if self._cuda:
+                torch.cuda.set_device(device)
+                lib().dsa_set_device(C.c_int(device.index))
             while True:
                 task = self._tasks.get()
                 if task is None:
                     return
                 try:
-                    with torch.cuda.stream(self._comm_stream):
-                        rows, cols, vals = (t.to(device, non_blocking=True) for t in task)   # host shares are copied here, overlapped too
-                        out = self._route_exchange(rows, cols, vals, self._comm_group)
-                        ev = torch.cuda.Event()
-                        ev.record(self._comm_stream)
+                    if self._cuda:
+                        with torch.cuda.stream(self._comm_stream):
+                            rows, cols, vals = (t.to(device, non_blocking=True) for t in task)   # pinned host shares are copied here
+                            out = self._route_exchange_router(rows, cols, vals, self._comm_group)
+                            ev = torch.cuda.Event()
+                            ev.record(self._comm_stream)
+                    else:
+                        out, ev = self._route_exchange_router(*task, self._comm_group), None
                     self._routed.put((out, ev, None))
                 except Exception as ex:   # surfaced by apply_next
                     self._routed.put((None, None, ex))
+                finally:
+                    with self._order:
+                        self._unissued -= 1
+                        self._order.notify_all()
 
         self._router = threading.Thread(target=loop, daemon=True)
         self._router.start()
@@ -210,19 +272,34 @@ class ShardedMatrix:
     def submit(self, rows, cols, vals):
         """enqueue this rank's share of the next global batch (device tensors, or pinned host tensors)"""
         if self._router is None:
-            self._start_router(self.local.device)
+            self._start_router(getattr(self.local, "device", None))
+        with self._order:
+            self._unissued += 1
         self._tasks.put((rows, cols, vals))
+
+    def _wait_router_issued(self):
+        if self._router is not None:
+            with self._order:
+                while self._unissued > 0:
+                    self._order.wait()
 
     def apply_next(self):
         """apply the oldest submitted batch to the local shards (blocks until its routing has been issued)"""
         out, ev, ex = self._routed.get()
         if ex is not None:
             raise ex
-        torch.cuda.current_stream().wait_event(ev)
-        self.local.set_batch_two(out[0], out[1])
-        for triple in out:   # the tensors were allocated on the router's stream
-            for t in triple:
-                t.record_stream(torch.cuda.current_stream())
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+        if hasattr(self.local, "set_batch_two"):
+            self.local.set_batch_two(out[0], out[1])
+        else:   # backends with one call per orientation (the CPU backend of the gloo tests)
+            (r1, c1, v1), (r2, c2, v2) = out
+            self.local.set_batch(_lib.COLMAJOR, r1, c1, v1)
+            self.local.set_batch(_lib.ROWMAJOR, c2, r2, v2)
+        if ev is not None:
+            for triple in out:   # the tensors were allocated on the router's stream
+                for t in triple:
+                    t.record_stream(torch.cuda.current_stream())
 
     def close(self):
         if self._router is not None:
@@ -245,6 +322,7 @@ class ShardedMatrix:
         y = torch.zeros(per * self.world, dtype=torch.float64, device=x.device)
         y_slice = y[self.rank * per:(self.rank + 1) * per]
         self.local.spmv_range(trans, x, y_slice, lo, lo + per)   # epilogue writes this rank's slice of the gather buffer
+        self._wait_router_issued()                               # keep the cross-communicator collective order identical on all ranks
         if y.is_cuda:
             dist.all_gather_into_tensor(y, y_slice, group=self.group)      # in place: the slice already sits at its offset
         else:                                                              # gloo (CPU tests)

@@ -46,7 +46,7 @@ class OracleBackend:
         y_slice.copy_(torch.from_numpy(y[key_lo - 1:key_hi - 1].copy()))
 
 
-def _worker(rank, world, port, m, n, seed, q):
+def _worker(rank, world, port, m, n, seed, q, pipelined=False):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -59,11 +59,11 @@ def _worker(rank, world, port, m, n, seed, q):
         A = ShardedMatrix(m, n, OracleBackend())
         G = O.Matrix(fill_mode=False)     # the global matrix, replicated as the checker
         rng = np.random.default_rng(seed)  # same stream on both ranks: every rank knows the whole global batch
+        rounds = []
         for rnd in range(4):
             nb = 3000
             I, J = rng.integers(1, m + 1, nb), rng.integers(1, n + 1, nb)
             V = np.where(rng.random(nb) < 0.3, 0.0, rng.integers(1, 9, nb).astype(float))
-            G.set_batch_policy(I, J, V)
             mine = slice(rank * nb // world, (rank + 1) * nb // world)   # this rank's share, in arrival order
             # LWW across ranks needs a global arrival order: shares are disjoint in (i, j) here (dedupe the global batch first)
             lin = I * (n + 1) + J
@@ -72,11 +72,22 @@ def _worker(rank, world, port, m, n, seed, q):
             keep[nb - 1 - first] = True
             sel = np.nonzero(keep)[0]
             sel = sel[(sel >= mine.start) & (sel < mine.stop)]
-            A.set_batch(torch.from_numpy(I[sel]), torch.from_numpy(J[sel]), torch.from_numpy(V[sel]))
+            share = (torch.from_numpy(I[sel]), torch.from_numpy(J[sel]), torch.from_numpy(V[sel]))
             x = torch.from_numpy(rng.integers(0, 4, n).astype(float))
+            xt = torch.from_numpy(rng.integers(0, 4, m).astype(float))
+            rounds.append((I, J, V, share, x, xt))
+        if pipelined:   # background router (own communicator): batch s+1 is routed + exchanged while batch s is applied and
+            A.submit(*rounds[0][3])   # multiplied -- the all-gathers of spmv interleave with the router's all-to-alls
+        for s, (I, J, V, share, x, xt) in enumerate(rounds):
+            G.set_batch_policy(I, J, V)
+            if pipelined:
+                if s + 1 < len(rounds):
+                    A.submit(*rounds[s + 1][3])
+                A.apply_next()
+            else:
+                A.set_batch(*share)
             y = A.spmv(x).numpy()
             assert np.array_equal(y, G.mul_dense(x.numpy(), m)), "A*x differs"
-            xt = torch.from_numpy(rng.integers(0, 4, m).astype(float))
             yt = A.spmv(xt, trans=True).numpy()
             assert np.array_equal(yt, G.mul_dense(xt.numpy(), n, trans=True)), "A'*x differs"
         # shard contents == global contents restricted to the shard
@@ -90,6 +101,7 @@ def _worker(rank, world, port, m, n, seed, q):
         e = A.local.cm.export(0)
         ck = e["col_keys"][e["col_live"] == 1]
         assert np.all(owner_of(ck, A.col_split) == rank)
+        A.close()
         q.put((rank, "ok"))
     except Exception as ex:  # pragma: no cover
         import traceback
@@ -107,12 +119,13 @@ def _free_port():
     return p
 
 
-def test_sharded_two_ranks_gloo():
+@pytest.mark.parametrize("pipelined", [False, True])
+def test_sharded_two_ranks_gloo(pipelined):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, 90, 70, 123, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 90, 70, 123, q, pipelined)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in range(world)]
