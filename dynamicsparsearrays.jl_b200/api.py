@@ -15,6 +15,9 @@ same names, same argument meaning, same error behaviour; the structures themselv
     view(m, :, j) / view(m, i, :)             m.col(j) / m.row(i)  -> (keys, vals) in ascending key order
     m * v, transpose(m) * v, v * m, ...       m @ v, m.T @ v, v @ m, v @ m.T -> SparseVector
     nnz, nbpartitions, shrink_size!           nnz(x), nbpartitions(m.colmajor), shrink_size(v)
+    u + v, u - v, -v (SparseArrays generics)  same operators -> SparseVector (math.jl:53-93)
+    Char / other isbits keys                  KeyCodec: order-preserving map onto the device's Int64 keys (CharCodec is
+                                              picked automatically for one-character string keys, sparsematrix.jl:302-336)
 """
 import ctypes as C
 
@@ -25,7 +28,7 @@ from ._lib import ArgumentError, ErrorException, check, lib
 
 __all__ = ["DynamicSparseVector", "DynamicSparseMatrix", "DynamicMatrixColView", "SparseVector", "dynamicsparsevec",
            "dynamicsparse", "nbpartitions", "deletepartition", "deletecolumn", "deleterow", "addrow", "closefillmode",
-           "shrink_size", "nnz"]
+           "shrink_size", "nnz", "KeyCodec", "CharCodec"]
 
 
 def _i64(a):
@@ -49,6 +52,101 @@ def _combine(c):
     return _lib.COMBINE[c]
 
 
+class KeyCodec:
+    """Order-preserving map between a caller's key type and the device's Int64 keys.  The device stores and
+    compares Int64 only; any key type whose order an injective, monotone `encode` preserves (Char, Int32, UInt32, enums,
+    dates) goes through the same kernels.  Encoded keys must be >= 1: 0 is the semaphore key (pcsr.jl:23)."""
+
+    identity = False
+
+    def __init__(self, encode, decode):
+        self._enc, self._dec = encode, decode
+
+    def encode(self, keys):
+        out = _i64([self._enc(k) for k in keys])
+        if len(out) and out.min() < 1:
+            raise ArgumentError(_lib.DSA_ERR_ARGUMENT, "encoded keys must be >= 1 (0 is the semaphore key)")
+        return out
+
+    def encode1(self, key):
+        return int(self.encode([key])[0])
+
+    def decode(self, codes):
+        return [self._dec(int(c)) for c in codes]
+
+    def decode1(self, code):
+        return self._dec(int(code))
+
+
+class _IdentityCodec(KeyCodec):
+    identity = True
+
+    def __init__(self):
+        pass
+
+    def encode(self, keys):
+        return _i64(keys)
+
+    def encode1(self, key):
+        return int(key)
+
+    def decode(self, codes):
+        return codes
+
+    def decode1(self, code):
+        return int(code)
+
+
+class CharCodec(KeyCodec):
+    """Julia `Char` keys (one-character strings here): the code point, which is Char's own ordering."""
+
+    def __init__(self):
+        super().__init__(ord, chr)
+
+
+_IDENTITY = _IdentityCodec()
+
+
+def _codec_for(keys):
+    """CharCodec for one-character string keys, identity for integers (what `dynamicsparse(I, J, V)` infers from eltype)."""
+    if isinstance(keys, np.ndarray):
+        return CharCodec() if keys.dtype.kind in "US" else _IDENTITY
+    for k in keys:
+        return CharCodec() if isinstance(k, str) else _IDENTITY
+    return _IDENTITY
+
+
+def _sv_binary(ka, va, kb, vb, sign):
+    """Merge of two sorted (index, value) lists: a + sign * b, entries that come out 0 are not stored (what SparseArrays'
+    `_binarymap` does for + and -; the reference has no method of its own and falls back to it, math.jl:53-93)."""
+    keys = np.union1d(ka, kb)
+    out = np.zeros(len(keys), np.float64)
+    out[np.searchsorted(keys, ka)] = va
+    ib = np.searchsorted(keys, kb)
+    out[ib] = out[ib] + vb if sign > 0 else out[ib] - vb
+    keep = out != 0.0
+    return keys[keep].astype(np.int64), out[keep]
+
+
+def _as_sorted_pairs(x):
+    if isinstance(x, DynamicSparseVector):
+        k, v = x._raw_nonzeros()
+        return len(x), k, v
+    if isinstance(x, SparseVector):
+        return x.n, _i64(x.nzind), _f64(x.nzval)
+    return None
+
+
+def _sv_arith(a, b, sign):
+    pa, pb = _as_sorted_pairs(a), _as_sorted_pairs(b)
+    if pa is None or pb is None:
+        return NotImplemented
+    if pa[0] != pb[0]:   # SparseArrays: DimensionMismatch
+        raise ArgumentError(_lib.DSA_ERR_ARGUMENT, f"dimension mismatch: {pa[0]} != {pb[0]}")
+    k, v = _sv_binary(pa[1], pa[2], pb[1], pb[2], sign)
+    return SparseVector(pa[0], k, v)
+
+
 class SparseVector:
     """Result of a product (SparseArrays.SparseVector in the reference, operations.jl:11-12): sorted indices + values."""
 
@@ -69,9 +167,21 @@ class SparseVector:
         return y
 
     def __eq__(self, other):   # SparseArrays `==` ignores stored zeros
+        if isinstance(other, DynamicSparseVector):
+            n, k, v = _as_sorted_pairs(other)
+            other = SparseVector(n, k, v)
         return self.n == other.n and np.array_equal(self.todense(), other.todense())
 
     __hash__ = None
+
+    def __add__(self, other):
+        return _sv_arith(self, other, +1)
+
+    def __sub__(self, other):
+        return _sv_arith(self, other, -1)
+
+    def __neg__(self):
+        return SparseVector(self.n, _i64(self.nzind).copy(), -_f64(self.nzval))
 
 
 class _PendingWrites:
@@ -89,24 +199,26 @@ class _PendingWrites:
 
 
 class DynamicSparseVector:
-    """DynamicSparseVector{Int64,Float64} (vector.jl:1-4) backed by a device PMA."""
+    """DynamicSparseVector{K,Float64} (vector.jl:1-4) backed by a device PMA (Int64 keys; other K through a KeyCodec)."""
 
-    def __init__(self, handle, owner=True):
+    def __init__(self, handle, owner=True, key_codec=None):
         self._h = handle
+        self._L = lib()                  # the library that owns the handle (destroy goes back to it)
+        self._kc = key_codec or _IDENTITY
         self._pending = _PendingWrites()
         self.flush_threshold = 1 << 20
 
     def __del__(self):
         try:
             if getattr(self, "_h", None):
-                lib().dsa_vec_destroy(self._h)
+                self._L.dsa_vec_destroy(self._h)
                 self._h = None
         except Exception:
             pass
 
     # -- writes -------------------------------------------------------------------------------
     def __setitem__(self, key, value):   # vector.jl:76-81
-        self._pending.a.append(int(key))
+        self._pending.a.append(self._kc.encode1(key))
         self._pending.v.append(float(value))
         if len(self._pending) >= self.flush_threshold:
             self.flush()
@@ -114,7 +226,7 @@ class DynamicSparseVector:
     def set_batch(self, keys, vals):
         """Batched setindex!: last writer wins, 0.0 deletes (pma.jl:196-213)."""
         self.flush()
-        keys, vals = _i64(keys), _f64(vals)
+        keys, vals = self._kc.encode(keys), _f64(vals)
         if len(keys) != len(vals):
             raise ArgumentError(_lib.DSA_ERR_ARGUMENT, "keys & values must have same length.")
         check(lib().dsa_vec_set_batch(self._h, _p(keys), _p(vals), C.c_int64(len(keys))))
@@ -133,7 +245,7 @@ class DynamicSparseVector:
 
     def get_batch(self, keys):
         self.flush()
-        keys = _i64(keys)
+        keys = self._kc.encode(keys)
         out = np.zeros(len(keys), np.float64)
         check(lib().dsa_vec_get_batch(self._h, _p(keys), C.c_int64(len(keys)), _p(out)))
         return out
@@ -154,6 +266,10 @@ class DynamicSparseVector:
 
     def nonzeros(self):
         """(nonzeroinds, nonzeros) = iteration order of the PMA (vector.jl:93-109, pma.jl:165-180)."""
+        k, v = self._raw_nonzeros()
+        return self._kc.decode(k), v
+
+    def _raw_nonzeros(self):
         self.flush()
         n = self.info()["nnz"]
         k, v = np.zeros(max(n, 1), np.int64), np.zeros(max(n, 1), np.float64)
@@ -163,7 +279,7 @@ class DynamicSparseVector:
 
     def __iter__(self):      # vector.jl:71
         k, v = self.nonzeros()
-        return iter(zip(k.tolist(), v.tolist()))
+        return iter(zip(k.tolist() if hasattr(k, "tolist") else k, v.tolist()))
 
     def export(self):
         """Raw layout (occupied, keys, vals) for parity checks."""
@@ -173,11 +289,13 @@ class DynamicSparseVector:
         return occ, k, v
 
     def __eq__(self, other):   # vector.jl:85-87 + pma.jl:262-266: same length, same stored sequence
+        if isinstance(other, SparseVector):   # AbstractSparseVector `==`: same length, same non-zero content
+            return other.__eq__(self)
         if not isinstance(other, DynamicSparseVector):
             return NotImplemented
         if len(self) != len(other):
             return False
-        (ka, va), (kb, vb) = self.nonzeros(), other.nonzeros()
+        (ka, va), (kb, vb) = self._raw_nonzeros(), other._raw_nonzeros()
         return np.array_equal(ka, kb) and np.array_equal(va, vb)
 
     __hash__ = None
@@ -189,30 +307,46 @@ class DynamicSparseVector:
         self.flush()
         h = C.c_void_p()
         check(lib().dsa_vec_clone(self._h, C.byref(h)))
-        return DynamicSparseVector(h)
+        return DynamicSparseVector(h, key_codec=self._kc)
+
+    # +, -, unary -: the reference defines none and falls back to SparseArrays' generic methods through
+    # nonzeroinds / nonzeros (vector.jl:93-109); the result is a SparseVector (math.jl:53-93)
+    def __add__(self, other):
+        return _sv_arith(self, other, +1)
+
+    def __sub__(self, other):
+        return _sv_arith(self, other, -1)
+
+    def __neg__(self):
+        k, v = self._raw_nonzeros()
+        return SparseVector(len(self), k.copy(), -v)
 
     def filter(self, f):       # pma.jl:224-234
-        k, v = self.nonzeros()
-        keep = [i for i, e in enumerate(zip(k.tolist(), v.tolist())) if f(e)]
-        return dynamicsparsevec(k[keep], v[keep])
+        k, v = self._raw_nonzeros()
+        keep = [i for i, e in enumerate(zip(self._kc.decode(k.tolist()), v.tolist())) if f(e)]
+        return dynamicsparsevec(k[keep], v[keep], key_codec=self._kc if not self._kc.identity else None, _encoded=True)
 
     def __matmul__(self, mat):   # v * mat / v * transpose(mat)  (operations.jl:38-60)
         if isinstance(mat, _Transposed):
-            return mat.array._mul(self, trans=False, n=mat.array.size[0])
+            return mat.array._mul(self, trans=False, n=mat.array._dims()[0])
         if isinstance(mat, DynamicSparseMatrix):
-            return mat._mul(self, trans=True, n=mat.size[1])
+            return mat._mul(self, trans=True, n=mat._dims()[1])
         return NotImplemented
 
 
-def dynamicsparsevec(I, V, combine="+", n=None):
+def dynamicsparsevec(I, V, combine="+", n=None, key_codec=None, _encoded=False):
     """dynamicsparsevec(I, V, [combine, n]) (vector.jl:44-62)."""
+    if not _encoded:
+        key_codec = key_codec or _codec_for(I)
+        I = key_codec.encode(I)
+        n = None if n is None else key_codec.encode1(n)
     I, V = _i64(I), _f64(V)
     if len(I) != len(V):
         raise ArgumentError(_lib.DSA_ERR_ARGUMENT, "keys & nonzeros vectors must have same length.")
     h = C.c_void_p()
     check(lib().dsa_vec_build(_p(I), _p(V), C.c_int64(len(I)), C.c_int(_combine(combine)), C.c_int64(0 if n is None else n),
                               C.c_int(0 if n is None else 1), C.byref(h)))
-    return DynamicSparseVector(h)
+    return DynamicSparseVector(h, key_codec=key_codec)
 
 
 def shrink_size(v):   # shrink_size! (vector.jl:64)
@@ -290,7 +424,8 @@ class DynamicMatrixColView:
         self.keys, self.vals = keys, vals
 
     def __iter__(self):
-        return iter(zip(self.keys.tolist(), self.vals.tolist()))
+        keys = self.keys.tolist() if hasattr(self.keys, "tolist") else self.keys   # decoded keys of a codec are a list
+        return iter(zip(keys, self.vals.tolist()))
 
     def __len__(self):
         return len(self.keys)
@@ -311,14 +446,17 @@ class _Transposed:   # operations.jl:1-9
         self.array[idx[1], idx[0]] = val
 
     def __matmul__(self, v):   # transpose(mat) * v  (operations.jl:26-36)
-        return self.array._mul(v, trans=True, n=self.array.size[1])
+        return self.array._mul(v, trans=True, n=self.array._dims()[1])
 
 
 class DynamicSparseMatrix:
-    """DynamicSparseMatrix{Int64,Int64,Float64} (matrix.jl:1-8): both orientations live on the device."""
+    """DynamicSparseMatrix{K,L,Float64} (matrix.jl:1-8): both orientations live on the device with Int64 keys; other key
+    types K / L go through an order-preserving KeyCodec per axis (identity for integers)."""
 
-    def __init__(self, handle=None, fill_mode=False):
+    def __init__(self, handle=None, fill_mode=False, row_codec=None, col_codec=None):
         self._h = handle
+        self._L = lib()                  # the library that owns the handle (destroy goes back to it)
+        self._rc, self._cc = row_codec or _IDENTITY, col_codec or _IDENTITY
         self.fillmode = fill_mode
         self.buffer = Buffer() if fill_mode else None
         self._m = self._n = 0            # dims while in fill mode (matrix.jl:44-47)
@@ -330,14 +468,14 @@ class DynamicSparseMatrix:
     def __del__(self):
         try:
             if getattr(self, "_h", None):
-                lib().dsa_matrix_destroy(self._h)
+                self._L.dsa_matrix_destroy(self._h)
                 self._h = None
         except Exception:
             pass
 
     # -- writes -------------------------------------------------------------------------------
     def __setitem__(self, idx, val):   # matrix.jl:43-62
-        row, col = idx
+        row, col = self._rc.encode1(idx[0]), self._cc.encode1(idx[1])
         val = float(val)
         if self.fillmode:
             if val != 0.0:
@@ -354,7 +492,7 @@ class DynamicSparseMatrix:
         """Batched setindex! on both orientations: last writer wins, 0.0 deletes, absent rows/columns are created."""
         self._not_fillmode("Cannot apply a batch in fill mode")
         self.flush()
-        rows, cols, vals = _i64(rows), _i64(cols), _f64(vals)
+        rows, cols, vals = self._rc.encode(rows), self._cc.encode(cols), _f64(vals)
         if not (len(rows) == len(cols) == len(vals)):
             raise ArgumentError(_lib.DSA_ERR_ARGUMENT, "rows, columns, and nonzeros do not have same length.")
         check(lib().dsa_matrix_set_batch(self._h, _p(rows), _p(cols), _p(vals), C.c_int64(len(rows))))
@@ -370,7 +508,7 @@ class DynamicSparseMatrix:
         The arrays must stay alive (and should be pinned) until the matching apply_staged() returns."""
         self._not_fillmode("Cannot apply a batch in fill mode")
         self.flush()
-        rows, cols, vals = _i64(rows), _i64(cols), _f64(vals)
+        rows, cols, vals = self._rc.encode(rows), self._cc.encode(cols), _f64(vals)
         if not (len(rows) == len(cols) == len(vals)):
             raise ArgumentError(_lib.DSA_ERR_ARGUMENT, "rows, columns, and nonzeros do not have same length.")
         check(lib().dsa_matrix_stage_batch(self._h, _p(rows), _p(cols), _p(vals), C.c_int64(len(rows))))
@@ -391,21 +529,21 @@ class DynamicSparseMatrix:
         row, col = idx
         if self.fillmode:
             if isinstance(col, slice):       # buffer[row, :] (buffer.jl:52-55): PMA of the row, duplicates NOT combined
-                bc, bv = self.buffer.rowmajor_coo[row]
+                bc, bv = self.buffer.rowmajor_coo[self._rc.encode1(row)]
                 return dynamicsparsevec(bc, bv, combine="last")
             raise ErrorException(_lib.DSA_ERR_ERROR, "getindex(row, col) is not available in fill mode")
-        if isinstance(col, slice):
-            k, v = self.row(row)
+        if isinstance(col, slice):           # keys of the returned vector are the encoded (Int64) column keys
+            k, v = self._span(lib().dsa_matrix_row, self._rc.encode1(row))
             return dynamicsparsevec(k, v)
         if isinstance(row, slice):
-            k, v = self.col(col)
+            k, v = self._span(lib().dsa_matrix_column, self._cc.encode1(col))
             return dynamicsparsevec(k, v)
         return float(self.get_batch([row], [col])[0])
 
     def get_batch(self, rows, cols, which=_lib.COLMAJOR):
         self._not_fillmode("Matrix is in fill mode")
         self.flush()
-        rows, cols = _i64(rows), _i64(cols)
+        rows, cols = self._rc.encode(rows), self._cc.encode(cols)
         out = np.zeros(len(rows), np.float64)
         check(lib().dsa_matrix_get_batch(self._h, C.c_int(which), _p(rows), _p(cols), C.c_int64(len(rows)), _p(out)))
         return out
@@ -423,12 +561,14 @@ class DynamicSparseMatrix:
     def col(self, col):
         """view(matrix, :, col) (matrix.jl:83-88)."""
         self._not_fillmode("View of a column not available in fill mode.")
-        return self._span(lib().dsa_matrix_column, col)
+        k, v = self._span(lib().dsa_matrix_column, self._cc.encode1(col))
+        return self._rc.decode(k), v
 
     def row(self, row):
         """view(matrix, row, :) (matrix.jl:70-81), served from the row-major twin."""
         self._not_fillmode("Matrix is in fill mode, cannot create a view. However, you can use the view method on the buffer.")
-        return self._span(lib().dsa_matrix_row, row)
+        k, v = self._span(lib().dsa_matrix_row, self._rc.encode1(row))
+        return self._cc.decode(k), v
 
     def view(self, row, col):
         if isinstance(row, slice):
@@ -452,11 +592,20 @@ class DynamicSparseMatrix:
         return dict(tag=occ, key=k, val=v, semaphores=sem[:ns], col_keys=ck[:ns], col_live=cl[:ns], **inf)
 
     @property
-    def size(self):   # matrix.jl:92
+    def size(self):   # matrix.jl:92; with a codec the dimensions are keys too: size(matrix) == (5, 'e') (sparsematrix.jl:317)
         if self.fillmode:
-            return (self._m, self._n)
+            m, n = self._m, self._n
+        else:
+            inf = self.info()
+            m, n = inf["m"], inf["n"]
+        return (self._rc.decode1(m) if m or self._rc.identity else None, self._cc.decode1(n) if n or self._cc.identity else None)
+
+    def _dims(self):
+        """encoded (Int64) dimensions"""
+        if self.fillmode:
+            return self._m, self._n
         inf = self.info()
-        return (inf["m"], inf["n"])
+        return inf["m"], inf["n"]
 
     @property
     def T(self):      # transpose (operations.jl:5)
@@ -467,16 +616,21 @@ class DynamicSparseMatrix:
         self.flush()
         h = C.c_void_p()
         check(lib().dsa_matrix_clone(self._h, C.byref(h)))
-        return DynamicSparseMatrix(h)
+        return DynamicSparseMatrix(h, row_codec=self._rc, col_codec=self._cc)
 
     # -- products -----------------------------------------------------------------------------
     def _mul(self, x, trans, n):
         self._not_fillmode("Matrix is in fill mode")
         self.flush()
-        if isinstance(x, DynamicSparseVector):
-            xk, xv = x.nonzeros()
+        xcodec, ycodec = (self._rc, self._cc) if trans else (self._cc, self._rc)
+        if isinstance(x, DynamicSparseVector):   # its key type is the matrix's key type on that axis: same codec
+            xk, xv = x._raw_nonzeros()
         elif isinstance(x, SparseVector):
             xk, xv = x.nzind, x.nzval
+        elif isinstance(x, dict):            # a vector over non-integer keys
+            xk = xcodec.encode(list(x.keys()))
+            o = np.argsort(xk, kind="stable")
+            xk, xv = xk[o], _f64(list(x.values()))[o]
         else:
             xk, xv = x
         xk, xv = _i64(xk), _f64(xv)
@@ -485,38 +639,43 @@ class DynamicSparseMatrix:
         cnt = C.c_int64()
         check(lib().dsa_matrix_spmv(self._h, C.c_int(1 if trans else 0), _p(xk), _p(xv), C.c_int64(len(xk)), _p(yk), _p(yv),
                                     C.c_int64(cap), C.byref(cnt)))
+        if not ycodec.identity:   # _mul_output for non-integer keys: the Dict itself (operations.jl:11; test/unit/spmv.jl:19-24)
+            return dict(zip(ycodec.decode(yk[:cnt.value]), yv[:cnt.value].tolist()))
         return SparseVector(n, yk[:cnt.value].copy(), yv[:cnt.value].copy())
 
     def __matmul__(self, x):   # mat * v  (operations.jl:14-24)
-        return self._mul(x, trans=False, n=self.size[0])
+        return self._mul(x, trans=False, n=self._dims()[0])
 
     def mul_dense(self, x, trans=False):
         """Dense-x product: x[j-1] for every j in 1..len(x); returns dense y of length size[0] (or size[1] if trans)."""
         self._not_fillmode("Matrix is in fill mode")
         self.flush()
         x = _f64(x)
-        ny = self.size[1] if trans else self.size[0]
+        ny = self._dims()[1] if trans else self._dims()[0]
         y = np.zeros(max(ny, 1), np.float64)
         check(lib().dsa_matrix_spmv_dense(self._h, C.c_int(1 if trans else 0), _p(x), C.c_int64(len(x)), _p(y), C.c_int64(ny)))
         return y[:ny]
 
 
-def dynamicsparse(I=None, J=None, V=None, m=None, n=None, fill_mode=True, combine="+"):
+def dynamicsparse(I=None, J=None, V=None, m=None, n=None, fill_mode=True, combine="+", row_codec=None, col_codec=None):
     """dynamicsparse(I, J, V, [m, n]) (matrix.jl:15-19) or dynamicsparse(Ti, Tj, Tv; fill_mode) (matrix.jl:31-41)."""
     if I is None:
         if fill_mode:
-            return DynamicSparseMatrix(None, fill_mode=True)
+            return DynamicSparseMatrix(None, fill_mode=True, row_codec=row_codec, col_codec=col_codec)
         h = C.c_void_p()
         check(lib().dsa_matrix_create(C.byref(h)))
-        return DynamicSparseMatrix(h)
-    I, J, V = _i64(I), _i64(J), _f64(V)
+        return DynamicSparseMatrix(h, row_codec=row_codec, col_codec=col_codec)
+    row_codec, col_codec = row_codec or _codec_for(I), col_codec or _codec_for(J)
+    I, J, V = row_codec.encode(I), col_codec.encode(J), _f64(V)
+    m = None if m is None else row_codec.encode1(m)
+    n = None if n is None else col_codec.encode1(n)
     if not (len(I) == len(J) == len(V)):
         raise ArgumentError(_lib.DSA_ERR_ARGUMENT, "rows, columns, and nonzeros do not have same length.")
     h = C.c_void_p()
     given = m is not None
     check(lib().dsa_matrix_build_coo(_p(I), _p(J), _p(V), C.c_int64(len(I)), C.c_int64(m or 0), C.c_int64(n or 0),
                                      C.c_int(1 if given else 0), C.c_int(_combine(combine)), C.byref(h)))
-    return DynamicSparseMatrix(h)
+    return DynamicSparseMatrix(h, row_codec=row_codec, col_codec=col_codec)
 
 
 def closefillmode(matrix):   # closefillmode! (matrix.jl:126-134)
@@ -535,7 +694,7 @@ def closefillmode(matrix):   # closefillmode! (matrix.jl:126-134)
 def addrow(matrix, row, colids, vals):   # addrow! (matrix.jl:113-124)
     if matrix.fillmode:
         # like the reference, addrow! in fill mode does not touch the dimensions (matrix.jl:116-117)
-        matrix.buffer.addrow(row, colids, vals)
+        matrix.buffer.addrow(matrix._rc.encode1(row), matrix._cc.encode(colids), vals)
     else:
         for c, v in zip(colids, vals):
             matrix[row, c] = v
@@ -543,13 +702,13 @@ def addrow(matrix, row, colids, vals):   # addrow! (matrix.jl:113-124)
 
 
 def _as_list(x):
-    return [int(x)] if np.isscalar(x) else [int(e) for e in x]
+    return [x] if np.isscalar(x) or isinstance(x, str) else list(x)
 
 
 def deletecolumn(matrix, col):   # deletecolumn! (matrix.jl:95-102); a list deletes in one bulk call
     matrix._not_fillmode("Cannot delete a column in fill mode")
     matrix.flush()
-    ids = _i64(_as_list(col))
+    ids = matrix._cc.encode(_as_list(col))
     check(lib().dsa_matrix_delete_columns(matrix._h, _p(ids), C.c_int64(len(ids))))
     return True
 
@@ -557,7 +716,7 @@ def deletecolumn(matrix, col):   # deletecolumn! (matrix.jl:95-102); a list dele
 def deleterow(matrix, row):      # deleterow! (matrix.jl:104-111)
     matrix._not_fillmode("Cannot delete a row in fill mode")
     matrix.flush()
-    ids = _i64(_as_list(row))
+    ids = matrix._rc.encode(_as_list(row))
     check(lib().dsa_matrix_delete_rows(matrix._h, _p(ids), C.c_int64(len(ids))))
     return True
 
