@@ -4,7 +4,7 @@ The CPU suite (`-m "not gpu"`) has no GPU, yet the host glue in dynamicsparsearr
 fill-mode buffer, key codecs, operand-order wrappers, exception mapping, two-call size queries) is logic worth testing there.
 FakeLib answers the subset of include/dsa.h that api.py calls, with the same argument conventions (ctypes pointers + sizes,
 int return code + dsa_last_error), executing on the CPU oracle.  It lives under tests/ and is installed only by the
-`api` fixture of tests/test_api_hostlogic.py through monkeypatching; the package itself never imports it, and the same
+`api` fixture of tests/test_zz_api_hostlogic.py through monkeypatching; the package itself never imports it, and the same
 tests run against the real library under `-m gpu`.
 """
 import ctypes as C
