@@ -492,6 +492,10 @@ __global__ void __launch_bounds__(256) k_spmv_fixup(double* __restrict__ yslot, 
     ycnt[slot] = n;
 }
 
+}  // namespace dsa
+#include "spmv_bulk.cuh"
+namespace dsa {
+
 // y by slot -> dense y indexed by partition key (1..ny)
 __global__ void __launch_bounds__(256) k_spmv_to_dense(const double* __restrict__ yslot, const int64_t* __restrict__ sem,
                                                         const int64_t* __restrict__ slot_key, int64_t nslots, double* __restrict__ y, int64_t ny) {
@@ -704,12 +708,53 @@ struct Pcsr {
                        carry, ccnt, clast, nchunks);
         DSA_LAUNCH("spmv_fixup", k_spmv_fixup, grid_for(nchunks, 256), 256, 0, st, yslot, ycnt, carry, ccnt, clast, nchunks);
     }
+    // EXPERIMENTAL (DSA_SPMV_BULK=1..3): same chunks and arithmetic as spmv_launch<4>, the stream staged through shared memory by
+    // cp.async.bulk (spmv_bulk.cuh).  Returns false when the geometry does not fit (capacity not a multiple of the tile).
+    template <int TILE, int STAGES, int NCONS>
+    bool spmv_launch_bulk(PcsrWorkspace& ws, const double* d_x, const uint8_t* d_xmask, int64_t nx, int ctas_per_sm, cudaStream_t st) {
+        const int64_t cap = pma.g.capacity;
+        if (cap < TILE || cap % TILE != 0) return false;
+        const int64_t ntiles = cap / TILE;
+        const int64_t nchunks = cap / 128;
+        const int64_t ns = nslots();
+        double* yslot = ws.yslot.ensure((size_t)ns + 1);
+        int32_t* ycnt = ws.ycnt.ensure((size_t)ns + 1);
+        double* carry = ws.carry.ensure((size_t)nchunks);
+        int32_t* ccnt = ws.carry_cnt.ensure((size_t)nchunks);
+        int32_t* clast = ws.chunk_last.ensure((size_t)nchunks);
+        constexpr size_t smem = (size_t)STAGES * TILE * 16;
+        static int n_sm = 0;
+        if (n_sm == 0) {
+            int dev = 0;
+            DSA_CUDA(cudaGetDevice(&dev));
+            DSA_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+            DSA_CUDA(cudaFuncSetAttribute(k_spmv_bulk<true, TILE, STAGES, NCONS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            DSA_CUDA(cudaFuncSetAttribute(k_spmv_bulk<false, TILE, STAGES, NCONS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+        const unsigned gr = (unsigned)std::min<int64_t>(ntiles, (int64_t)n_sm * ctas_per_sm);
+        constexpr int threads = (NCONS + 1) * 32;
+        if (d_xmask)
+            DSA_LAUNCH("spmv_bulk", (k_spmv_bulk<true, TILE, STAGES, NCONS>), gr, threads, smem, st, pma.keys.p, pma.vals.p, ntiles, d_x, d_xmask,
+                       nx, yslot, ycnt, carry, ccnt, clast);
+        else
+            DSA_LAUNCH("spmv_bulk", (k_spmv_bulk<false, TILE, STAGES, NCONS>), gr, threads, smem, st, pma.keys.p, pma.vals.p, ntiles, d_x, d_xmask,
+                       nx, yslot, ycnt, carry, ccnt, clast);
+        DSA_LAUNCH("spmv_fixup", k_spmv_fixup, grid_for(nchunks, 256), 256, 0, st, yslot, ycnt, carry, ccnt, clast, nchunks);
+        return true;
+    }
     // flat SpMV; results by slot in ws.yslot / ws.ycnt
     void spmv_slots(PcsrWorkspace& ws, const double* d_x, const uint8_t* d_xmask, int64_t nx, cudaStream_t st) {
         static const int steps = [] {
             const char* e = getenv("DSA_SPMV_STEPS");
             return e ? atoi(e) : SPMV_STEPS_DEFAULT;
         }();
+        static const int bulk = [] {
+            const char* e = getenv("DSA_SPMV_BULK");   // experimental, off unless asked for
+            return e ? atoi(e) : 0;
+        }();
+        if (bulk == 1 && spmv_launch_bulk<2048, 4, 16>(ws, d_x, d_xmask, nx, 1, st)) return;   // 128 KB in flight per SM, 16 consumer warps
+        if (bulk == 2 && spmv_launch_bulk<2048, 3, 8>(ws, d_x, d_xmask, nx, 2, st)) return;    // 2 CTAs per SM x 96 KB
+        if (bulk == 3 && spmv_launch_bulk<4096, 3, 16>(ws, d_x, d_xmask, nx, 1, st)) return;   // 192 KB in flight per SM
         if (steps == 8) spmv_launch<8>(ws, d_x, d_xmask, nx, st);
         else if (steps == 2) spmv_launch<2>(ws, d_x, d_xmask, nx, st);
         else spmv_launch<4>(ws, d_x, d_xmask, nx, st);
