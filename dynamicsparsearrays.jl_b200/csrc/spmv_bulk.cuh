@@ -41,12 +41,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// A protocol error must not hang the GPU: after ~2^24 failed probes (seconds; a probe already blocks for a hardware-defined
+// A protocol error must not hang the GPU: after 2^20 failed probes (a legitimate wait is microseconds; a probe already blocks for a hardware-defined
 // time slice) the kernel traps, which surfaces as a CUDA error on the next synchronisation.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity))
-        if (++spins == (1u << 24)) __trap();
+        if (++spins == (1u << 20)) __trap();
 }
 // 1-D bulk copy global -> shared, completion signalled on `bar` in bytes (dst, src and bytes are multiples of 16)
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {

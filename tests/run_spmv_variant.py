@@ -26,15 +26,28 @@ def main():
     D.deletecolumn(A, np.unique(J[:40]).tolist())     # tombstones: the deleted partitions' slots stay in the column map
     x, xt = rng.random(n), rng.random(m)
     y, yt = A.mul_dense(x), A.mul_dense(xt, trans=True)
+    # kernel time from the library's per-launch CUDA events (prof mode), after warm-up
+    import ctypes as C
+    L = D.lib()
+    for _ in range(3):
+        A.mul_dense(x)
+    L.dsa_prof_reset()
+    L.dsa_prof_enable(C.c_int(1))
     t0 = time.perf_counter()
     for _ in range(20):
         A.mul_dense(x)
     ms = (time.perf_counter() - t0) / 20 * 1e3
+    L.dsa_prof_enable(C.c_int(0))
+    need = L.dsa_prof_dump(None, C.c_int64(0))
+    buf = C.create_string_buffer(int(need) + 16)
+    L.dsa_prof_dump(buf, C.c_int64(len(buf)))
+    kern = {ln.split(",")[0]: 1e3 * float(ln.split(",")[2]) / int(ln.split(",")[1]) for ln in buf.value.decode().strip().splitlines()}
     xs_k = np.sort(rng.choice(np.arange(1, n + 1), n // 3, replace=False))
     ys = A @ (xs_k, rng.random(len(xs_k)))            # sparse x (mask path)
     np.savez(out, y=y, yt=yt, ys_k=ys.nzind, ys_v=ys.nzval, ms=ms, cap=A.info(1)["capacity"])
-    print(f"variant BULK={os.environ.get('DSA_SPMV_BULK', '0')} STEPS={os.environ.get('DSA_SPMV_STEPS', '4')}: "
-          f"{ms:.3f} ms per host-pointer mul_dense, capacity {A.info(1)['capacity']}")
+    print(f"variant BULK={os.environ.get('DSA_SPMV_BULK', '0')} STEPS={os.environ.get('DSA_SPMV_STEPS', '4')}: capacity {A.info(1)['capacity']}, "
+          f"{ms:.3f} ms per host-pointer mul_dense; kernel us per launch: "
+          + ", ".join(f"{k}={v:.1f}" for k, v in sorted(kern.items()) if k.startswith("spmv")))
 
 
 if __name__ == "__main__":

@@ -29,7 +29,7 @@ def _bits(a):
     return a.view(np.int64) if a.dtype == np.float64 else a
 
 
-@pytest.mark.parametrize("size", [(20_000, 30_000, 2_000_000), (300, 200, 3_000)])
+@pytest.mark.parametrize("size", [(100_000, 100_000, 10_000_000), (20_000, 30_000, 2_000_000), (300, 200, 3_000)])
 def test_spmv_bulk_variants_are_bit_identical_to_flat(tmp_path, size):
     """k_spmv_bulk keeps k_spmv_flat<., 4>'s chunking and arithmetic: same bits, dense and sparse x, both orientations.
     The small size has capacity < tile for some variants: they must fall back to the flat kernel."""
