@@ -235,10 +235,16 @@ struct dsa_matrix {
     } slot[2];
     cudaStream_t copy_st = nullptr;
     int staged_head = 0, staged_count = 0;
+    // EXPERIMENTAL (DSA_TWO_STREAMS=1): the row-major twin's batch phases run on their own stream, forked from / joined to sh.st
+    cudaStream_t twin_st = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     ~dsa_matrix() {
         for (auto& s : slot)
             if (s.ev) cudaEventDestroy(s.ev);
         if (copy_st) cudaStreamDestroy(copy_st);
+        if (twin_st) cudaStreamDestroy(twin_st);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
     }
     DBuf<int32_t> d_slots;
     DBuf<int64_t> d_ids;
@@ -372,21 +378,50 @@ static void matrix_set_batch_two(dsa_matrix* A, const int64_t* rows_c, const int
     BatchCtx cc, cr;
     cc.inkeys = rows_c; cc.partkeys = cols_c; cc.vals = vals_c; cc.n = nc;   // colmajor[row, col] = v  (matrix.jl:53-55)
     cr.inkeys = cols_r; cr.partkeys = rows_r; cr.vals = vals_r; cr.n = nr;   // rowmajor[col, row] = v  (matrix.jl:57-59)
-    if (nc > 0) phase1_launch(A->colmajor, A->ws, cc, st);
-    if (nr > 0) phase1_launch(A->rowmajor, A->ws2, cr, st);
-    DSA_CUDA(cudaStreamSynchronize(st));
-    if (nc > 0) phase1_read(A->ws, cc);
-    if (nr > 0) phase1_read(A->ws2, cr);
-    // validate before mutate: rows are the in-array keys of the col-major structure, columns those of the row-major one
-    if ((nc > 0 && cc.bs.minkey < 1) || (nr > 0 && cr.bs.minkey < 1))
-        throw DsaError{DSA_ERR_ARGUMENT, "row and column keys must be >= 1 (each is an in-array key of one orientation; key 0 is the semaphore key, pcsr.jl:23)"};
-    if (nc > 0) phase1_finish(A->colmajor, A->ws, cc, st);
-    if (nr > 0) phase1_finish(A->rowmajor, A->ws2, cr, st);
-    if (nc > 0) phase2_launch(A->colmajor, A->ws, cc, st);
-    if (nr > 0) phase2_launch(A->rowmajor, A->ws2, cr, st);
-    DSA_CUDA(cudaStreamSynchronize(st));
-    if (nc > 0) phase3(A->colmajor, A->ws, cc, st);
-    if (nr > 0) phase3(A->rowmajor, A->ws2, cr, st);
+    // EXPERIMENTAL, off unless DSA_TWO_STREAMS=1: the two orientations are independent (own structure, own workspace), and
+    // most of their kernels are single-wave and latency-bound, so the twin's phases go to a second stream (st2) that forks
+    // from st here and joins it at the end.  With the switch off st2 == st and the sequence below is the validated one.
+    static const bool two_streams = [] {
+        const char* e = getenv("DSA_TWO_STREAMS");
+        return e && atoi(e) == 1;
+    }();
+    cudaStream_t st2 = st;
+    if (two_streams && nc > 0 && nr > 0) {
+        if (!A->twin_st) {
+            DSA_CUDA(cudaStreamCreateWithFlags(&A->twin_st, cudaStreamNonBlocking));
+            DSA_CUDA(cudaEventCreateWithFlags(&A->ev_fork, cudaEventDisableTiming));
+            DSA_CUDA(cudaEventCreateWithFlags(&A->ev_join, cudaEventDisableTiming));
+        }
+        st2 = A->twin_st;
+        DSA_CUDA(cudaEventRecord(A->ev_fork, st));        // everything queued on st so far (input copies) precedes the twin's work
+        DSA_CUDA(cudaStreamWaitEvent(st2, A->ev_fork, 0));
+    }
+    try {
+        if (nc > 0) phase1_launch(A->colmajor, A->ws, cc, st);
+        if (nr > 0) phase1_launch(A->rowmajor, A->ws2, cr, st2);
+        DSA_CUDA(cudaStreamSynchronize(st));
+        if (st2 != st) DSA_CUDA(cudaStreamSynchronize(st2));
+        if (nc > 0) phase1_read(A->ws, cc);
+        if (nr > 0) phase1_read(A->ws2, cr);
+        // validate before mutate: rows are the in-array keys of the col-major structure, columns those of the row-major one
+        if ((nc > 0 && cc.bs.minkey < 1) || (nr > 0 && cr.bs.minkey < 1))
+            throw DsaError{DSA_ERR_ARGUMENT, "row and column keys must be >= 1 (each is an in-array key of one orientation; key 0 is the semaphore key, pcsr.jl:23)"};
+        if (nc > 0) phase1_finish(A->colmajor, A->ws, cc, st);
+        if (nr > 0) phase1_finish(A->rowmajor, A->ws2, cr, st2);
+        if (nc > 0) phase2_launch(A->colmajor, A->ws, cc, st);
+        if (nr > 0) phase2_launch(A->rowmajor, A->ws2, cr, st2);
+        DSA_CUDA(cudaStreamSynchronize(st));
+        if (st2 != st) DSA_CUDA(cudaStreamSynchronize(st2));
+        if (nc > 0) phase3(A->colmajor, A->ws, cc, st);
+        if (nr > 0) phase3(A->rowmajor, A->ws2, cr, st2);
+        if (st2 != st) {   // later work on st (SpMV, reads, the next batch) sees the twin's merges
+            DSA_CUDA(cudaEventRecord(A->ev_join, st2));
+            DSA_CUDA(cudaStreamWaitEvent(st, A->ev_join, 0));
+        }
+    } catch (...) {
+        if (st2 != st) cudaStreamSynchronize(st2);
+        throw;
+    }
     // matrix.jl:44-47: dimensions grow on non-zero writes
     if (nc > 0 && cc.bs.maxkey_nz != INT64_MIN && cc.bs.maxkey_nz > A->m) A->m = cc.bs.maxkey_nz;
     if (nc > 0 && cc.bs.maxpart_nz != INT64_MIN && cc.bs.maxpart_nz > A->n) A->n = cc.bs.maxpart_nz;

@@ -15,10 +15,10 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("DSA_EXPERIMENTAL") != "1", reason="experimental kernels: set DSA_EXPERIMENTAL=1")]
 
 
-def _run(tmp_path, name, env_extra, size=()):
+def _run(tmp_path, name, env_extra, size=(), script="run_spmv_variant.py"):
     out = str(tmp_path / f"{name}.npz")
     env = dict(os.environ, **env_extra)
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "run_spmv_variant.py"), out, *map(str, size)], env=env, timeout=300,
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", script), out, *map(str, size)], env=env, timeout=300,
                        capture_output=True, text=True)
     print(r.stdout.strip())
     assert r.returncode == 0, r.stderr[-2000:]
@@ -38,3 +38,22 @@ def test_spmv_bulk_variants_are_bit_identical_to_flat(tmp_path, size):
         got = _run(tmp_path, f"bulk{mode}", {"DSA_SPMV_BULK": mode, "DSA_SPMV_STEPS": "4"}, size)
         for key in ("y", "yt", "ys_k", "ys_v"):
             assert np.array_equal(_bits(ref[key]), _bits(got[key])), (mode, key)
+
+
+@pytest.mark.parametrize("size", [(100_000, 10_000_000, 1_000_000, 10), (3_000, 200_000, 50_000, 6)])
+def test_two_stream_batches_leave_the_same_layout(tmp_path, size):
+    """DSA_TWO_STREAMS=1 only changes which stream the twin orientation's kernels run on: both layouts, the column maps and
+    the SpMV result must be bit-identical to the one-stream run (prints the step time of both)."""
+    ref = _run(tmp_path, "one", {"DSA_TWO_STREAMS": "0"}, size, script="run_update_variant.py")
+    got = _run(tmp_path, "two", {"DSA_TWO_STREAMS": "1"}, size, script="run_update_variant.py")
+    assert str(ref["col"]) == str(got["col"]) and str(ref["row"]) == str(got["row"]) and int(ref["nnz"]) == int(got["nnz"])
+    assert np.array_equal(_bits(ref["y"]), _bits(got["y"]))
+
+
+def test_parity_suite_under_two_streams():
+    """the matrix parity tests (oracle comparisons) with the switch on"""
+    env = dict(os.environ, DSA_TWO_STREAMS="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-q", "-m", "gpu", "-k", "matrix or fill or staged"],
+                       env=env, timeout=300, capture_output=True, text=True, cwd=ROOT)
+    print(r.stdout[-600:])
+    assert r.returncode == 0, r.stdout[-3000:]
