@@ -40,20 +40,27 @@ def test_spmv_bulk_variants_are_bit_identical_to_flat(tmp_path, size):
             assert np.array_equal(_bits(ref[key]), _bits(got[key])), (mode, key)
 
 
+SWITCHES = [{"DSA_TWO_STREAMS": "1"}, {"DSA_SCAN_ONEPASS": "1"}, {"DSA_TWO_STREAMS": "1", "DSA_SCAN_ONEPASS": "1"}]
+OFF = {"DSA_TWO_STREAMS": "0", "DSA_SCAN_ONEPASS": "0", "DSA_SPMV_BULK": "0"}
+
+
 @pytest.mark.parametrize("size", [(100_000, 10_000_000, 1_000_000, 10), (3_000, 200_000, 50_000, 6)])
-def test_two_stream_batches_leave_the_same_layout(tmp_path, size):
-    """DSA_TWO_STREAMS=1 only changes which stream the twin orientation's kernels run on: both layouts, the column maps and
-    the SpMV result must be bit-identical to the one-stream run (prints the step time of both)."""
-    ref = _run(tmp_path, "one", {"DSA_TWO_STREAMS": "0"}, size, script="run_update_variant.py")
-    got = _run(tmp_path, "two", {"DSA_TWO_STREAMS": "1"}, size, script="run_update_variant.py")
-    assert str(ref["col"]) == str(got["col"]) and str(ref["row"]) == str(got["row"]) and int(ref["nnz"]) == int(got["nnz"])
-    assert np.array_equal(_bits(ref["y"]), _bits(got["y"]))
+def test_update_switches_leave_the_same_layout(tmp_path, size):
+    """DSA_TWO_STREAMS=1 only changes which stream the twin orientation's kernels run on, DSA_SCAN_ONEPASS=1 only how prefix
+    sums are computed: both layouts, the column maps and the SpMV result must be bit-identical to the default run (the step
+    time of every variant is printed)."""
+    ref = _run(tmp_path, "default", OFF, size, script="run_update_variant.py")
+    for i, sw in enumerate(SWITCHES):
+        got = _run(tmp_path, f"sw{i}", dict(OFF, **sw), size, script="run_update_variant.py")
+        assert str(ref["col"]) == str(got["col"]) and str(ref["row"]) == str(got["row"]) and int(ref["nnz"]) == int(got["nnz"]), sw
+        assert np.array_equal(_bits(ref["y"]), _bits(got["y"])), sw
 
 
-def test_parity_suite_under_two_streams():
-    """the matrix parity tests (oracle comparisons) with the switch on"""
-    env = dict(os.environ, DSA_TWO_STREAMS="1")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-q", "-m", "gpu", "-k", "matrix or fill or staged"],
+@pytest.mark.parametrize("sw", SWITCHES[:2])
+def test_parity_suite_under_switch(sw):
+    """the parity tests (oracle comparisons) with one switch on"""
+    env = dict(os.environ, **sw)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-q", "-m", "gpu", "-k", "not full_size"],
                        env=env, timeout=300, capture_output=True, text=True, cwd=ROOT)
-    print(r.stdout[-600:])
+    print(sw, r.stdout[-300:])
     assert r.returncode == 0, r.stdout[-3000:]
