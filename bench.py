@@ -165,7 +165,10 @@ def workload_config(n_gpus):
     return {"workload": "C2: dynamicsparse PCSR 1e5 x 1e5, 1e7 nnz resident; step = 1M-update batch (50% insert/overwrite, 50% delete, "
                         "both orientations) + SpMV A*x (dense x)", "rows": M_ROWS, "cols": N_COLS, "nnz": NNZ0, "batch": BATCH,
             "l2_policy": "inputs larger than L2 (2 x 268 MB gapped arrays per matrix vs 126 MB L2)", "seed": hex(SEED),
-            "parallelism": f"column-range shards x{n_gpus}" if n_gpus > 1 else "single GPU"}
+            "parallelism": f"column-range shards x{n_gpus}" if n_gpus > 1 else "single GPU",
+            # experimental kernel switches in effect (empty = the validated defaults)
+            "switches": {k: os.environ[k] for k in ("DSA_SPMV_BULK", "DSA_SPMV_STEPS", "DSA_TWO_STREAMS", "DSA_SCAN_ONEPASS",
+                                                    "DSA_DIST_PIPELINE") if k in os.environ}}
 
 
 def main():
@@ -259,18 +262,19 @@ def main():
     peak, peak_src = measured_peak_gbs()
     spmv_alg_bytes = 16 * (inf["nnz"] + inf["nb_partitions"]) + 8 * (N_COLS + M_ROWS)
     spmv_phys_bytes = 16 * inf["capacity"] + 8 * (N_COLS + M_ROWS)
-    spmv_us = kernels.get("spmv_flat", {}).get("avg_us")
+    spmv_name = "spmv_bulk" if "spmv_bulk" in kernels else "spmv_flat"   # DSA_SPMV_BULK selects the shared-memory-staged variant
+    spmv_us = kernels.get(spmv_name, {}).get("avg_us")
     spmv = None
     if spmv_us:
         a = spmv_alg_bytes / (spmv_us * 1e-6) / 1e9
-        spmv = {"kernel": "spmv_flat", "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak,
+        spmv = {"kernel": spmv_name, "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak,
                 "frac_of_8TBs": a / 8000.0, "physical_gbs": spmv_phys_bytes / (spmv_us * 1e-6) / 1e9, "avg_us": spmv_us,
-                "algorithmic_bytes": spmv_alg_bytes, "traffic": ncu_traffic("spmv_flat"), "peak_source": peak_src}
+                "algorithmic_bytes": spmv_alg_bytes, "traffic": ncu_traffic(spmv_name), "peak_source": peak_src}
     dom = max(kernels.items(), key=lambda kv: kv[1]["ms_per_step"]) if kernels else (None, None)
     roofline = None
     if dom[0]:
         name, k = dom
-        if name == "spmv_flat":
+        if name == spmv_name:
             alg = spmv_alg_bytes
         else:   # a kernel of the update pipeline processes one orientation's share of the batch per launch
             alg = BYTES_PER_UPDATE_ONE * BATCH

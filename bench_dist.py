@@ -152,12 +152,12 @@ def main_dist(args, rank, world, local_rank):
     L.dsa_prof_dump(buf, C.c_int64(len(buf)))
     for ln in buf.value.decode().strip().splitlines():
         name, cnt, tms = ln.split(",")
-        if name == "spmv_flat":
+        if name in ("spmv_flat", "spmv_bulk"):
             us = 1e3 * float(tms) / int(cnt)
             peak, src = B.measured_peak_gbs()
             alg = 16 * (inf["nnz"] + inf["nb_partitions"]) + 8 * (n + per)
             a = alg / (us * 1e-6) / 1e9
-            spmv = {"kernel": "spmv_flat", "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak,
+            spmv = {"kernel": name, "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak,
                     "avg_us": us, "algorithmic_bytes": alg, "traffic": None, "peak_source": src, "scope": "rank 0 shard"}
     if rank == 0:
         cfg = B.workload_config(world)
