@@ -708,7 +708,7 @@ struct Pcsr {
                        carry, ccnt, clast, nchunks);
         DSA_LAUNCH("spmv_fixup", k_spmv_fixup, grid_for(nchunks, 256), 256, 0, st, yslot, ycnt, carry, ccnt, clast, nchunks);
     }
-    // EXPERIMENTAL (DSA_SPMV_BULK=1..3): same chunks and arithmetic as spmv_launch<4>, the stream staged through shared memory by
+    // EXPERIMENTAL (DSA_SPMV_BULK=1..5): same chunks and arithmetic as spmv_launch<4>, the stream staged through shared memory by
     // cp.async.bulk (spmv_bulk.cuh).  Returns false when the geometry does not fit (capacity not a multiple of the tile).
     template <int TILE, int STAGES, int NCONS>
     bool spmv_launch_bulk(PcsrWorkspace& ws, const double* d_x, const uint8_t* d_xmask, int64_t nx, int ctas_per_sm, cudaStream_t st) {
@@ -755,6 +755,8 @@ struct Pcsr {
         if (bulk == 1 && spmv_launch_bulk<2048, 4, 16>(ws, d_x, d_xmask, nx, 1, st)) return;   // 128 KB in flight per SM, 16 consumer warps
         if (bulk == 2 && spmv_launch_bulk<2048, 3, 8>(ws, d_x, d_xmask, nx, 2, st)) return;    // 2 CTAs per SM x 96 KB
         if (bulk == 3 && spmv_launch_bulk<4096, 3, 16>(ws, d_x, d_xmask, nx, 1, st)) return;   // 192 KB in flight per SM
+        if (bulk == 4 && spmv_launch_bulk<2048, 3, 16>(ws, d_x, d_xmask, nx, 2, st)) return;   // 2 CTAs per SM x 96 KB, 32 consumer warps (register-limited)
+        if (bulk == 5 && spmv_launch_bulk<1024, 4, 8>(ws, d_x, d_xmask, nx, 3, st)) return;    // 3 CTAs per SM x 64 KB, small tiles
         if (steps == 8) spmv_launch<8>(ws, d_x, d_xmask, nx, st);
         else if (steps == 2) spmv_launch<2>(ws, d_x, d_xmask, nx, st);
         else spmv_launch<4>(ws, d_x, d_xmask, nx, st);
