@@ -235,7 +235,7 @@ struct dsa_matrix {
     } slot[2];
     cudaStream_t copy_st = nullptr;
     int staged_head = 0, staged_count = 0;
-    // EXPERIMENTAL (DSA_TWO_STREAMS=1): the row-major twin's batch phases run on their own stream, forked from / joined to sh.st
+    // the row-major twin's batch phases run on their own stream, forked from / joined to sh.st (DSA_TWO_STREAMS=0 disables)
     cudaStream_t twin_st = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     ~dsa_matrix() {
@@ -378,12 +378,13 @@ static void matrix_set_batch_two(dsa_matrix* A, const int64_t* rows_c, const int
     BatchCtx cc, cr;
     cc.inkeys = rows_c; cc.partkeys = cols_c; cc.vals = vals_c; cc.n = nc;   // colmajor[row, col] = v  (matrix.jl:53-55)
     cr.inkeys = cols_r; cr.partkeys = rows_r; cr.vals = vals_r; cr.n = nr;   // rowmajor[col, row] = v  (matrix.jl:57-59)
-    // EXPERIMENTAL, off unless DSA_TWO_STREAMS=1: the two orientations are independent (own structure, own workspace), and
-    // most of their kernels are single-wave and latency-bound, so the twin's phases go to a second stream (st2) that forks
-    // from st here and joins it at the end.  With the switch off st2 == st and the sequence below is the validated one.
+    // The two orientations are independent (own structure, own workspace) and most of their kernels are single-wave and
+    // latency-bound, so the twin's phases run on a second stream (st2) that forks from st here and joins it at the end:
+    // 0.764 -> 0.668 ms per config-2 step, layouts bit-identical (profiles/exp_r01_update_switches.log).
+    // DSA_TWO_STREAMS=0 puts everything back on one stream (st2 == st).
     static const bool two_streams = [] {
         const char* e = getenv("DSA_TWO_STREAMS");
-        return e && atoi(e) == 1;
+        return !e || atoi(e) != 0;
     }();
     cudaStream_t st2 = st;
     if (two_streams && nc > 0 && nr > 0) {

@@ -742,6 +742,52 @@ struct Pcsr {
         DSA_LAUNCH("spmv_fixup", k_spmv_fixup, grid_for(nchunks, 256), 256, 0, st, yslot, ycnt, carry, ccnt, clast, nchunks);
         return true;
     }
+    // EXPERIMENTAL (DSA_SPMV_BULK=8): x spread over the shared memory of 8-CTA clusters, gathers through DSMEM (spmv_bulk.cuh).
+    // Dense x only, 8 x 2^slice_lg >= nx with a slice of at most 128 KB; otherwise false (the flat kernel runs).
+    bool spmv_launch_dsmem(PcsrWorkspace& ws, const double* d_x, const uint8_t* d_xmask, int64_t nx, cudaStream_t st) {
+        constexpr int CL = 8;
+        if (d_xmask || nx <= 0) return false;
+        int slice_lg = 4;
+        while ((int64_t(CL) << slice_lg) < nx) ++slice_lg;
+        if (slice_lg > 14) return false;   // 2^14 doubles = 128 KB per CTA
+        const int64_t cap = pma.g.capacity;
+        const int64_t nchunks = (cap + 127) / 128;
+        const int64_t ns = nslots();
+        double* yslot = ws.yslot.ensure((size_t)ns + 1);
+        int32_t* ycnt = ws.ycnt.ensure((size_t)ns + 1);
+        double* carry = ws.carry.ensure((size_t)nchunks);
+        int32_t* ccnt = ws.carry_cnt.ensure((size_t)nchunks);
+        int32_t* clast = ws.chunk_last.ensure((size_t)nchunks);
+        const size_t smem = (size_t)8 << slice_lg;
+        static int n_clusters = 0;
+        if (n_clusters == 0) {
+            DSA_CUDA(cudaFuncSetAttribute(k_spmv_dsmem<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(CL * 16);
+            cfg.blockDim = dim3(1024);
+            cfg.dynamicSmemBytes = 128 * 1024;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = CL;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            int nc = 0;
+            if (cudaOccupancyMaxActiveClusters(&nc, k_spmv_dsmem<CL>, &cfg) != cudaSuccess || nc <= 0) {
+                cudaGetLastError();
+                n_clusters = -1;
+            } else {
+                n_clusters = nc;
+            }
+        }
+        if (n_clusters <= 0) return false;
+        const unsigned gr = (unsigned)(n_clusters * CL);   // one resident wave of clusters, persistent warps
+        DSA_LAUNCH("spmv_dsmem", (k_spmv_dsmem<CL>), gr, 1024, smem, st, pma.keys.p, pma.vals.p, cap, d_x, nx, slice_lg, yslot, ycnt, carry, ccnt,
+                   clast, nchunks);
+        DSA_LAUNCH("spmv_fixup", k_spmv_fixup, grid_for(nchunks, 256), 256, 0, st, yslot, ycnt, carry, ccnt, clast, nchunks);
+        return true;
+    }
     // flat SpMV; results by slot in ws.yslot / ws.ycnt
     void spmv_slots(PcsrWorkspace& ws, const double* d_x, const uint8_t* d_xmask, int64_t nx, cudaStream_t st) {
         static const int steps = [] {
@@ -757,6 +803,7 @@ struct Pcsr {
         if (bulk == 3 && spmv_launch_bulk<4096, 3, 16>(ws, d_x, d_xmask, nx, 1, st)) return;   // 192 KB in flight per SM
         if (bulk == 4 && spmv_launch_bulk<2048, 3, 16>(ws, d_x, d_xmask, nx, 2, st)) return;   // 2 CTAs per SM x 96 KB, 32 consumer warps (register-limited)
         if (bulk == 5 && spmv_launch_bulk<1024, 4, 8>(ws, d_x, d_xmask, nx, 3, st)) return;    // 3 CTAs per SM x 64 KB, small tiles
+        if (bulk == 8 && spmv_launch_dsmem(ws, d_x, d_xmask, nx, st)) return;                  // x in cluster shared memory
         if (steps == 8) spmv_launch<8>(ws, d_x, d_xmask, nx, st);
         else if (steps == 2) spmv_launch<2>(ws, d_x, d_xmask, nx, st);
         else spmv_launch<4>(ws, d_x, d_xmask, nx, st);

@@ -110,8 +110,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_apply(const InT* __r
     }
 }
 
-// EXPERIMENTAL (DSA_SCAN_ONEPASS=1, not validated on hardware yet): the same scan in ONE launch — chained scan with decoupled
-// look-back.  Tiles are handed out by an atomic ticket (so a tile's predecessors have always started: forward progress), every
+// Default since round 1 (DSA_SCAN_ONEPASS=0 selects the three-phase version above): the same scan in ONE launch — chained scan
+// with decoupled look-back (parity suite green and layouts bit-identical with either version, profiles/exp_r01_update_switches.log).  Tiles are handed out by an atomic ticket (so a tile's predecessors have always started: forward progress), every
 // tile publishes one 64-bit word {epoch:30 | flag:2 | sum:32} (aggregate first, inclusive prefix once known); a tile adds up its
 // predecessors' words back to the nearest inclusive one.  The epoch makes stale words of earlier calls invisible, so the state
 // array needs no clearing between calls; the tile that draws the last ticket resets the ticket counter.
@@ -210,7 +210,7 @@ struct ScanWorkspace {
 inline bool scan_onepass_enabled() {
     static const bool on = [] {
         const char* e = getenv("DSA_SCAN_ONEPASS");
-        return e && atoi(e) == 1;
+        return !e || atoi(e) != 0;
     }();
     return on;
 }

@@ -34,7 +34,7 @@ def test_spmv_bulk_variants_are_bit_identical_to_flat(tmp_path, size):
     """k_spmv_bulk keeps k_spmv_flat<., 4>'s chunking and arithmetic: same bits, dense and sparse x, both orientations.
     The small size has capacity < tile for some variants: they must fall back to the flat kernel."""
     ref = _run(tmp_path, "flat", {"DSA_SPMV_BULK": "0", "DSA_SPMV_STEPS": "4"}, size)
-    for mode in ("1", "2", "3", "4", "5"):
+    for mode in os.environ.get("DSA_EXP_SPMV_MODES", "1,2,3,4,5,8").split(","):
         got = _run(tmp_path, f"bulk{mode}", {"DSA_SPMV_BULK": mode, "DSA_SPMV_STEPS": "4"}, size)
         for key in ("y", "yt", "ys_k", "ys_v"):
             assert np.array_equal(_bits(ref[key]), _bits(got[key])), (mode, key)
