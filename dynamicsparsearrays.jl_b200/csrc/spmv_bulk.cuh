@@ -4,8 +4,9 @@
 // 91.5 us with 32 — the results are bit-identical, but the kernel is NOT bound by the bytes the stream keeps in flight (the
 // hypothesis below was wrong): time scales with the number of warps issuing gathers, and the floor that fits both kernels is the
 // L1 replay rate of divergent loads (~2 cycles per distinct 128 B line, B300_MICROARCH.md: 1e7 lines / 148 SMs x 2.07 cycles = 71 us).
-// k_spmv_dsmem (mode 8) therefore moves the gathers off the L1 path: x is spread over the shared memory of an 8-CTA cluster and
-// read through distributed shared memory.
+// k_spmv_dsmem (mode 8) moves the gathers off the L1 path: x is spread over the shared memory of an 8-CTA cluster and read
+// through distributed shared memory.  Measured: 186 us (profiles/exp_r01_spmv_dsmem.log) — random 8-byte DSMEM reads run at
+// ~0.2 words/cycle/SM, far below the L1 path.  Both variants stay here as measured dead ends with their switches.
 //
 // --- bulk-copy pipelined variant (modes 1..5) ---
 // Why: k_spmv_flat is bound by the bytes each warp keeps in flight.  A warp loads its chunk (4 x 32 cells x 16 B = 2 KB), waits a
