@@ -28,6 +28,24 @@ def even_splitters(n_keys, world):
     return [1 + r * per for r in range(world)] + [max(n_keys, per * world) + 1]
 
 
+def sampled_splitters(local_sample, n_keys, world, group=None):
+    """Splitters from sampled quantiles (equal key ranges leave skewed data unbalanced).  Every rank passes a
+    sample of the partition keys it will submit (any length, any rank may pass none); the samples are all-gathered, sorted,
+    and cut at the world-quantiles.  Collective: every rank gets the same list.  split[0] = 1, split[world] = n_keys + 1."""
+    mine = np.asarray(local_sample, dtype=np.int64).ravel()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine, group=group)
+    allk = np.sort(np.concatenate(gathered)) if sum(len(g) for g in gathered) else np.zeros(0, np.int64)
+    if len(allk) == 0:
+        return even_splitters(n_keys, world)
+    cuts = [int(allk[min(len(allk) - 1, (r * len(allk)) // world)]) for r in range(1, world)]
+    split = [1]
+    for c in cuts:   # non-decreasing, inside [1, n_keys + 1]; equal splitters = an empty shard
+        split.append(min(max(c, split[-1]), n_keys + 1))
+    split.append(n_keys + 1)
+    return split
+
+
 def owner_of(keys, split):
     """owner(key) = number of interior splitters <= key."""
     inner = np.asarray(split[1:-1], dtype=np.int64)
@@ -126,16 +144,21 @@ class ShardedMatrix:
     enqueued the collectives of every submitted batch; the caller should also run its main work on a non-default stream)
     passes the gloo test but has not run on GPUs yet, so bench.py uses the synchronous path unless DSA_DIST_PIPELINE=1."""
 
-    def __init__(self, m, n, backend, group=None):
+    def __init__(self, m, n, backend, group=None, row_split=None, col_split=None):
+        """row_split / col_split: optional splitter lists (world + 1 entries, e.g. from sampled_splitters) for skewed keys;
+        the default is equal key ranges."""
         self.group = group
         self._router = None
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.m, self.n = int(m), int(n)
-        self.row_split = even_splitters(self.m, self.world)
-        self.col_split = even_splitters(self.n, self.world)
+        self._even = row_split is None and col_split is None
+        self.row_split = list(row_split) if row_split is not None else even_splitters(self.m, self.world)
+        self.col_split = list(col_split) if col_split is not None else even_splitters(self.n, self.world)
+        assert len(self.row_split) == self.world + 1 and len(self.col_split) == self.world + 1
         self.local = backend
-        self.rows_per = self.row_split[1] - self.row_split[0]
-        self.cols_per = self.col_split[1] - self.col_split[0]
+        # slice length of the SpMV gather buffer: the widest shard (all shards are equally wide with even splitters)
+        self.rows_per = max(b - a for a, b in zip(self.row_split[:-1], self.row_split[1:]))
+        self.cols_per = max(b - a for a, b in zip(self.col_split[:-1], self.col_split[1:]))
 
     # rank-local key ranges
     def my_rows(self):
@@ -318,6 +341,8 @@ class ShardedMatrix:
     def spmv(self, x, trans=False):
         """y = A * x (trans=False, x of length n) or transpose(A) * x; x replicated on every rank, y returned replicated."""
         per = self.cols_per if trans else self.rows_per
+        if not self._even:
+            return self._spmv_uneven(x, trans, per)
         lo = (self.col_split if trans else self.row_split)[self.rank]
         y = torch.zeros(per * self.world, dtype=torch.float64, device=x.device)
         y_slice = y[self.rank * per:(self.rank + 1) * per]
@@ -330,3 +355,22 @@ class ShardedMatrix:
             dist.all_gather(parts, y_slice.clone(), group=self.group)
             y = torch.cat(parts)
         return y[: (self.n if trans else self.m)]
+
+    def _spmv_uneven(self, x, trans, per):
+        """sampled splitters: shards differ in width; every rank still contributes a slice of `per` entries (padded), and the
+        result is assembled from the valid prefix of every slice"""
+        split = self.col_split if trans else self.row_split
+        lo, hi = split[self.rank], split[self.rank + 1]
+        y = torch.zeros(per * self.world, dtype=torch.float64, device=x.device)
+        y_slice = y[self.rank * per:(self.rank + 1) * per]
+        if hi > lo:
+            self.local.spmv_range(trans, x, y_slice[: hi - lo], lo, hi)
+        self._wait_router_issued()
+        if y.is_cuda:
+            dist.all_gather_into_tensor(y, y_slice, group=self.group)
+        else:
+            parts = [torch.empty(per, dtype=torch.float64) for _ in range(self.world)]
+            dist.all_gather(parts, y_slice.clone(), group=self.group)
+            y = torch.cat(parts)
+        out = torch.cat([y[r * per: r * per + (split[r + 1] - split[r])] for r in range(self.world)])
+        return out[: (self.n if trans else self.m)]

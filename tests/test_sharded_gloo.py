@@ -46,23 +46,37 @@ class OracleBackend:
         y_slice.copy_(torch.from_numpy(y[key_lo - 1:key_hi - 1].copy()))
 
 
-def _worker(rank, world, port, m, n, seed, q, pipelined=False):
+def _worker(rank, world, port, m, n, seed, q, pipelined=False, skew=False):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         import dsa_b200  # noqa: F401
-        from dsa_b200.sharded import ShardedMatrix, owner_of
+        from dsa_b200.sharded import ShardedMatrix, even_splitters, owner_of, sampled_splitters
         from oracle import oracle as O
 
-        A = ShardedMatrix(m, n, OracleBackend())
-        G = O.Matrix(fill_mode=False)     # the global matrix, replicated as the checker
         rng = np.random.default_rng(seed)  # same stream on both ranks: every rank knows the whole global batch
+
+        def draw(hi, size):
+            if not skew:
+                return rng.integers(1, hi + 1, size)
+            return np.minimum(hi, np.floor(hi ** rng.random(size)).astype(np.int64))   # log-uniform: half the keys below sqrt(hi)
+
+        if skew:   # splitters from sampled quantiles: each rank contributes a sample of the keys it is about to submit
+            own = np.random.default_rng([seed, rank])
+            rs = sampled_splitters(np.minimum(m, np.floor(m ** own.random(400)).astype(np.int64)), m, world)
+            cs = sampled_splitters(np.minimum(n, np.floor(n ** own.random(400)).astype(np.int64)), n, world)
+            assert rs[0] == 1 and rs[-1] == m + 1 and cs[0] == 1 and cs[-1] == n + 1 and len(rs) == world + 1
+            assert rs[1] < m // 3 and cs[1] < n // 3, (rs, cs)          # the cut follows the mass, not the key range
+            A = ShardedMatrix(m, n, OracleBackend(), row_split=rs, col_split=cs)
+        else:
+            A = ShardedMatrix(m, n, OracleBackend())
+        G = O.Matrix(fill_mode=False)     # the global matrix, replicated as the checker
         rounds = []
         for rnd in range(4):
             nb = 3000
-            I, J = rng.integers(1, m + 1, nb), rng.integers(1, n + 1, nb)
+            I, J = draw(m, nb), draw(n, nb)
             V = np.where(rng.random(nb) < 0.3, 0.0, rng.integers(1, 9, nb).astype(float))
             mine = slice(rank * nb // world, (rank + 1) * nb // world)   # this rank's share, in arrival order
             # LWW across ranks needs a global arrival order: shares are disjoint in (i, j) here (dedupe the global batch first)
@@ -101,6 +115,11 @@ def _worker(rank, world, port, m, n, seed, q, pipelined=False):
         e = A.local.cm.export(0)
         ck = e["col_keys"][e["col_live"] == 1]
         assert np.all(owner_of(ck, A.col_split) == rank)
+        if skew:   # balance of the routed work: equal key ranges would send ~85 % of a log-uniform key stream to rank 0
+            allJ = np.concatenate([r[1] for r in rounds])
+            share = np.bincount(owner_of(allJ, A.col_split), minlength=world) / len(allJ)
+            even = np.bincount(owner_of(allJ, even_splitters(n, world)), minlength=world) / len(allJ)
+            assert share.max() <= 0.65 and even.max() >= 0.8, (share, even)
         A.close()
         q.put((rank, "ok"))
     except Exception as ex:  # pragma: no cover
@@ -119,13 +138,13 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("pipelined", [False, True])
-def test_sharded_two_ranks_gloo(pipelined):
+@pytest.mark.parametrize("pipelined,skew", [(False, False), (True, False), (False, True)])
+def test_sharded_two_ranks_gloo(pipelined, skew):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, 90, 70, 123, q, pipelined)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 90, 70, 123, q, pipelined, skew)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in range(world)]
