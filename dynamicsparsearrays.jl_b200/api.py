@@ -28,7 +28,7 @@ from ._lib import ArgumentError, ErrorException, check, lib
 
 __all__ = ["DynamicSparseVector", "DynamicSparseMatrix", "DynamicMatrixColView", "SparseVector", "dynamicsparsevec",
            "dynamicsparse", "nbpartitions", "deletepartition", "deletecolumn", "deleterow", "addrow", "closefillmode",
-           "shrink_size", "nnz", "KeyCodec", "CharCodec"]
+           "shrink_size", "nnz", "KeyCodec", "CharCodec", "to_coo", "save_checkpoint", "load_checkpoint"]
 
 
 def _i64(a):
@@ -728,6 +728,47 @@ def deletepartition(orientation, key):   # deletecolumn!(mpcsc, col) on one orie
 
 def nbpartitions(orientation):   # pcsr.jl:21-22
     return orientation.info()["nb_partitions"]
+
+
+def to_coo(matrix):
+    """(rows, cols, vals) of every stored entry (explicit zeros included), column by column in ascending row order: the
+    column-major array with gaps and semaphores removed (what iterating the reference's colmajor PMA yields, pcsr.jl:269-283).
+    Keys are the device's Int64 keys (encoded if the matrix has codecs)."""
+    e = matrix.export(_lib.COLMAJOR)
+    occ = np.nonzero(e["tag"])[0]
+    key, val = e["key"][occ], e["val"][occ]
+    is_sem = key == 0                                         # semaphore cell: value = partition id (pcsr.jl:23, 26-63)
+    last_sem = np.maximum.accumulate(np.where(is_sem, np.arange(len(occ)), -1))
+    elem = ~is_sem
+    part = val[last_sem[elem]].astype(np.int64)               # partition id of the column each element belongs to
+    return key[elem], e["col_keys"][part - 1], val[elem]
+
+
+def save_checkpoint(x, path):
+    """Checkpoint of a vector or matrix as a compressed .npz of its entries.  The content is exact (keys,
+    Float64 bits, explicit zeros, dimensions); the gapped layout and deleted-column tombstones are not stored —
+    load_checkpoint rebuilds the canonical bulk-build layout, which is what the reference's own constructors produce."""
+    if isinstance(x, DynamicSparseVector):
+        k, v = x._raw_nonzeros()
+        np.savez_compressed(path, kind="vector", keys=k, vals=v, n=len(x))
+    elif isinstance(x, DynamicSparseMatrix):
+        x._not_fillmode("Cannot checkpoint a matrix in fill mode")
+        I, J, V = to_coo(x)
+        m, n = x._dims()
+        np.savez_compressed(path, kind="matrix", rows=I, cols=J, vals=V, m=m, n=n)
+    else:
+        raise TypeError(type(x))
+
+
+def load_checkpoint(path, key_codec=None, row_codec=None, col_codec=None):
+    z = np.load(path)
+    if str(z["kind"]) == "vector":
+        return dynamicsparsevec(z["keys"], z["vals"], n=int(z["n"]), key_codec=key_codec, _encoded=True)
+    h = C.c_void_p()
+    I, J, V = _i64(z["rows"]), _i64(z["cols"]), _f64(z["vals"])
+    check(lib().dsa_matrix_build_coo(_p(I), _p(J), _p(V), C.c_int64(len(I)), C.c_int64(int(z["m"])), C.c_int64(int(z["n"])),
+                                     C.c_int(1), C.c_int(_lib.COMBINE["+"]), C.byref(h)))
+    return DynamicSparseMatrix(h, row_codec=row_codec, col_codec=col_codec)
 
 
 def nnz(x):   # pma.jl:163, pcsr.jl:11, matrix.jl:91

@@ -203,3 +203,28 @@ def test_vector_misc(backend):   # vector.jl:64,85-90; pma.jl:224-234
     with pytest.raises(D.ArgumentError):
         D.dynamicsparsevec([1, 2], [1.0])
     assert D.dynamicsparsevec([1, 2, 1], [2.0, 3.0, 4.0], combine="*")[1] == 8.0
+
+
+def test_checkpoint_roundtrip(backend, tmp_path):
+    rng = np.random.default_rng(5)
+    I, J = rng.integers(1, 40, 300), rng.integers(1, 30, 300)
+    V = rng.integers(-3, 4, 300).astype(float)          # includes explicit zeros at build time (stored, vector.jl:10-36)
+    A = D.dynamicsparse(I, J, V, m=50, n=45)
+    A.set_batch(rng.integers(1, 40, 60), rng.integers(1, 30, 60), np.where(rng.random(60) < 0.5, 0.0, 2.5))
+    D.deletecolumn(A, int(J[0]))
+    r, c, v = D.to_coo(A)
+    assert len(r) == D.nnz(A) and np.all(np.diff(c) >= 0)            # column by column ...
+    same = np.diff(c) == 0
+    assert np.all(np.diff(r)[same] > 0)                              # ... ascending rows inside a column
+    assert np.array_equal(A.get_batch(r, c), v)
+    D.save_checkpoint(A, tmp_path / "a.npz")
+    B = D.load_checkpoint(tmp_path / "a.npz")
+    assert B.size == A.size == (50, 45) and D.nnz(B) == D.nnz(A)
+    rb, cb, vb = D.to_coo(B)
+    assert np.array_equal(r, rb) and np.array_equal(c, cb) and np.array_equal(v.view(np.int64), vb.view(np.int64))
+    x = rng.integers(0, 8, 45).astype(float)     # exact arithmetic: the two layouts may sum a row in different orders
+    assert np.array_equal(A.mul_dense(x), B.mul_dense(x))
+    w = D.dynamicsparsevec([5, 900, 17], [1.5, -2.0, 0.0], n=1000)
+    D.save_checkpoint(w, tmp_path / "w.npz")
+    w2 = D.load_checkpoint(tmp_path / "w.npz")
+    assert w2 == w and len(w2) == 1000 and list(w2) == [(5, 1.5), (17, 0.0), (900, -2.0)]
