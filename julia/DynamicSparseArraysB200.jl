@@ -9,7 +9,8 @@ module DynamicSparseArraysB200
 using SparseArrays
 
 export DynamicSparseVector, DynamicSparseMatrix, DynamicMatrixColView, dynamicsparsevec, dynamicsparse, nbpartitions,
-       deletecolumn!, deleterow!, addrow!, closefillmode!, shrink_size!
+       deletecolumn!, deleterow!, addrow!, closefillmode!, shrink_size!,
+       set_batch!, stage_batch!, apply_staged!        # additions: batched and double-buffered writes (no reference counterpart)
 
 const libdsa = get(ENV, "LIBDSA", joinpath(@__DIR__, "..", "dynamicsparsearrays.jl_b200", "libdsa.so"))
 const COMBINE = Dict{Any,Cint}(+ => 0, * => 1, max => 5, min => 4)
@@ -141,6 +142,28 @@ function flush!(A::DynamicSparseMatrix)
     empty!(A.pr); empty!(A.pc); empty!(A.pv)
     return
 end
+
+# Batched setindex! (no reference counterpart: the reference loops, matrix.jl:119-121): last writer wins, 0.0 deletes.
+function set_batch!(A::DynamicSparseMatrix, rows::Vector{Int64}, cols::Vector{Int64}, vals::Vector{Float64})
+    A.fillmode && error("Cannot apply a batch in fill mode")
+    length(rows) == length(cols) == length(vals) || throw(ArgumentError("rows, columns, and nonzeros do not have same length."))
+    flush!(A)
+    _check(ccall((:dsa_matrix_set_batch, libdsa), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int64),
+                 A.h, rows, cols, vals, length(vals)))
+    return A
+end
+
+# Double-buffered flush: stage_batch! starts the host->device copy of a batch and returns; apply_staged! applies the oldest
+# staged batch (two slots).  The arrays must stay reachable until their apply_staged! has returned (GC.@preserve / keep a reference).
+function stage_batch!(A::DynamicSparseMatrix, rows::Vector{Int64}, cols::Vector{Int64}, vals::Vector{Float64})
+    A.fillmode && error("Cannot apply a batch in fill mode")
+    length(rows) == length(cols) == length(vals) || throw(ArgumentError("rows, columns, and nonzeros do not have same length."))
+    flush!(A)
+    _check(ccall((:dsa_matrix_stage_batch, libdsa), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int64),
+                 A.h, rows, cols, vals, length(vals)))
+    return A
+end
+apply_staged!(A::DynamicSparseMatrix) = (_check(ccall((:dsa_matrix_apply_staged, libdsa), Cint, (Ptr{Cvoid},), A.h)); A)
 
 function Base.setindex!(A::DynamicSparseMatrix, val, row::Integer, col::Integer)                          # matrix.jl:43-62
     if A.fillmode
