@@ -167,7 +167,7 @@ def workload_config(n_gpus):
             "l2_policy": "inputs larger than L2 (2 x 268 MB gapped arrays per matrix vs 126 MB L2)", "seed": hex(SEED),
             "parallelism": f"column-range shards x{n_gpus}" if n_gpus > 1 else "single GPU",
             # experimental kernel switches in effect (empty = the validated defaults)
-            "switches": {k: os.environ[k] for k in ("DSA_SPMV_BULK", "DSA_SPMV_STEPS", "DSA_TWO_STREAMS", "DSA_SCAN_ONEPASS",
+            "switches": {k: os.environ[k] for k in ("DSA_SPMV_BULK", "DSA_SPMV_STEPS", "DSA_TWO_STREAMS", "DSA_SCAN_ONEPASS", "DSA_ILP",
                                                     "DSA_DIST_PIPELINE") if k in os.environ}}
 
 

@@ -200,6 +200,10 @@ __global__ void __launch_bounds__(256) k_bucket_rank(const BucketRec* __restrict
     u_dead[r] = dead ? 1 : 0;
 }
 
+}  // namespace dsa
+#include "ilp_pcsr.cuh"
+namespace dsa {
+
 // plain PMA: sort key = key - min
 __global__ void __launch_bounds__(256) k_make_sortkeys_vec(const int64_t* __restrict__ keys, int64_t n, int64_t mink,
                                                             uint64_t* __restrict__ sk, uint32_t* __restrict__ idx) {

@@ -1,5 +1,5 @@
 """Helper of tests/test_zz_experimental.py (not collected): config-2 style update steps with device-resident batches under
-whatever experimental switches the environment sets (DSA_TWO_STREAMS, DSA_SCAN_ONEPASS, DSA_SPMV_BULK are read once per process).  Prints the
+whatever experimental switches the environment sets (DSA_ILP, DSA_TWO_STREAMS, DSA_SCAN_ONEPASS, DSA_SPMV_BULK are read once per process).  Prints the
 time per step and saves a digest of the final layouts, so variants can be compared for bit-identical state.
 Device memory comes from libcudart through ctypes (no torch import: keeps the run short).
 usage: python tests/run_update_variant.py OUT.npz [m nnz batch steps]"""
@@ -85,7 +85,8 @@ def main():
     yh = np.zeros(m)
     assert rt.cudaMemcpy(yh.ctypes.data_as(C.c_void_p), y, C.c_size_t(yh.nbytes), C.c_int(2)) == 0
     np.savez(out, ms=ms, col=digest["col"], row=digest["row"], y=yh, nnz=D.nnz(A))
-    print(f"variant TWO_STREAMS={os.environ.get('DSA_TWO_STREAMS', '0')} SCAN_ONEPASS={os.environ.get('DSA_SCAN_ONEPASS', '0')} "
+    print(f"variant ILP={os.environ.get('DSA_ILP', '0')} TWO_STREAMS={os.environ.get('DSA_TWO_STREAMS', '1')} "
+          f"SCAN_ONEPASS={os.environ.get('DSA_SCAN_ONEPASS', '1')} "
           f"BULK={os.environ.get('DSA_SPMV_BULK', '0')}: "
           f"{ms:.3f} ms per step (wall clock, {batch} updates + SpMV) = {batch / ms / 1e3:.0f} Mupdates/s, nnz {D.nnz(A)}")
 

@@ -33,30 +33,31 @@ def _bits(a):
 def test_spmv_bulk_variants_are_bit_identical_to_flat(tmp_path, size):
     """k_spmv_bulk keeps k_spmv_flat<., 4>'s chunking and arithmetic: same bits, dense and sparse x, both orientations.
     The small size has capacity < tile for some variants: they must fall back to the flat kernel."""
-    ref = _run(tmp_path, "flat", {"DSA_SPMV_BULK": "0", "DSA_SPMV_STEPS": "4"}, size)
+    ref = _run(tmp_path, "flat", {"DSA_SPMV_BULK": "0", "DSA_SPMV_STEPS": "4"}, size)   # modes 1-5 and 8 were validated in round 1
     for mode in os.environ.get("DSA_EXP_SPMV_MODES", "1,2,3,4,5,8").split(","):
         got = _run(tmp_path, f"bulk{mode}", {"DSA_SPMV_BULK": mode, "DSA_SPMV_STEPS": "4"}, size)
         for key in ("y", "yt", "ys_k", "ys_v"):
             assert np.array_equal(_bits(ref[key]), _bits(got[key])), (mode, key)
 
 
-SWITCHES = [{"DSA_TWO_STREAMS": "1"}, {"DSA_SCAN_ONEPASS": "1"}, {"DSA_TWO_STREAMS": "1", "DSA_SCAN_ONEPASS": "1"}]
-OFF = {"DSA_TWO_STREAMS": "0", "DSA_SCAN_ONEPASS": "0", "DSA_SPMV_BULK": "0"}
+# default = two streams + one-pass scan (validated at the end of round 1); every variant below must leave bit-identical layouts
+DEFAULT = {"DSA_TWO_STREAMS": "1", "DSA_SCAN_ONEPASS": "1", "DSA_SPMV_BULK": "0", "DSA_ILP": "0"}
+SWITCHES = [{"DSA_ILP": "2"}, {"DSA_ILP": "4"}, {"DSA_TWO_STREAMS": "0"}, {"DSA_SCAN_ONEPASS": "0"}]
 
 
 @pytest.mark.parametrize("size", [(100_000, 10_000_000, 1_000_000, 10), (3_000, 200_000, 50_000, 6)])
 def test_update_switches_leave_the_same_layout(tmp_path, size):
-    """DSA_TWO_STREAMS=1 only changes which stream the twin orientation's kernels run on, DSA_SCAN_ONEPASS=1 only how prefix
-    sums are computed: both layouts, the column maps and the SpMV result must be bit-identical to the default run (the step
-    time of every variant is printed)."""
-    ref = _run(tmp_path, "default", OFF, size, script="run_update_variant.py")
+    """DSA_ILP only changes how many ops a thread of the per-op kernels handles, DSA_TWO_STREAMS which stream the twin
+    orientation's kernels run on, DSA_SCAN_ONEPASS how prefix sums are computed: both layouts, the column maps and the SpMV
+    result must be bit-identical to the default run (the step time of every variant is printed)."""
+    ref = _run(tmp_path, "default", DEFAULT, size, script="run_update_variant.py")
     for i, sw in enumerate(SWITCHES):
-        got = _run(tmp_path, f"sw{i}", dict(OFF, **sw), size, script="run_update_variant.py")
+        got = _run(tmp_path, f"sw{i}", dict(DEFAULT, **sw), size, script="run_update_variant.py")
         assert str(ref["col"]) == str(got["col"]) and str(ref["row"]) == str(got["row"]) and int(ref["nnz"]) == int(got["nnz"]), sw
         assert np.array_equal(_bits(ref["y"]), _bits(got["y"])), sw
 
 
-@pytest.mark.parametrize("sw", SWITCHES[:2])
+@pytest.mark.parametrize("sw", SWITCHES[:2])   # the unvalidated ones
 def test_parity_suite_under_switch(sw):
     """the parity tests (oracle comparisons) with one switch on"""
     env = dict(os.environ, **sw)
