@@ -7,6 +7,9 @@
 // 256-thread CTAs, so the kernel time is ~3.3 x the latency of one op's chain.  With ITEMS ops per thread the chains of ITEMS ops
 // are in flight together and the batch fits one wave.
 //
+// Also here: k_get_ilp (batched getindex, same multi-search) and k_insert_leaf_info_gallop (run end by galloping instead of a
+// ~19-step binary search; enabled by any DSA_ILP value).
+//
 // Every kernel here computes exactly what its one-op-per-thread twin computes (same outputs for every op; the only difference is
 // the arrival order of the bucket-count atomics, which the bucket path is independent of by construction: lidx is only used as a
 // unique slot inside the bucket and the in-bucket rank is by (key, arrival)).  tests/test_zz_experimental.py compares the final
@@ -205,6 +208,103 @@ __global__ void __launch_bounds__(256) k_locate_ilp(const int64_t* __restrict__ 
         op_pos[i] = pos[k];
         op_flag[i] = hit[k] ? (is_set[k] ? FL_OVERWRITE : FL_DELETE) : ((is_set[k] || (op_pid && key[k] == 0)) ? FL_INSERT : 0);
     }
+}
+
+// ---- batched getindex: ITEMS finds per thread (pma.jl:189-193 / pcsr.jl:228-232) --------------------------------------------------
+template <int ITEMS>
+__global__ void __launch_bounds__(256) k_get_ilp(const int64_t* __restrict__ keys, const double* __restrict__ vals, int64_t cap,
+                                                  const int32_t* __restrict__ q_pid, const int64_t* __restrict__ q_key, int64_t nq,
+                                                  const int64_t* __restrict__ sem, const int32_t* __restrict__ next_slot,
+                                                  double* __restrict__ out) {
+    const int64_t base = (int64_t)blockIdx.x * (256 * ITEMS) + threadIdx.x;
+    int64_t key[ITEMS], from[ITEMS], to[ITEMS], pos[ITEMS], s[ITEMS];
+    int32_t pid[ITEMS], ns[ITEMS];
+    bool in[ITEMS], go[ITEMS], hit[ITEMS];
+DSA_UNROLL
+    for (int k = 0; k < ITEMS; ++k) {
+        const int64_t i = base + (int64_t)k * 256;
+        in[k] = i < nq;
+        key[k] = 0;
+        pid[k] = -1;
+        if (in[k]) {
+            key[k] = q_key[i];
+            if (q_pid) pid[k] = q_pid[i];
+        }
+    }
+DSA_UNROLL
+    for (int k = 0; k < ITEMS; ++k) {
+        s[k] = -1;
+        ns[k] = -1;
+        if (in[k] && q_pid && pid[k] >= 0) {   // pid < 0: the column is absent (pcsr.jl:263-265)
+            s[k] = sem[pid[k]];
+            ns[k] = next_slot[pid[k]];
+        }
+    }
+DSA_UNROLL
+    for (int k = 0; k < ITEMS; ++k) {
+        pos[k] = -1;
+        hit[k] = false;
+        from[k] = 0;
+        to[k] = cap - 1;
+        go[k] = in[k];
+        if (q_pid) {
+            go[k] = in[k] && pid[k] >= 0 && s[k] >= 0;
+            if (go[k]) {
+                from[k] = s[k];
+                to[k] = (ns[k] >= 0 ? sem[ns[k]] : cap) - 1;
+            }
+        }
+    }
+    gapped_find_multi<ITEMS>(keys, key, from, to, go, pos, hit);
+    double v[ITEMS];
+DSA_UNROLL
+    for (int k = 0; k < ITEMS; ++k) v[k] = (go[k] && hit[k]) ? vals[pos[k]] : 0.0;
+DSA_UNROLL
+    for (int k = 0; k < ITEMS; ++k) {
+        const int64_t i = base + (int64_t)k * 256;
+        if (in[k]) out[i] = v[k];
+    }
+}
+
+// ---- per-leaf bookkeeping of the compacted inserts: the run end by galloping -----------------------------------------------------
+// k_insert_leaf_info finds the end of a leaf's run of inserts with a binary search over [j+1, n): ~19 dependent loads per leaf at
+// 500k inserts, although a run is 1-3 inserts long.  Galloping (probe j+1, j+2, j+4, ...) brackets the end in 1-3 loads, then the
+// binary search runs inside the bracket.  Same result: the first index >= j+1 whose predecessor position is >= leaf_end.
+__global__ void __launch_bounds__(256) k_insert_leaf_info_gallop(const int64_t* __restrict__ ins_pos, const int64_t* __restrict__ nins_dev,
+                                                                  int32_t* __restrict__ inscnt, int32_t* __restrict__ ins_first,
+                                                                  uint8_t* __restrict__ touched, int lgS, ActiveLeaf* __restrict__ act,
+                                                                  int64_t* __restrict__ nact_dev) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n = *nins_dev;
+    if (j >= n) return;
+    const int64_t pos = ins_pos[j];
+    const int64_t leaf = (pos < 0 ? 0 : pos) >> lgS;
+    if (j > 0) {
+        const int64_t pq = ins_pos[j - 1];
+        if (((pq < 0 ? 0 : pq) >> lgS) == leaf) return;
+    }
+    const int64_t leaf_end = (leaf + 1) << lgS;
+    int64_t lo = j + 1, hi = n;
+    for (int64_t step = 1;; step <<= 1) {   // invariant: ins_pos[lo - 1] < leaf_end (positions are sorted)
+        const int64_t p = j + step;
+        if (p >= n) break;
+        if (ins_pos[p] >= leaf_end) {
+            hi = p;
+            break;
+        }
+        lo = p + 1;
+    }
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (ins_pos[mid] < leaf_end) lo = mid + 1;
+        else hi = mid;
+    }
+    const int cnt = (int)(lo - j);
+    inscnt[leaf] = cnt;
+    ins_first[leaf] = (int32_t)j;
+    touched[leaf] = 1;
+    const unsigned long long slot = atomicAdd((unsigned long long*)nact_dev, 1ull);
+    act[slot] = ActiveLeaf{(int32_t)leaf, cnt, (int32_t)j, 0};
 }
 
 // ---- hits / deletes in place ------------------------------------------------------------------------------------------------------

@@ -636,8 +636,15 @@ int dsa_vec_get_batch(dsa_vec_t* v, const int64_t* keys, int64_t n, double* out)
     cudaStream_t st = v->sh.st;
     int64_t* dk = h2d(v->stg.a, keys, n, st);
     double* dout = v->stg.out.ensure((size_t)n);
-    DSA_LAUNCH("get", k_get, grid_for(n, 256), 256, 0, st, v->pma.keys.p, v->pma.vals.p, v->pma.g.capacity, (const int32_t*)nullptr, dk, n,
-               (const int64_t*)nullptr, (const int32_t*)nullptr, dout);
+    if (ilp_items() == 4)   // EXPERIMENTAL: 4 finds per thread in lock step (ilp.cuh)
+        DSA_LAUNCH("get", k_get_ilp<4>, grid_for(n, 1024), 256, 0, st, v->pma.keys.p, v->pma.vals.p, v->pma.g.capacity, (const int32_t*)nullptr,
+                   dk, n, (const int64_t*)nullptr, (const int32_t*)nullptr, dout);
+    else if (ilp_items() == 2)
+        DSA_LAUNCH("get", k_get_ilp<2>, grid_for(n, 512), 256, 0, st, v->pma.keys.p, v->pma.vals.p, v->pma.g.capacity, (const int32_t*)nullptr,
+                   dk, n, (const int64_t*)nullptr, (const int32_t*)nullptr, dout);
+    else
+        DSA_LAUNCH("get", k_get, grid_for(n, 256), 256, 0, st, v->pma.keys.p, v->pma.vals.p, v->pma.g.capacity, (const int32_t*)nullptr, dk, n,
+                   (const int64_t*)nullptr, (const int32_t*)nullptr, dout);
     DSA_CUDA(cudaMemcpyAsync(out, dout, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     DSA_CUDA(cudaStreamSynchronize(st));
     return DSA_OK;

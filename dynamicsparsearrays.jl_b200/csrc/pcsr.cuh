@@ -653,8 +653,15 @@ struct Pcsr {
         DSA_LAUNCH("colstat_init", k_colstat_init, 1, 1, 0, st, cs);
         DSA_LAUNCH("col_lookup", k_col_lookup, grid_for(n, 256), 256, 0, st, d_partkeys, (const int64_t*)nullptr, (const double*)nullptr, n,
                    d_live_keys.p, d_live_slot.p, nlive(), keymap(), keymap_min, keymap_len, op_slot, cs, (int32_t*)nullptr, (int32_t*)nullptr);
-        DSA_LAUNCH("get", k_get, grid_for(n, 256), 256, 0, st, pma.keys.p, pma.vals.p, pma.g.capacity, op_slot, d_inkeys, n, d_sem.p,
-                   d_next_slot.p, d_out);
+        if (ilp_items() == 4)   // EXPERIMENTAL: 4 finds per thread in lock step (ilp.cuh)
+            DSA_LAUNCH("get", k_get_ilp<4>, grid_for(n, 1024), 256, 0, st, pma.keys.p, pma.vals.p, pma.g.capacity, op_slot, d_inkeys, n,
+                       d_sem.p, d_next_slot.p, d_out);
+        else if (ilp_items() == 2)
+            DSA_LAUNCH("get", k_get_ilp<2>, grid_for(n, 512), 256, 0, st, pma.keys.p, pma.vals.p, pma.g.capacity, op_slot, d_inkeys, n,
+                       d_sem.p, d_next_slot.p, d_out);
+        else
+            DSA_LAUNCH("get", k_get, grid_for(n, 256), 256, 0, st, pma.keys.p, pma.vals.p, pma.g.capacity, op_slot, d_inkeys, n, d_sem.p,
+                       d_next_slot.p, d_out);
     }
 
     // spans of the listed slots, emitted in list order: returns total count; outputs in ws.tmp_k / tmp_v / tmp_owner

@@ -998,8 +998,12 @@ struct PmaCore {
                 DSA_LAUNCH("compact_inserts", k_compact_inserts, gr, 256, 0, st, op_key, op_val, ws.op_pos.p, ws.op_flag.p, ws.ins_idx.p,
                            nops, ws.ins_key.p, ws.ins_val.p, ws.ins_pos.p, n_dev);
             ActiveLeaf* act = ws.act.ensure((size_t)std::min<int64_t>(nops, g.nb_segments) + 1);
-            DSA_LAUNCH("insert_leaf_info", k_insert_leaf_info, gr, 256, 0, st, ws.ins_pos.p, ws.status + ST_NINS, ws.inscnt,
-                       ws.ins_first.p, ws.touched, lgS, act, ws.status + ST_NACT);
+            if (ilp)
+                DSA_LAUNCH("insert_leaf_info", k_insert_leaf_info_gallop, gr, 256, 0, st, ws.ins_pos.p, ws.status + ST_NINS, ws.inscnt,
+                           ws.ins_first.p, ws.touched, lgS, act, ws.status + ST_NACT);
+            else
+                DSA_LAUNCH("insert_leaf_info", k_insert_leaf_info, gr, 256, 0, st, ws.ins_pos.p, ws.status + ST_NINS, ws.inscnt,
+                           ws.ins_first.p, ws.touched, lgS, act, ws.status + ST_NACT);
         }
         rebalance_launch(ws, st);
         if (!launch_only) {
