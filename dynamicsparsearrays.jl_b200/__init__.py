@@ -7,4 +7,4 @@ from . import _lib
 from ._lib import (ArgumentError, BoundsError, CudaError, DsaError, ErrorException, build, declared_symbols, device_count, lib,
                    require_gpu)
 from .api import (Buffer, CharCodec, DynamicMatrixColView, DynamicSparseMatrix, DynamicSparseVector, SparseVector, addrow, closefillmode,
-                  deletecolumn, deletepartition, deleterow, dynamicsparse, dynamicsparsevec, KeyCodec, load_checkpoint, nbpartitions, nnz, save_checkpoint, shrink_size, to_coo)
+                  deletecolumn, deletepartition, deleterow, dynamicsparse, dynamicsparsevec, KeyCodec, load_checkpoint, nbpartitions, nnz, PackedCSC, save_checkpoint, shrink_size, to_coo)

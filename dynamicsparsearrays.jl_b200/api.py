@@ -28,7 +28,7 @@ from ._lib import ArgumentError, ErrorException, check, lib
 
 __all__ = ["DynamicSparseVector", "DynamicSparseMatrix", "DynamicMatrixColView", "SparseVector", "dynamicsparsevec",
            "dynamicsparse", "nbpartitions", "deletepartition", "deletecolumn", "deleterow", "addrow", "closefillmode",
-           "shrink_size", "nnz", "KeyCodec", "CharCodec", "to_coo", "save_checkpoint", "load_checkpoint"]
+           "shrink_size", "nnz", "KeyCodec", "CharCodec", "to_coo", "save_checkpoint", "load_checkpoint", "PackedCSC"]
 
 
 def _i64(a):
@@ -721,12 +721,16 @@ def deleterow(matrix, row):      # deleterow! (matrix.jl:104-111)
     return True
 
 
-def deletepartition(orientation, key):   # deletecolumn!(mpcsc, col) on one orientation is not exposed separately:
+def deletepartition(orientation, key):   # deletepartition!(pcsc, id) (pcsr.jl:188-204) on the PackedCSC facade; a single
+    if isinstance(orientation, PackedCSC):   # orientation of a matrix cannot lose a column on its own:
+        return orientation.deletepartition(key)
     raise ErrorException(_lib.DSA_ERR_ERROR, "deletepartition! on a single orientation would desynchronise the twin; "
                                              "use deletecolumn / deleterow on the matrix")
 
 
 def nbpartitions(orientation):   # pcsr.jl:21-22
+    if isinstance(orientation, PackedCSC):
+        return orientation.nbpartitions
     return orientation.info()["nb_partitions"]
 
 
@@ -771,6 +775,78 @@ def load_checkpoint(path, key_codec=None, row_codec=None, col_codec=None):
     return DynamicSparseMatrix(h, row_codec=row_codec, col_codec=col_codec)
 
 
+class PackedCSC:
+    """The reference's partition-id addressed PackedCSC (pcsr.jl:4-63): `pcsc[key, partition]`, partitions numbered 1..n in
+    creation order, empty partitions allowed, deleting a partition is irreversible (pcsr.jl:188-204, 294-310).
+
+    The device has no separate entry point for it — every caller in the reference goes through MappedPackedCSC — so this is a
+    facade over a DynamicSparseMatrix whose column key IS the partition id: what the facade adds is the host-side bookkeeping
+    that distinguishes the two types (creation of all partitions up to the written id, `_add_partitions!` pcsr.jl:312-319; the
+    error on a deleted partition, pcsr.jl:299)."""
+
+    def __init__(self, keys=None, values=None, combine="+", _matrix=None, _nparts=0, _deleted=()):
+        if _matrix is not None:
+            self._m, self._nparts, self._deleted = _matrix, _nparts, set(_deleted)
+            return
+        keys, values = keys or [], values or []
+        if len(keys) != len(values):
+            raise ArgumentError(_lib.DSA_ERR_ARGUMENT, "keys & values must have same length.")
+        I = [k for part in keys for k in part]
+        J = [p + 1 for p, part in enumerate(keys) for _ in part]
+        V = [v for part in values for v in part]
+        if len(I) != len(V):
+            raise ArgumentError(_lib.DSA_ERR_ARGUMENT, "keys & values must have same length.")
+        self._m = dynamicsparse(I, J, V, combine=combine) if I else dynamicsparse(fill_mode=False)
+        self._nparts, self._deleted = 0, set()
+        self._ensure_partitions(len(keys), existing={p + 1 for p, part in enumerate(keys) if len(part)})
+
+    def _ensure_partitions(self, upto, existing=()):
+        """partitions nparts+1 .. upto exist afterwards (empty unless `existing`): a zero write creates the column (pcsr.jl:341-347)"""
+        for p in range(self._nparts + 1, upto + 1):
+            if p not in existing:
+                self._m[1, p] = 0.0
+        self._nparts = max(self._nparts, upto)
+
+    def __setitem__(self, idx, val):   # pcsr.jl:294-310
+        key, part = idx
+        if part in self._deleted:
+            raise ErrorException(_lib.DSA_ERR_ERROR, f"The partition {part} has been deleted.")
+        self._ensure_partitions(part - 1)
+        self._m[key, part] = val
+        self._nparts = max(self._nparts, part)
+
+    def __getitem__(self, idx):        # pcsr.jl:222-291
+        key, part = idx
+        if isinstance(key, slice):
+            return self._m[:, part]
+        if isinstance(part, slice):
+            return self._m[key, :]
+        return self._m[key, part]
+
+    def deletepartition(self, part):   # pcsr.jl:188-204
+        if part < 1 or part > self._nparts:
+            raise _lib.BoundsError(_lib.DSA_ERR_BOUNDS, f"partition {part} out of bounds 1:{self._nparts}")
+        if part in self._deleted:
+            raise ArgumentError(_lib.DSA_ERR_ARGUMENT, f"partition {part} does not exist.")
+        deletecolumn(self._m, part)
+        self._deleted.add(part)
+        return True
+
+    @property
+    def nbpartitions(self):            # pcsr.jl:21
+        return self._nparts - len(self._deleted)
+
+    @property
+    def nnz(self):                     # pcsr.jl:11
+        return nnz(self._m)
+
+    ndim = 2
+
+    def __deepcopy__(self, memo):      # PackedCSC(pcsc) (pcsr.jl:65-71)
+        import copy
+        return PackedCSC(_matrix=copy.deepcopy(self._m), _nparts=self._nparts, _deleted=self._deleted)
+
+
 def nnz(x):   # pma.jl:163, pcsr.jl:11, matrix.jl:91
     if isinstance(x, DynamicSparseVector):
         return x.info()["nnz"]
@@ -780,4 +856,6 @@ def nnz(x):   # pma.jl:163, pcsr.jl:11, matrix.jl:91
         return x.info()["nnz"]
     if isinstance(x, SparseVector):
         return len(x.nzind)
+    if isinstance(x, PackedCSC):
+        return x.nnz
     raise TypeError(type(x))

@@ -228,3 +228,55 @@ def test_checkpoint_roundtrip(backend, tmp_path):
     D.save_checkpoint(w, tmp_path / "w.npz")
     w2 = D.load_checkpoint(tmp_path / "w.npz")
     assert w2 == w and len(w2) == 1000 and list(w2) == [(5, 1.5), (17, 0.0), (900, -2.0)]
+
+
+def test_packedcsc_simple_use(backend):   # test/functional/sparsematrix.jl:1-121 (pcsc_simple_use)
+    keys = [[1, 2, 3], [2, 6, 7], [1, 6, 8]]
+    values = [[2, 3, 4], [2, 4, 5], [3, 5, 7]]
+    p1 = D.PackedCSC(keys, values)
+    assert D.nbpartitions(p1) == 3 and p1.ndim == 2 and D.nnz(p1) == 9
+    M = np.array([[2, 0, 3], [3, 2, 0], [4, 0, 0], [0, 0, 0], [0, 0, 0], [0, 4, 5], [0, 5, 0], [0, 0, 7]], float)
+    nr, nc = M.shape
+
+    def same(p, M):
+        for i in range(nr):
+            for j in range(nc):
+                assert p[i + 1, j + 1] == M[i, j], (i, j)
+
+    same(p1, M)
+    M[0, 0] = 4; p1[1, 1] = 4                       # set
+    M[0, 1] += 3; p1[1, 2] = p1[1, 2] + 3           # new element
+    M[2, 0] = 0; p1[3, 1] = 0                       # rm
+    M[3, 1] = 1; p1[4, 2] = 1                       # new element
+    assert D.nnz(p1) == 10 and D.nbpartitions(p1) == 3
+    same(p1, M)
+    p3 = copy.deepcopy(p1)                          # PackedCSC(pcsc1)
+    row = p1[2, :]
+    assert D.nnz(row) == 2 and [row[j + 1] for j in range(nc)] == M[1].tolist()
+    col = p1[:, 2]
+    assert D.nnz(col) == 5 and [col[i + 1] for i in range(nr)] == M[:, 1].tolist()
+    for j in (1, 2, 3):
+        p3[2, j] = 0
+    assert D.nnz(p3[2, :]) == 0
+    for i in range(1, 9):
+        p3[i, 2] = 0
+    assert D.nnz(p3[:, 2]) == 0
+    p1[10, 5] = 9                                   # new element and new column: partitions 4 and 5 are created
+    assert D.nnz(p1) == 11 and D.nbpartitions(p1) == 5
+    p1[1, 4] = 2
+    assert D.nnz(p1) == 12
+    nb, nb2 = D.nnz(p1), D.nnz(p1[:, 2])
+    D.deletepartition(p1, 2)
+    assert D.nbpartitions(p1) == 4 and D.nnz(p1) == nb - nb2
+    with pytest.raises(D.ErrorException):
+        p1[1, 2] = 1                                # column 2 has been deleted (irreversible)
+    assert D.nbpartitions(p3) == 3                  # the copy is independent
+    # Test B: empty partition, duplicates combined with +
+    keys = [[1, 2, 3, 1, 2], [], [2, 6, 7, 7, 5], [1, 6, 8, 2, 1]]
+    values = [[2, 3, 4, 1, 1], [], [2, 4, 5, 1, 1], [3, 5, 7, 1, 1]]
+    p2 = D.PackedCSC(keys, values)
+    assert D.nbpartitions(p2) == 4 and D.nnz(p2) == 11
+    M2 = np.array([[3, 0, 0, 4], [4, 0, 2, 1], [4, 0, 0, 0], [0, 0, 0, 0], [0, 0, 1, 0], [0, 0, 4, 5], [0, 0, 6, 0], [0, 0, 0, 7]], float)
+    for i in range(8):
+        for j in range(4):
+            assert p2[i + 1, j + 1] == M2[i, j], (i, j)
