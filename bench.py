@@ -282,6 +282,9 @@ def main():
         roofline = {"kernel": name, "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "traffic": ncu_traffic(name),
                     "avg_us": k["avg_us"], "algorithmic_bytes": alg, "share_of_step": k["ms_per_step"] / sum(v["ms_per_step"] for v in kernels.values()),
                     "peak_source": peak_src}
+        if roofline["traffic"]:   # what the kernel physically moves (ncu DRAM bytes of the committed capture) over the live duration
+            roofline["physical_gbs"] = roofline["traffic"] / (k["avg_us"] * 1e-6) / 1e9
+            roofline["physical_frac"] = roofline["physical_gbs"] / peak
 
     # ---- e2e: host buffers through the host-pointer C-ABI calls ---------------------------------------------
     e2e = None
