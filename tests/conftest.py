@@ -13,6 +13,11 @@ def pytest_configure(config):
 
 
 def _has_gpu():
+    try:   # libdsa's own device query: no torch import (tens of seconds on a fresh box) just to collect tests
+        import dsa_b200
+        return dsa_b200.device_count() > 0
+    except Exception:
+        pass
     try:
         import torch
         return torch.cuda.is_available()
