@@ -139,4 +139,55 @@ __global__ void __launch_bounds__(256) k_bucket_scatter_ilp(const int32_t* __res
     }
 }
 
+// in-bucket ranking, ITEMS ops per thread: the four dependent rounds (own record -> bucket bounds -> bucket scan -> value gather)
+// of ITEMS ops overlap.  Same outputs as k_bucket_rank.
+template <int ITEMS>
+__global__ void __launch_bounds__(256) k_bucket_rank_ilp(const BucketRec* __restrict__ rec, const int32_t* __restrict__ boff,
+                                                          const int32_t* __restrict__ bcnt, int64_t n, const double* __restrict__ vals,
+                                                          int32_t* __restrict__ u_pid, int64_t* __restrict__ u_key, double* __restrict__ u_val,
+                                                          uint8_t* __restrict__ u_dead) {
+    const int64_t base = (int64_t)blockIdx.x * (256 * ITEMS) + threadIdx.x;
+    BucketRec me[ITEMS];
+    bool in[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const int64_t p = base + (int64_t)k * 256;
+        in[k] = p < n;
+        me[k] = BucketRec{0, 0u, 0};
+        if (in[k]) me[k] = rec[p];
+    }
+    int64_t lo[ITEMS], hi[ITEMS];
+    double v[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        lo[k] = hi[k] = 0;
+        v[k] = 0.0;
+        if (in[k]) {
+            lo[k] = boff[me[k].slot];
+            hi[k] = lo[k] + bcnt[me[k].slot];
+            v[k] = vals[me[k].arr];          // independent of the ranking: issued now, consumed at the end
+        }
+    }
+    int64_t r[ITEMS];
+    bool dead[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        r[k] = lo[k];
+        dead[k] = false;
+        for (int64_t q = lo[k]; q < hi[k]; ++q) {
+            const BucketRec o = rec[q];
+            r[k] += (o.key < me[k].key) || (o.key == me[k].key && o.arr < me[k].arr);
+            dead[k] |= (o.key == me[k].key && o.arr > me[k].arr);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        if (!in[k]) continue;
+        u_pid[r[k]] = me[k].slot;
+        u_key[r[k]] = me[k].key;
+        u_val[r[k]] = v[k];
+        u_dead[r[k]] = dead[k] ? 1 : 0;
+    }
+}
+
 }  // namespace dsa

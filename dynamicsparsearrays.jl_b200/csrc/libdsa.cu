@@ -155,7 +155,12 @@ static void phase2_launch(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t 
             DSA_LAUNCH("bucket_scatter", k_bucket_scatter_ilp<2>, grid_for(n, 512), 256, 0, st, ws.op_slot.p, ws.lidx.p, c.inkeys, n, boff, rec);
         else
             DSA_LAUNCH("bucket_scatter", k_bucket_scatter, grt, 256, 0, st, ws.op_slot.p, ws.lidx.p, c.inkeys, n, boff, rec);
-        DSA_LAUNCH("bucket_rank", k_bucket_rank, grt, 256, 0, st, rec, boff, ws.bcnt.p, n, c.vals, u_pid, u_key, u_val, dead);
+        if (ilp == 4)
+            DSA_LAUNCH("bucket_rank", k_bucket_rank_ilp<4>, grid_for(n, 1024), 256, 0, st, rec, boff, ws.bcnt.p, n, c.vals, u_pid, u_key, u_val, dead);
+        else if (ilp == 2)
+            DSA_LAUNCH("bucket_rank", k_bucket_rank_ilp<2>, grid_for(n, 512), 256, 0, st, rec, boff, ws.bcnt.p, n, c.vals, u_pid, u_key, u_val, dead);
+        else
+            DSA_LAUNCH("bucket_rank", k_bucket_rank, grt, 256, 0, st, rec, boff, ws.bcnt.p, n, c.vals, u_pid, u_key, u_val, dead);
         P.pma.apply_sorted_ops(ws.batch, u_pid, u_key, u_val, n, P.d_sem.p, P.d_next_slot.p, st, false, nullptr, /*launch_only=*/true, dead);
         return;
     }
