@@ -20,6 +20,7 @@ same names, same argument meaning, same error behaviour; the structures themselv
                                               picked automatically for one-character string keys, sparsematrix.jl:302-336)
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -218,7 +219,10 @@ class DynamicSparseVector:
 
     # -- writes -------------------------------------------------------------------------------
     def __setitem__(self, key, value):   # vector.jl:76-81
-        self._pending.a.append(self._kc.encode1(key))
+        k = int(self._kc.encode1(key))
+        if k == -(1 << 63):              # the error fires at the offending write, like the reference's setindex! would
+            raise ArgumentError(_lib.DSA_ERR_ARGUMENT, "key typemin(Int64) is reserved")
+        self._pending.a.append(k)
         self._pending.v.append(float(value))
         if len(self._pending) >= self.flush_threshold:
             self.flush()
@@ -234,8 +238,8 @@ class DynamicSparseVector:
     def flush(self):
         if len(self._pending):
             k, v = _i64(self._pending.a), _f64(self._pending.v)
-            self._pending.clear()
             check(lib().dsa_vec_set_batch(self._h, _p(k), _p(v), C.c_int64(len(k))))
+            self._pending.clear()        # only once the library has applied them: a failed flush loses nothing
 
     # -- reads --------------------------------------------------------------------------------
     def __getitem__(self, key):   # vector.jl:72-73
@@ -461,6 +465,7 @@ class DynamicSparseMatrix:
         self.buffer = Buffer() if fill_mode else None
         self._m = self._n = 0            # dims while in fill mode (matrix.jl:44-47)
         self._pending = _PendingWrites()
+        self._staged = []                # host arrays of the batches staged in the library, oldest first
         self.flush_threshold = 1 << 20
         self.colmajor = _Orientation(self, _lib.COLMAJOR)
         self.rowmajor = _Orientation(self, _lib.ROWMAJOR)
@@ -475,8 +480,11 @@ class DynamicSparseMatrix:
 
     # -- writes -------------------------------------------------------------------------------
     def __setitem__(self, idx, val):   # matrix.jl:43-62
-        row, col = self._rc.encode1(idx[0]), self._cc.encode1(idx[1])
+        row, col = int(self._rc.encode1(idx[0])), int(self._cc.encode1(idx[1]))
         val = float(val)
+        if not self.fillmode and (row < 1 or col < 1):   # device contract; raised at the offending write
+            raise ArgumentError(_lib.DSA_ERR_ARGUMENT, "row and column keys must be >= 1 (each is an in-array key of one "
+                                                       "orientation; key 0 is the semaphore key, pcsr.jl:23)")
         if self.fillmode:
             if val != 0.0:
                 self._m, self._n = max(self._m, row), max(self._n, col)
@@ -498,26 +506,32 @@ class DynamicSparseMatrix:
         check(lib().dsa_matrix_set_batch(self._h, _p(rows), _p(cols), _p(vals), C.c_int64(len(rows))))
 
     def flush(self):
+        """Everything written so far becomes visible, in arrival order: staged batches first (they were submitted before any
+        write still sitting in the queue: stage_batch flushes the queue in front of itself), then the queued single writes."""
+        while self._staged:
+            self.apply_staged()
         if len(self._pending):
             r, c, v = _i64(self._pending.a), _i64(self._pending.b), _f64(self._pending.v)
-            self._pending.clear()
             check(lib().dsa_matrix_set_batch(self._h, _p(r), _p(c), _p(v), C.c_int64(len(r))))
+            self._pending.clear()        # only once the library has applied them: a failed flush loses nothing
 
     def stage_batch(self, rows, cols, vals):
         """Start the host->device copy of a batch and return at once; apply_staged() applies it (double-buffered flush).
         The arrays must stay alive (and should be pinned) until the matching apply_staged() returns."""
         self._not_fillmode("Cannot apply a batch in fill mode")
-        self.flush()
+        if len(self._pending):           # earlier single writes go first (flush also drains the batches staged before them)
+            self.flush()
         rows, cols, vals = self._rc.encode(rows), self._cc.encode(cols), _f64(vals)
         if not (len(rows) == len(cols) == len(vals)):
             raise ArgumentError(_lib.DSA_ERR_ARGUMENT, "rows, columns, and nonzeros do not have same length.")
         check(lib().dsa_matrix_stage_batch(self._h, _p(rows), _p(cols), _p(vals), C.c_int64(len(rows))))
-        self._staged = getattr(self, "_staged", [])
         self._staged.append((rows, cols, vals))   # keep the host arrays alive until the copy has been consumed
 
     def apply_staged(self):
+        """Apply the oldest staged batch.  Reads, single writes, deletes and copies drain the staged batches themselves
+        (flush), so arrival order — last writer wins — holds whatever the caller interleaves."""
         check(lib().dsa_matrix_apply_staged(self._h))
-        if getattr(self, "_staged", None):
+        if self._staged:
             self._staged.pop(0)
 
     def _not_fillmode(self, msg):
@@ -672,7 +686,10 @@ def dynamicsparse(I=None, J=None, V=None, m=None, n=None, fill_mode=True, combin
     if not (len(I) == len(J) == len(V)):
         raise ArgumentError(_lib.DSA_ERR_ARGUMENT, "rows, columns, and nonzeros do not have same length.")
     h = C.c_void_p()
-    given = m is not None
+    given = m is not None or n is not None
+    if given:   # each missing dimension defaults on its own: m = _guess_length(I), n = _guess_length(J)  (matrix.jl:15, vector.jl:6)
+        m = int(m) if m is not None else (int(I.max()) if len(I) else 0)
+        n = int(n) if n is not None else (int(J.max()) if len(J) else 0)
     check(lib().dsa_matrix_build_coo(_p(I), _p(J), _p(V), C.c_int64(len(I)), C.c_int64(m or 0), C.c_int64(n or 0),
                                      C.c_int(1 if given else 0), C.c_int(_combine(combine)), C.byref(h)))
     return DynamicSparseMatrix(h, row_codec=row_codec, col_codec=col_codec)
@@ -765,6 +782,9 @@ def save_checkpoint(x, path):
 
 
 def load_checkpoint(path, key_codec=None, row_codec=None, col_codec=None):
+    path = str(path)
+    if not path.endswith(".npz") and not os.path.exists(path):   # np.savez appends the suffix on save
+        path += ".npz"
     z = np.load(path)
     if str(z["kind"]) == "vector":
         return dynamicsparsevec(z["keys"], z["vals"], n=int(z["n"]), key_codec=key_codec, _encoded=True)

@@ -112,8 +112,9 @@ mutable struct DynamicSparseMatrix
     fillmode::Bool
     buffer::Union{Buffer,Nothing}
     pr::Vector{Int64}; pc::Vector{Int64}; pv::Vector{Float64}           # queued single writes
+    staged::Vector{Any}                                                  # host arrays of the batches staged in the library, oldest first
     function DynamicSparseMatrix(h, fillmode)
-        A = new(h, 0, 0, fillmode, fillmode ? Buffer() : nothing, Int64[], Int64[], Float64[])
+        A = new(h, 0, 0, fillmode, fillmode ? Buffer() : nothing, Int64[], Int64[], Float64[], Any[])
         finalizer(x -> x.h != C_NULL && ccall((:dsa_matrix_destroy, libdsa), Cint, (Ptr{Cvoid},), x.h), A)
         return A
     end
@@ -124,7 +125,10 @@ function dynamicsparse(I::Vector{Int64}, J::Vector{Int64}, V::Vector{Float64}, m
     h = Ref{Ptr{Cvoid}}()
     _check(ccall((:dsa_matrix_build_coo, libdsa), Cint,
                  (Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int64, Int64, Int64, Cint, Cint, Ref{Ptr{Cvoid}}),
-                 I, J, V, length(I), m === nothing ? 0 : m, n === nothing ? 0 : n, m === nothing ? 0 : 1, 0, h))
+                 I, J, V, length(I),
+                 # each missing dimension defaults on its own: m = _guess_length(I), n = _guess_length(J)  (matrix.jl:15, vector.jl:6)
+                 m === nothing ? maximum(I; init = 0) : m, n === nothing ? maximum(J; init = 0) : n,
+                 (m === nothing && n === nothing) ? 0 : 1, 0, h))
     return DynamicSparseMatrix(h[], false)
 end
 
@@ -135,7 +139,13 @@ function dynamicsparse(::Type{Int64}, ::Type{Int64}, ::Type{Float64}; fill_mode 
     return DynamicSparseMatrix(h[], false)
 end
 
+# Everything written so far becomes visible, in arrival order: staged batches first (stage_batch! flushes the queue in front
+# of itself, so they are older than any queued write), then the queued single writes.  The queue is emptied only once the
+# library has applied it: a failed flush loses nothing.
 function flush!(A::DynamicSparseMatrix)
+    while !isempty(A.staged)
+        apply_staged!(A)
+    end
     isempty(A.pv) && return
     _check(ccall((:dsa_matrix_set_batch, libdsa), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int64),
                  A.h, A.pr, A.pc, A.pv, length(A.pv)))
@@ -158,12 +168,17 @@ end
 function stage_batch!(A::DynamicSparseMatrix, rows::Vector{Int64}, cols::Vector{Int64}, vals::Vector{Float64})
     A.fillmode && error("Cannot apply a batch in fill mode")
     length(rows) == length(cols) == length(vals) || throw(ArgumentError("rows, columns, and nonzeros do not have same length."))
-    flush!(A)
+    isempty(A.pv) || flush!(A)                                          # earlier single writes (and the batches staged before them) go first
     _check(ccall((:dsa_matrix_stage_batch, libdsa), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int64),
                  A.h, rows, cols, vals, length(vals)))
+    push!(A.staged, (rows, cols, vals))                                 # keeps the host arrays reachable until the copy is consumed
     return A
 end
-apply_staged!(A::DynamicSparseMatrix) = (_check(ccall((:dsa_matrix_apply_staged, libdsa), Cint, (Ptr{Cvoid},), A.h)); A)
+function apply_staged!(A::DynamicSparseMatrix)                           # reads, writes, deletes and copies drain staged batches through flush!
+    _check(ccall((:dsa_matrix_apply_staged, libdsa), Cint, (Ptr{Cvoid},), A.h))
+    isempty(A.staged) || popfirst!(A.staged)
+    return A
+end
 
 function Base.setindex!(A::DynamicSparseMatrix, val, row::Integer, col::Integer)                          # matrix.jl:43-62
     if A.fillmode
@@ -173,6 +188,8 @@ function Base.setindex!(A::DynamicSparseMatrix, val, row::Integer, col::Integer)
         r = get!(A.buffer.rowmajor_coo, row, (Int64[], Float64[]))                                        # buffer.jl:20-31
         push!(r[1], col); push!(r[2], val); A.buffer.length += 1
     else
+        # device contract: the error fires at the offending write, like the reference's setindex! would
+        (row >= 1 && col >= 1) || throw(ArgumentError("row and column keys must be >= 1 (key 0 is the semaphore key, pcsr.jl:23)"))
         push!(A.pr, row); push!(A.pc, col); push!(A.pv, val)
     end
     return A

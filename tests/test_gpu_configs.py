@@ -1,5 +1,7 @@
 """GPU parity at BASELINE.json's configurations (the other configs are parity-test cases, not bench lines):
 C1 vector 1M keys + 100k mixed ops, C3 column generation rounds, C5 skewed inserts forcing cascading rebalances."""
+import copy
+
 import numpy as np
 import pytest
 
@@ -40,6 +42,43 @@ def test_config1_vector_1M_keys_100k_mixed_ops():
     probe = np.concatenate([bk[:5000], keys[:5000]])
     assert np.array_equal(gv.get_batch(probe), seq.get_many(probe))
     assert len(gv) == len(seq)
+
+
+def test_full_size_config2_vs_oracle():
+    """BASELINE.json configs[1] at FULL size, bit for bit: PCSR 1e5 x 1e5 / 1e7 nnz built from the bench's own COO, then the
+    bench's first two 1M-update batches and its insert-only batch.  Layout + semaphores + column map against the oracle's batch
+    policy, logical contents against the reference's sequential setindex! loop (oracle), SpMV <= 1e-12 both ways.
+    The oracle needs ~9 s per build and ~2 s per batch."""
+    import bench as B
+    x, coo, batches, insert_only = B.make_workload(3)
+    m, n = B.M_ROWS, B.N_COLS
+    gm = D.dynamicsparse(coo[0], coo[1], coo[2], m=m, n=n)
+    pol = O.Matrix(coo[0], coo[1], coo[2], m=m, n=n)
+    assert_matrix_equal(gm, pol)                               # bulk build: layout bit-exact with the reference
+    for which in (0, 1):
+        inf = gm.info(which)
+        assert (inf["capacity"], inf["segment_capacity"], inf["height"]) == (1 << 24, 16, 20)   # SURVEY §8 table
+    seq = pol.clone()
+    g_io, pol_io, seq_io = copy.deepcopy(gm), pol.clone(), pol.clone()
+    xt = np.random.default_rng(1).random(m)
+    for bi, bj, bv in batches[:2]:
+        gm.set_batch(bi, bj, bv)
+        pol.set_batch_policy(bi, bj, bv)
+        seq.set_many(bi, bj, bv)
+        assert_matrix_equal(gm, pol)                           # layout / semaphores / column map: bit-exact vs the batch policy
+        assert_matrix_equal(gm, seq, layout=False)             # contents: bit-exact vs the reference's one-op-at-a-time loop
+        assert _rel_close(gm.mul_dense(x), seq.mul_dense(x, m))
+        assert _rel_close(gm.mul_dense(xt, trans=True), seq.mul_dense(xt, n, trans=True))
+    # configs[1] as written: ONE batched insert of 1M new entries into the fresh matrix, then SpMV
+    g_io.set_batch(*insert_only)
+    pol_io.set_batch_policy(*insert_only)
+    seq_io.set_many(*insert_only)
+    assert_matrix_equal(g_io, pol_io)
+    assert_matrix_equal(g_io, seq_io, layout=False)
+    assert g_io.info(1)["nnz"] == B.NNZ0 - B.N_OVER + B.BATCH
+    assert _rel_close(g_io.mul_dense(x), seq_io.mul_dense(x, m))
+    probe = np.random.default_rng(2).integers(0, B.BATCH, 50_000)
+    assert np.array_equal(g_io.get_batch(insert_only[0][probe], insert_only[1][probe]), insert_only[2][probe])
 
 
 def test_config3_column_generation_rounds():

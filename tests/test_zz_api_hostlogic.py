@@ -280,3 +280,53 @@ def test_packedcsc_simple_use(backend):   # test/functional/sparsematrix.jl:1-12
     for i in range(8):
         for j in range(4):
             assert p2[i + 1, j + 1] == M2[i, j], (i, j)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# round-1 advisor findings
+def test_bad_queued_write_raises_at_the_write_site_and_loses_nothing(backend):
+    """A[0, 3] = 1 must throw where it is written (the reference throws at the offending setindex!), and the valid writes
+    queued around it must survive."""
+    A = D.dynamicsparse([1], [1], [1.0])
+    A[2, 2] = 5
+    with pytest.raises(D.ArgumentError):
+        A[0, 3] = 1
+    A[3, 3] = 7
+    assert A[2, 2] == 5.0 and A[3, 3] == 7.0 and A[1, 1] == 1.0
+    v = D.dynamicsparsevec([1], [1.0])
+    v[4] = 2.0
+    with pytest.raises(D.ArgumentError):
+        v[-(1 << 63)] = 1.0
+    assert v[4] == 2.0
+
+
+def test_staged_batch_keeps_arrival_order(backend):
+    """stage_batch / apply_staged are last-writer-wins in ARRIVAL order whatever the caller interleaves: a write issued after
+    a staged batch wins over it; reads, deletes and copies see the staged batch."""
+    E = D.dynamicsparse([1], [1], [1.0])
+    E.stage_batch([1], [1], [2.0])
+    E[1, 1] = 3.0                          # later than the staged batch
+    assert E[1, 1] == 3.0                  # the read drains the staged batch first, then the queue
+    assert not E._staged
+    E.stage_batch([2, 2], [2, 3], [4.0, 5.0])
+    assert E[2, 3] == 5.0                  # reads see a staged batch
+    E.stage_batch([3], [3], [6.0])
+    c = copy.deepcopy(E)                   # so do copies ...
+    assert c[3, 3] == 6.0
+    E.stage_batch([4], [3], [8.0])
+    D.deletecolumn(E, 3)                   # ... and deletes (the staged entry of column 3 is applied, then deleted)
+    assert E[4, 3] == 0.0 and E[3, 3] == 0.0 and E[2, 2] == 4.0
+    E.stage_batch([1], [1], [9.0])
+    E.stage_batch([1], [1], [10.0])
+    E.apply_staged()
+    assert len(E._staged) == 1
+    assert E[1, 1] == 10.0 and not E._staged
+
+
+def test_missing_dimension_is_guessed_on_its_own(backend):   # matrix.jl:15: m = _guess_length(I), n = _guess_length(J)
+    A = D.dynamicsparse([1, 3], [2, 7], [1.0, 2.0], m=5)
+    assert A.size == (5, 7)
+    B = D.dynamicsparse([1, 3], [2, 7], [1.0, 2.0], n=9)
+    assert B.size == (3, 9)
+    y = A.mul_dense(np.ones(5), trans=True)
+    assert len(y) == 7 and y[1] == 1.0 and y[6] == 2.0
