@@ -237,6 +237,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle legs (cpu_baseline AND the parity check)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="multi-GPU arm: skip the full-size configs[3] run")
     ap.add_argument("--min-timed-s", type=float, default=1.0, help="the K-step region is repeated until this much time is covered")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -472,7 +472,7 @@ class DynamicSparseMatrix:
 
     def __del__(self):
         try:
-            if getattr(self, "_h", None):
+            if getattr(self, "_h", None) and getattr(self, "_owner", True):   # _owner = False: a borrowed handle (DistMatrix.local)
                 self._L.dsa_matrix_destroy(self._h)
                 self._h = None
         except Exception:

@@ -1,5 +1,6 @@
 // libdsa — C ABI (include/dsa.h) over the device structures of pma.cuh / pcsr.cuh.
 // Host orchestration only: every data-parallel step is a kernel launched on the handle's stream.
+#include <functional>
 #include <memory>
 #include <mutex>
 #include "pcsr.cuh"
@@ -35,7 +36,8 @@ struct BatchCtx {
     const int64_t* inkeys = nullptr;
     const int64_t* partkeys = nullptr;
     const double* vals = nullptr;
-    int64_t n = 0;
+    int64_t n = 0;                     // number of ops; an UPPER BOUND while n_dev is set and phase 1 has not been read back
+    const int64_t* n_dev = nullptr;    // device-side op count (distributed batches: the exchange's receive counts never visit the host)
     BatchStats bs{};
     std::vector<int32_t> new_slots_h;
 };
@@ -49,7 +51,7 @@ static void phase1_launch(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t 
     int32_t* bcnt = ws.bcnt.ensure((size_t)ns + 1);
     int32_t* lidx = ws.lidx.ensure((size_t)c.n);
     DSA_CUDA(cudaMemsetAsync(bcnt, 0, ((size_t)ns + 1) * 4, st));
-    const int ilp = ilp_items();   // EXPERIMENTAL: several ops per thread (ilp_pcsr.cuh); 0 = the validated one-op kernel
+    const int ilp = c.n_dev ? 0 : ilp_items();   // EXPERIMENTAL: several ops per thread (ilp_pcsr.cuh); 0 = the validated one-op kernel
     if (ilp == 4)
         DSA_LAUNCH("col_lookup", k_col_lookup_ilp<4>, grid_for(c.n, 1024), 256, 0, st, c.partkeys, c.inkeys, c.vals, c.n, P.d_live_keys.p,
                    P.d_live_slot.p, P.nlive(), P.keymap(), P.keymap_min, P.keymap_len, op_slot, cs, bcnt, lidx);
@@ -57,7 +59,7 @@ static void phase1_launch(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t 
         DSA_LAUNCH("col_lookup", k_col_lookup_ilp<2>, grid_for(c.n, 512), 256, 0, st, c.partkeys, c.inkeys, c.vals, c.n, P.d_live_keys.p,
                    P.d_live_slot.p, P.nlive(), P.keymap(), P.keymap_min, P.keymap_len, op_slot, cs, bcnt, lidx);
     else
-        DSA_LAUNCH("col_lookup", k_col_lookup, grid_for(c.n, 256), 256, 0, st, c.partkeys, c.inkeys, c.vals, c.n, P.d_live_keys.p,
+        DSA_LAUNCH("col_lookup", k_col_lookup, lookup_grid(c.n), 256, 0, st, c.partkeys, c.inkeys, c.vals, c.n, c.n_dev, P.d_live_keys.p,
                    P.d_live_slot.p, P.nlive(), P.keymap(), P.keymap_min, P.keymap_len, op_slot, cs, bcnt, lidx);
     DSA_CUDA(cudaMemcpyAsync(hcs, cs, CS_WORDS * 8, cudaMemcpyDeviceToHost, st));
 }
@@ -65,6 +67,10 @@ static void phase1_launch(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t 
 static void phase1_read(PcsrWorkspace& ws, BatchCtx& c) {
     const int64_t* hcs = ws.h_cs.p;
     c.bs = BatchStats{hcs[CS_MISSING], hcs[CS_MINKEY], hcs[CS_MAXKEY], hcs[CS_MAXPART_NZ], hcs[CS_MAXKEY_NZ], hcs[CS_MINPART], hcs[CS_MAXBUCKET]};
+    if (c.n_dev) {   // the count the kernels used is now known to the host: the remaining phases run on the exact size
+        c.n = hcs[CS_N];
+        c.n_dev = nullptr;
+    }
 }
 
 static void phase1_finish(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t st) {
@@ -122,8 +128,8 @@ static void phase1_finish(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t 
         // slots changed: look every op up again
         int64_t* cs = ws.cs.ensure(CS_WORDS);
         DSA_LAUNCH("colstat_init", k_colstat_init, 1, 1, 0, st, cs);
-        DSA_LAUNCH("col_lookup", k_col_lookup, gr, 256, 0, st, c.partkeys, (const int64_t*)nullptr, (const double*)nullptr, n,
-                   P.d_live_keys.p, P.d_live_slot.p, P.nlive(), P.keymap(), P.keymap_min, P.keymap_len, ws.op_slot.p, cs,
+        DSA_LAUNCH("col_lookup", k_col_lookup, lookup_grid(n), 256, 0, st, c.partkeys, (const int64_t*)nullptr, (const double*)nullptr, n,
+                   (const int64_t*)nullptr, P.d_live_keys.p, P.d_live_slot.p, P.nlive(), P.keymap(), P.keymap_min, P.keymap_len, ws.op_slot.p, cs,
                    (int32_t*)nullptr, (int32_t*)nullptr);
     }
 }
@@ -391,12 +397,15 @@ static void vec_set_batch_dev(dsa_vec* v, const int64_t* d_keys, const double* d
 // ---- matrix helpers -----------------------------------------------------------------------------------------------
 // The two orientations go through the batch phases together so that they share each stream synchronisation.  A plain matrix
 // batch feeds both with the same triples; a shard of a distributed matrix feeds them different ones.
+// nc_dev / nr_dev (nullable): device-side op counts; nc / nr are then upper bounds (distributed batches).
 static void matrix_set_batch_two(dsa_matrix* A, const int64_t* rows_c, const int64_t* cols_c, const double* vals_c, int64_t nc,
-                                 const int64_t* rows_r, const int64_t* cols_r, const double* vals_r, int64_t nr) {
+                                 const int64_t* rows_r, const int64_t* cols_r, const double* vals_r, int64_t nr,
+                                 const int64_t* nc_dev = nullptr, const int64_t* nr_dev = nullptr,
+                                 const std::function<void()>* pre_mutate = nullptr) {
     cudaStream_t st = A->sh.st;
     BatchCtx cc, cr;
-    cc.inkeys = rows_c; cc.partkeys = cols_c; cc.vals = vals_c; cc.n = nc;   // colmajor[row, col] = v  (matrix.jl:53-55)
-    cr.inkeys = cols_r; cr.partkeys = rows_r; cr.vals = vals_r; cr.n = nr;   // rowmajor[col, row] = v  (matrix.jl:57-59)
+    cc.inkeys = rows_c; cc.partkeys = cols_c; cc.vals = vals_c; cc.n = nc; cc.n_dev = nc_dev;   // colmajor[row, col] = v  (matrix.jl:53-55)
+    cr.inkeys = cols_r; cr.partkeys = rows_r; cr.vals = vals_r; cr.n = nr; cr.n_dev = nr_dev;   // rowmajor[col, row] = v  (matrix.jl:57-59)
     // The two orientations are independent (own structure, own workspace) and most of their kernels are single-wave and
     // latency-bound, so the twin's phases run on a second stream (st2) that forks from st here and joins it at the end:
     // 0.764 -> 0.668 ms per config-2 step, layouts bit-identical (profiles/exp_r01_update_switches.log).
@@ -421,8 +430,9 @@ static void matrix_set_batch_two(dsa_matrix* A, const int64_t* rows_c, const int
         if (nr > 0) phase1_launch(A->rowmajor, A->ws2, cr, st2);
         DSA_CUDA(cudaStreamSynchronize(st));
         if (st2 != st) DSA_CUDA(cudaStreamSynchronize(st2));
-        if (nc > 0) phase1_read(A->ws, cc);
-        if (nr > 0) phase1_read(A->ws2, cr);
+        if (nc > 0) { phase1_read(A->ws, cc); nc = cc.n; }
+        if (nr > 0) { phase1_read(A->ws2, cr); nr = cr.n; }
+        if (pre_mutate) (*pre_mutate)();   // caller-side validation that needs the first host synchronisation (may throw: nothing is mutated yet)
         // validate before mutate: rows are the in-array keys of the col-major structure, columns those of the row-major one
         if ((nc > 0 && cc.bs.minkey < 1) || (nr > 0 && cr.bs.minkey < 1))
             throw DsaError{DSA_ERR_ARGUMENT, "row and column keys must be >= 1 (each is an in-array key of one orientation; key 0 is the semaphore key, pcsr.jl:23)"};
@@ -1043,140 +1053,6 @@ int dsa_matrix_spmv_dense_range_d(dsa_matrix_t* A, int trans, const double* d_x,
     DSA_CATCH
 }
 
-// ---- multi-GPU routing ------------------------------------------------------------------------------------------------
-}  // extern "C"
-
-namespace dsa {
-__global__ void __launch_bounds__(256) k_route_owner(const int64_t* __restrict__ route_keys, int64_t n, const int64_t* __restrict__ splitters,
-                                                      int nranks, uint64_t* __restrict__ sk, uint32_t* __restrict__ idx) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int64_t k = route_keys[i];
-    int lo = 0, hi = nranks - 1;   // owner = number of splitters <= k
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (splitters[mid] <= k) lo = mid + 1;
-        else hi = mid;
-    }
-    sk[i] = (uint64_t)lo;
-    idx[i] = (uint32_t)i;
-}
-__global__ void __launch_bounds__(256) k_route_gather(const uint64_t* __restrict__ sk, const uint32_t* __restrict__ perm, int64_t n,
-                                                       const int64_t* __restrict__ rows, const int64_t* __restrict__ cols,
-                                                       const double* __restrict__ vals, int64_t* __restrict__ orows, int64_t* __restrict__ ocols,
-                                                       double* __restrict__ ovals, int64_t* __restrict__ counts) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t s = perm[i];
-    orows[i] = rows[s];
-    ocols[i] = cols[s];
-    ovals[i] = vals[s];
-    if (i == n - 1 || sk[i] != sk[i + 1]) counts[(int)sk[i] + 1] = i + 1;   // end offset of this owner's run
-}
-}  // namespace dsa
-
-extern "C" {
-
-int dsa_route_batch_d(const int64_t* d_route_keys, const int64_t* d_rows, const int64_t* d_cols, const double* d_vals, int64_t n,
-                      const int64_t* splitters, int nranks, int64_t* d_rows_out, int64_t* d_cols_out, double* d_vals_out,
-                      int64_t* counts_out, void* cuda_stream) {
-    DSA_TRY
-    static SortWorkspace sws;
-    static DBuf<uint64_t> sk;
-    static DBuf<uint32_t> perm;
-    static DBuf<int64_t> d_split, d_ends;
-    cudaStream_t st = (cudaStream_t)cuda_stream;
-    for (int r = 0; r < nranks; ++r) counts_out[r] = 0;
-    if (n <= 0) return DSA_OK;
-    const int ns = std::max(nranks - 1, 0);
-    d_split.ensure((size_t)ns + 1);
-    d_ends.ensure((size_t)nranks + 1);
-    if (ns) DSA_CUDA(cudaMemcpyAsync(d_split.p, splitters, (size_t)ns * 8, cudaMemcpyHostToDevice, st));
-    DSA_CUDA(cudaMemsetAsync(d_ends.p, 0xff, (size_t)(nranks + 1) * 8, st));   // -1 = owner absent
-    sk.ensure((size_t)n);
-    perm.ensure((size_t)n);
-    const unsigned gr = grid_for(n, 256);
-    DSA_LAUNCH("route_owner", k_route_owner, gr, 256, 0, st, d_route_keys, n, d_split.p, nranks, sk.p, perm.p);
-    radix_sort_pairs(sws, sk.p, perm.p, n, std::max(1, bits_for((uint64_t)std::max(nranks - 1, 1))), st);
-    DSA_LAUNCH("route_gather", k_route_gather, gr, 256, 0, st, sk.p, perm.p, n, d_rows, d_cols, d_vals, d_rows_out, d_cols_out, d_vals_out,
-               d_ends.p);
-    std::vector<int64_t> ends((size_t)nranks + 1);
-    DSA_CUDA(cudaMemcpyAsync(ends.data(), d_ends.p, (size_t)(nranks + 1) * 8, cudaMemcpyDeviceToHost, st));
-    DSA_CUDA(cudaStreamSynchronize(st));
-    int64_t prev = 0;
-    for (int r = 0; r < nranks; ++r) {
-        int64_t e = ends[(size_t)r + 1];
-        if (e < 0) e = prev;
-        counts_out[r] = e - prev;
-        prev = e;
-    }
-    return DSA_OK;
-    DSA_CATCH
-}
-
-}  // extern "C"
-namespace dsa {
-__global__ void __launch_bounds__(256) k_route_gather_packed(const uint64_t* __restrict__ sk, const uint32_t* __restrict__ perm, int64_t n,
-                                                              const int64_t* __restrict__ rows, const int64_t* __restrict__ cols,
-                                                              const double* __restrict__ vals, int64_t* __restrict__ packed,
-                                                              int64_t* __restrict__ ends) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t s = perm[i];
-    packed[3 * i + 0] = rows[s];
-    packed[3 * i + 1] = cols[s];
-    packed[3 * i + 2] = __double_as_longlong(vals[s]);
-    if (i == n - 1 || sk[i] != sk[i + 1]) ends[(int)sk[i] + 1] = i + 1;   // end offset of this owner's run
-}
-}  // namespace dsa
-extern "C" {
-int dsa_route_batch2_d(const int64_t* d_rows, const int64_t* d_cols, const double* d_vals, int64_t n, const int64_t* col_splitters,
-                       const int64_t* row_splitters, int nranks, int64_t* d_packed_by_col, int64_t* d_packed_by_row,
-                       int64_t* counts_by_col, int64_t* counts_by_row, void* cuda_stream) {
-    DSA_TRY
-    static SortWorkspace sws[2];
-    static DBuf<uint64_t> sk[2];
-    static DBuf<uint32_t> perm[2];
-    static DBuf<int64_t> d_split, d_ends;
-    static HPinned<int64_t> h_ends;
-    cudaStream_t st = (cudaStream_t)cuda_stream;
-    for (int r = 0; r < nranks; ++r) counts_by_col[r] = counts_by_row[r] = 0;
-    if (n <= 0) return DSA_OK;
-    const int ns = std::max(nranks - 1, 0);
-    d_split.ensure((size_t)2 * ns + 2);
-    d_ends.ensure((size_t)2 * (nranks + 1));
-    int64_t* he = h_ends.ensure((size_t)2 * (nranks + 1));
-    if (ns) {
-        DSA_CUDA(cudaMemcpyAsync(d_split.p, col_splitters, (size_t)ns * 8, cudaMemcpyHostToDevice, st));
-        DSA_CUDA(cudaMemcpyAsync(d_split.p + ns, row_splitters, (size_t)ns * 8, cudaMemcpyHostToDevice, st));
-    }
-    DSA_CUDA(cudaMemsetAsync(d_ends.p, 0xff, (size_t)2 * (nranks + 1) * 8, st));   // -1 = owner absent
-    const unsigned gr = grid_for(n, 256);
-    const int bits = std::max(1, bits_for((uint64_t)std::max(nranks - 1, 1)));
-    for (int o = 0; o < 2; ++o) {
-        sk[o].ensure((size_t)n);
-        perm[o].ensure((size_t)n);
-        DSA_LAUNCH("route_owner", k_route_owner, gr, 256, 0, st, o == 0 ? d_cols : d_rows, n, d_split.p + o * ns, nranks, sk[o].p, perm[o].p);
-        radix_sort_pairs(sws[o], sk[o].p, perm[o].p, n, bits, st);
-        DSA_LAUNCH("route_gather", k_route_gather_packed, gr, 256, 0, st, sk[o].p, perm[o].p, n, d_rows, d_cols, d_vals,
-                   o == 0 ? d_packed_by_col : d_packed_by_row, d_ends.p + o * (nranks + 1));
-    }
-    DSA_CUDA(cudaMemcpyAsync(he, d_ends.p, (size_t)2 * (nranks + 1) * 8, cudaMemcpyDeviceToHost, st));
-    DSA_CUDA(cudaStreamSynchronize(st));
-    for (int o = 0; o < 2; ++o) {
-        int64_t prev = 0;
-        int64_t* out = o == 0 ? counts_by_col : counts_by_row;
-        for (int r = 0; r < nranks; ++r) {
-            int64_t e = he[o * (nranks + 1) + r + 1];
-            if (e < 0) e = prev;
-            out[r] = e - prev;
-            prev = e;
-        }
-    }
-    return DSA_OK;
-    DSA_CATCH
-}
-
 // ---- measurement ------------------------------------------------------------------------------------------------------
 int dsa_trim_memory(void) {
     DSA_TRY
@@ -1211,3 +1087,5 @@ int64_t dsa_prof_dump(char* buf, int64_t cap) {
 }
 
 }  // extern "C"
+
+#include "dist_api.cuh"

@@ -13,7 +13,7 @@ namespace dsa {
 // (find(mpcsc.col_keys, col), pcsr.jl:342 — tombstones are kept out of the searched list instead of being skipped)
 // also reduces: #ops whose column is absent, min/max in-array key, max partition key / in-array key of non-zero writes
 // ---------------------------------------------------------------------------------------------
-enum { CS_MISSING = 0, CS_MINKEY = 1, CS_MAXKEY = 2, CS_MAXPART_NZ = 3, CS_MAXKEY_NZ = 4, CS_MINPART = 5, CS_MAXBUCKET = 6, CS_WORDS = 8 };
+enum { CS_MISSING = 0, CS_MINKEY = 1, CS_MAXKEY = 2, CS_MAXPART_NZ = 3, CS_MAXKEY_NZ = 4, CS_MINPART = 5, CS_MAXBUCKET = 6, CS_N = 7, CS_WORDS = 8 };
 
 __global__ void k_colstat_init(int64_t* cs) {
     cs[CS_MISSING] = 0;
@@ -24,6 +24,9 @@ __global__ void k_colstat_init(int64_t* cs) {
     cs[CS_MINPART] = INT64_MAX;
     cs[CS_MAXBUCKET] = 0;
 }
+
+// grid of the (grid-stride) column lookup: one op per thread up to 16 CTAs per SM of a 148-SM part, then strided
+inline unsigned lookup_grid(int64_t n) { return (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148 * 16)); }
 
 __device__ __forceinline__ int32_t live_lookup(const int64_t* __restrict__ live_keys, const int32_t* __restrict__ live_slot,
                                                int64_t nlive, int64_t key) {
@@ -36,19 +39,23 @@ __device__ __forceinline__ int32_t live_lookup(const int64_t* __restrict__ live_
     return (lo < nlive && live_keys[lo] == key) ? live_slot[lo] : -1;
 }
 
+// Grid-stride: the launch is sized from an upper bound when the op count only exists on the device (n_dev, distributed batches:
+// the receive counts of the exchange are never read by the host before this kernel runs); cs[CS_N] reports the count used.
 __global__ void __launch_bounds__(256) k_col_lookup(const int64_t* __restrict__ partkeys, const int64_t* __restrict__ inkeys,
-                                                     const double* __restrict__ vals, int64_t n,
+                                                     const double* __restrict__ vals, int64_t n_host, const int64_t* __restrict__ n_dev,
                                                      const int64_t* __restrict__ live_keys, const int32_t* __restrict__ live_slot,
                                                      int64_t nlive, const int32_t* __restrict__ keymap, int64_t keymap_min,
                                                      int64_t keymap_len, int32_t* __restrict__ op_slot, int64_t* __restrict__ cs,
                                                      int32_t* __restrict__ bcnt, int32_t* __restrict__ lidx) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t n = n_host;
+    if (n_dev) n = *n_dev < n_host ? *n_dev : n_host;
+    if (blockIdx.x == 0 && threadIdx.x == 0) cs[CS_N] = n;
     int64_t mink = INT64_MAX, maxk = INT64_MIN, maxp = INT64_MIN, maxknz = INT64_MIN, minp = INT64_MAX;
     int miss = 0;
     int bmax = 0;
-    if (i < n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t pk = partkeys[i];
-        minp = pk;
+        minp = pk < minp ? pk : minp;
         int32_t s;
         if (keymap) {   // dense key range: direct-address table (one load instead of a binary search)
             const int64_t r = pk - keymap_min;
@@ -57,16 +64,20 @@ __global__ void __launch_bounds__(256) k_col_lookup(const int64_t* __restrict__ 
             s = live_lookup(live_keys, live_slot, nlive, pk);
         }
         op_slot[i] = s;
-        miss = s < 0;
+        miss += s < 0;
         if (bcnt && s >= 0) {   // bucket-sort bookkeeping: arrival-independent local index inside the partition's bucket
             const int li = atomicAdd(&bcnt[s], 1);
             lidx[i] = li;
-            bmax = li + 1;
+            bmax = li + 1 > bmax ? li + 1 : bmax;
         }
         if (inkeys) {
             const int64_t k = inkeys[i];
-            mink = maxk = k;
-            if (vals && vals[i] != 0.0) { maxp = pk; maxknz = k; }
+            mink = k < mink ? k : mink;
+            maxk = k > maxk ? k : maxk;
+            if (vals && vals[i] != 0.0) {
+                maxp = pk > maxp ? pk : maxp;
+                maxknz = k > maxknz ? k : maxknz;
+            }
         }
     }
 #pragma unroll
@@ -651,8 +662,8 @@ struct Pcsr {
         int32_t* op_slot = ws.op_slot.ensure((size_t)n);
         int64_t* cs = ws.cs.ensure(CS_WORDS);
         DSA_LAUNCH("colstat_init", k_colstat_init, 1, 1, 0, st, cs);
-        DSA_LAUNCH("col_lookup", k_col_lookup, grid_for(n, 256), 256, 0, st, d_partkeys, (const int64_t*)nullptr, (const double*)nullptr, n,
-                   d_live_keys.p, d_live_slot.p, nlive(), keymap(), keymap_min, keymap_len, op_slot, cs, (int32_t*)nullptr, (int32_t*)nullptr);
+        DSA_LAUNCH("col_lookup", k_col_lookup, lookup_grid(n), 256, 0, st, d_partkeys, (const int64_t*)nullptr, (const double*)nullptr, n,
+                   (const int64_t*)nullptr, d_live_keys.p, d_live_slot.p, nlive(), keymap(), keymap_min, keymap_len, op_slot, cs, (int32_t*)nullptr, (int32_t*)nullptr);
         if (ilp_items() == 4)   // EXPERIMENTAL: 4 finds per thread in lock step (ilp.cuh)
             DSA_LAUNCH("get", k_get_ilp<4>, grid_for(n, 1024), 256, 0, st, pma.keys.p, pma.vals.p, pma.g.capacity, op_slot, d_inkeys, n,
                        d_sem.p, d_next_slot.p, d_out);

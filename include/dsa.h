@@ -161,18 +161,66 @@ int dsa_matrix_set_batch_two_d(dsa_matrix_t* A, const int64_t* d_rows_c, const i
 int dsa_matrix_spmv_dense_range_d(dsa_matrix_t* A, int trans, const double* d_x, int64_t nx, double* d_y, int64_t key_lo,
                                   int64_t key_hi);
 
-/* ---------------------------------------------------------------- multi-GPU routing ---- */
-/* owner(key) = number of splitters <= key (rank r owns keys in [splitter[r-1], splitter[r])). Stable partition of a device batch by
- * the owner of `route_keys` into rank order; counts_out[nranks] (host) gives the send counts for the all-to-all. */
-int dsa_route_batch_d(const int64_t* d_route_keys, const int64_t* d_rows, const int64_t* d_cols, const double* d_vals, int64_t n,
-                      const int64_t* splitters, int nranks, int64_t* d_rows_out, int64_t* d_cols_out, double* d_vals_out,
-                      int64_t* counts_out, void* cuda_stream);
-
-/* both routings of a matrix batch in one call: by owner(col) for the col-major shards and by owner(row) for the row-major ones.
- * Outputs are packed (n, 3) int64 rows {row, col, bits(val)} in rank order, ready for one all-to-all each; one host sync. */
-int dsa_route_batch2_d(const int64_t* d_rows, const int64_t* d_cols, const double* d_vals, int64_t n, const int64_t* col_splitters,
-                       const int64_t* row_splitters, int nranks, int64_t* d_packed_by_col, int64_t* d_packed_by_row,
-                       int64_t* counts_by_col, int64_t* counts_by_row, void* cuda_stream);
+/* ---------------------------------------------------------------- multi-GPU ---- */
+/* One process per GPU.  A dsa_dist_t is this rank's seat in a group of `world` ranks on one NVLink box; a dsa_dmatrix_t is a
+ * DynamicSparseMatrix sharded by key range over the group: rank r owns the column-major PCSR of the columns in
+ * [col_split[r], col_split[r+1]) and the row-major PCSR of the rows in [row_split[r], row_split[r+1]).  The Julia methods these
+ * replace are the same as for dsa_matrix_* (matrix.jl:15-19,43-68,95-111; operations.jl:14-36); what is new is that each is a
+ * COLLECTIVE: every rank of the group must make the same call in the same order.
+ * Communication: routed updates travel as direct NVLink stores into the owner's receive regions (CUDA IPC peer memory), fused
+ * into the routing kernel; NCCL carries only the 2 x world send counts of a batch (one small all-gather, which is also the
+ * barrier) and the all-gather of the SpMV result.  DSA_DIST_TRANSPORT=nccl selects grouped ncclSend/ncclRecv instead. */
+typedef struct dsa_dist dsa_dist_t;
+typedef struct dsa_dmatrix dsa_dmatrix_t;
+#define DSA_ERR_NCCL 13
+#define DSA_UNIQUE_ID_BYTES 128
+/* rank 0 creates the id (ncclGetUniqueId) and hands the 128 bytes to the other ranks by any host-side means */
+int dsa_dist_unique_id(void* id_out128);
+/* joins the group on the CURRENT CUDA device (collective): creates an NCCL communicator owned by the handle */
+int dsa_dist_init(const void* id128, int rank, int world, dsa_dist_t** out);
+/* same, on a communicator the host already has (an `ncclComm_t` of the same libnccl); it is not destroyed with the handle */
+int dsa_dist_init_comm(void* nccl_comm, int rank, int world, dsa_dist_t** out);
+int dsa_dist_destroy(dsa_dist_t* d);
+/* out = {rank, world, transport (0 = peer-memory stores, 1 = nccl send/recv), nccl version} */
+int dsa_dist_info(const dsa_dist_t* d, int64_t* out4);
+/* empty m x n matrix sharded over the group (collective).  row_split / col_split: world + 1 ascending first-owned keys
+ * (split[0] = 1, split[world] = dimension + 1), or NULL for equal key ranges.  max_share = the largest number of updates ONE
+ * rank will pass to a single set_batch / build round: it sizes the receive regions (a full share per (source, owner) pair and
+ * orientation, double-buffered: 96 x world x max_share bytes per rank), so no skew can overflow them. */
+int dsa_dmatrix_create(dsa_dist_t* d, int64_t m, int64_t n, const int64_t* row_split, const int64_t* col_split, int64_t max_share,
+                       dsa_dmatrix_t** out);
+int dsa_dmatrix_destroy(dsa_dmatrix_t* D);
+int dsa_dmatrix_set_stream(dsa_dmatrix_t* D, void* cuda_stream);
+/* this rank's shards as a plain matrix handle (owned by D): for dsa_matrix_info / dsa_matrix_export / dsa_matrix_column ... */
+dsa_matrix_t* dsa_dmatrix_local(dsa_dmatrix_t* D);
+/* dynamicsparse(I, J, V, m, n) (matrix.jl:15-19) over the group: every rank passes ITS share of the global COO (host
+ * pointers, any split); entries are routed to the owners of both orientations in rounds of max_share, then each shard is
+ * bulk-built (pcsr.jl:354-449).  Duplicate (i, j) are folded in global order = round-major, then rank-major, then arrival. */
+int dsa_dmatrix_build_coo(dsa_dmatrix_t* D, const int64_t* rows, const int64_t* cols, const double* vals, int64_t n, int combine);
+/* shard-local bulk build without any exchange: the caller passes exactly the entries of ITS shard of one orientation
+ * ((rows, cols) for DSA_COLMAJOR within its column range, (cols, rows) for DSA_ROWMAJOR within its row range) */
+int dsa_dmatrix_build_local(dsa_dmatrix_t* D, int which, const int64_t* inkeys, const int64_t* partkeys, const double* vals,
+                            int64_t n, int combine);
+int dsa_dmatrix_build_local_d(dsa_dmatrix_t* D, int which, const int64_t* d_inkeys, const int64_t* d_partkeys, const double* d_vals,
+                              int64_t n, int combine);
+/* batched setindex! (matrix.jl:43-62) over the group: every rank passes its share (n <= max_share, may be 0) of ONE global
+ * batch whose op order is rank-major, then arrival within a rank: last writer wins in that order, 0.0 deletes. */
+int dsa_dmatrix_set_batch(dsa_dmatrix_t* D, const int64_t* rows, const int64_t* cols, const double* vals, int64_t n);
+int dsa_dmatrix_set_batch_d(dsa_dmatrix_t* D, const int64_t* d_rows, const int64_t* d_cols, const double* d_vals, int64_t n);
+/* mat * x (trans = 0) / transpose(mat) * x (trans = 1), x replicated on every rank, y (ny entries) returned on every rank:
+ * each rank computes its slice from its row-major (col-major) shard into the gather buffer, one ncclAllGather (operations.jl:14-36) */
+int dsa_dmatrix_spmv_dense(dsa_dmatrix_t* D, int trans, const double* x, int64_t nx, double* y, int64_t ny);
+int dsa_dmatrix_spmv_dense_d(dsa_dmatrix_t* D, int trans, const double* d_x, int64_t nx, double* d_y, int64_t ny);
+/* batched getindex (matrix.jl:64-68): every rank may ask for different (row, col) pairs (n may differ); answered by the owners */
+int dsa_dmatrix_get_batch(dsa_dmatrix_t* D, int which, const int64_t* rows, const int64_t* cols, int64_t n, double* out);
+/* deletecolumn! / deleterow! (matrix.jl:95-111) over the group: the SAME list on every rank; owner(col) purges its partitions
+ * and the (row, col) delete list is routed to the owners of the rows.  DSA_ERR_ARGUMENT on every rank, with
+ * nothing changed, if a listed column does not exist. */
+int dsa_dmatrix_delete_columns(dsa_dmatrix_t* D, const int64_t* cols, int64_t n);
+int dsa_dmatrix_delete_rows(dsa_dmatrix_t* D, const int64_t* rows, int64_t n);
+/* out = {m, n, nnz over all ranks (matrix.jl:91: of the row-major shards), col-major partitions over all ranks, row-major
+ * partitions over all ranks, max_share, nnz of the col-major shards over all ranks, transport} (collective) */
+int dsa_dmatrix_info(dsa_dmatrix_t* D, int64_t* out8);
 
 /* ---------------------------------------------------------------- memory --------------- */
 /* device buffers are recycled through a size-class cache (growth of a structure would otherwise pay cudaMalloc/cudaFree of

@@ -315,16 +315,24 @@ def test_staged_flush_equals_synchronous_flush():
     for _ in range(4):
         nb = 5000
         batches.append((rng.integers(1, 450, nb), rng.integers(1, 350, nb), np.where(rng.random(nb) < 0.3, 0.0, rng.random(nb) + 0.5)))
+    def same(a, b):
+        for which in (0, 1):
+            ea, eb = a.export(which), b.export(which)   # a read: drains whatever is still staged, in arrival order
+            assert np.array_equal(ea["tag"], eb["tag"]) and np.array_equal(ea["key"], eb["key"]) and np.array_equal(ea["val"], eb["val"])
+            assert np.array_equal(ea["semaphores"], eb["semaphores"])
+
     a.stage_batch(*batches[0])
     for s in range(4):
         if s + 1 < 4:
             a.stage_batch(*batches[s + 1])       # copy of the next batch overlaps the kernels of this one
         a.apply_staged()
         b.set_batch(*batches[s])
-        for which in (0, 1):
-            ea, eb = a.export(which), b.export(which)
-            assert np.array_equal(ea["tag"], eb["tag"]) and np.array_equal(ea["key"], eb["key"]) and np.array_equal(ea["val"], eb["val"])
-            assert np.array_equal(ea["semaphores"], eb["semaphores"])
+        if s == 1:                               # reading in the middle applies the staged batch 2 first: b must have it too
+            b.set_batch(*batches[2])
+            same(a, b)
+            a.stage_batch(*batches[2])           # re-stage so that the loop's apply_staged has its batch (idempotent rewrite)
+            b.set_batch(*batches[2])
+    same(a, b)
     with pytest.raises(D.ErrorException):
         a.apply_staged()
     a.stage_batch(*batches[0])
