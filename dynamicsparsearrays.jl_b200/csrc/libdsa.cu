@@ -51,16 +51,8 @@ static void phase1_launch(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t 
     int32_t* bcnt = ws.bcnt.ensure((size_t)ns + 1);
     int32_t* lidx = ws.lidx.ensure((size_t)c.n);
     DSA_CUDA(cudaMemsetAsync(bcnt, 0, ((size_t)ns + 1) * 4, st));
-    const int ilp = c.n_dev ? 0 : ilp_items();   // EXPERIMENTAL: several ops per thread (ilp_pcsr.cuh); 0 = the validated one-op kernel
-    if (ilp == 4)
-        DSA_LAUNCH("col_lookup", k_col_lookup_ilp<4>, grid_for(c.n, 1024), 256, 0, st, c.partkeys, c.inkeys, c.vals, c.n, P.d_live_keys.p,
-                   P.d_live_slot.p, P.nlive(), P.keymap(), P.keymap_min, P.keymap_len, op_slot, cs, bcnt, lidx);
-    else if (ilp == 2)
-        DSA_LAUNCH("col_lookup", k_col_lookup_ilp<2>, grid_for(c.n, 512), 256, 0, st, c.partkeys, c.inkeys, c.vals, c.n, P.d_live_keys.p,
-                   P.d_live_slot.p, P.nlive(), P.keymap(), P.keymap_min, P.keymap_len, op_slot, cs, bcnt, lidx);
-    else
-        DSA_LAUNCH("col_lookup", k_col_lookup, lookup_grid(c.n), 256, 0, st, c.partkeys, c.inkeys, c.vals, c.n, c.n_dev, P.d_live_keys.p,
-                   P.d_live_slot.p, P.nlive(), P.keymap(), P.keymap_min, P.keymap_len, op_slot, cs, bcnt, lidx);
+    DSA_LAUNCH("col_lookup", k_col_lookup, lookup_grid(c.n), 256, 0, st, c.partkeys, c.inkeys, c.vals, c.n, c.n_dev, P.d_live_keys.p,
+               P.d_live_slot.p, P.nlive(), P.keymap(), P.keymap_min, P.keymap_len, op_slot, cs, bcnt, lidx);
     DSA_CUDA(cudaMemcpyAsync(hcs, cs, CS_WORDS * 8, cudaMemcpyDeviceToHost, st));
 }
 
@@ -154,19 +146,8 @@ static void phase2_launch(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t 
         BucketRec* rec = ws.brec.ensure((size_t)n);
         uint8_t* dead = ws.u_dead.ensure((size_t)n);
         exclusive_scan_i32<int32_t>(ws.batch.scan, ws.bcnt.p, boff, ns, nullptr, st);
-        const int ilp = ilp_items();
-        if (ilp == 4)
-            DSA_LAUNCH("bucket_scatter", k_bucket_scatter_ilp<4>, grid_for(n, 1024), 256, 0, st, ws.op_slot.p, ws.lidx.p, c.inkeys, n, boff, rec);
-        else if (ilp == 2)
-            DSA_LAUNCH("bucket_scatter", k_bucket_scatter_ilp<2>, grid_for(n, 512), 256, 0, st, ws.op_slot.p, ws.lidx.p, c.inkeys, n, boff, rec);
-        else
-            DSA_LAUNCH("bucket_scatter", k_bucket_scatter, grt, 256, 0, st, ws.op_slot.p, ws.lidx.p, c.inkeys, n, boff, rec);
-        if (ilp == 4)
-            DSA_LAUNCH("bucket_rank", k_bucket_rank_ilp<4>, grid_for(n, 1024), 256, 0, st, rec, boff, ws.bcnt.p, n, c.vals, u_pid, u_key, u_val, dead);
-        else if (ilp == 2)
-            DSA_LAUNCH("bucket_rank", k_bucket_rank_ilp<2>, grid_for(n, 512), 256, 0, st, rec, boff, ws.bcnt.p, n, c.vals, u_pid, u_key, u_val, dead);
-        else
-            DSA_LAUNCH("bucket_rank", k_bucket_rank, grt, 256, 0, st, rec, boff, ws.bcnt.p, n, c.vals, u_pid, u_key, u_val, dead);
+        DSA_LAUNCH("bucket_scatter", k_bucket_scatter, grt, 256, 0, st, ws.op_slot.p, ws.lidx.p, c.inkeys, n, boff, rec);
+        DSA_LAUNCH("bucket_rank", k_bucket_rank, grt, 256, 0, st, rec, boff, ws.bcnt.p, n, c.vals, u_pid, u_key, u_val, dead);
         P.pma.apply_sorted_ops(ws.batch, u_pid, u_key, u_val, n, P.d_sem.p, P.d_next_slot.p, st, false, nullptr, /*launch_only=*/true, dead);
         return;
     }
@@ -542,17 +523,6 @@ int dsa_level_bounds(int64_t segment_capacity, int64_t height, int64_t* mn, int6
     return DSA_OK;
 }
 int64_t dsa_spread_dest(int64_t c, int64_t m, int64_t r) { return spread_dest(spread_make(c, m), r); }
-int dsa_find_multi_host(const int64_t* keys, int64_t cap, const int64_t* q_keys, const int64_t* from, const int64_t* to, int64_t nq,
-                        int items, int64_t* pos_out, uint8_t* hit_out) {
-    DSA_TRY
-    if (items != 2 && items != 4) throw DsaError{DSA_ERR_ARGUMENT, "items must be 2 or 4"};
-    for (int64_t i = 0; i < nq; ++i)
-        if (from[i] < 0 || to[i] >= cap) throw DsaError{DSA_ERR_BOUNDS, "search range outside the array"};
-    if (items == 2) find_multi_host<2>(keys, q_keys, from, to, nq, pos_out, hit_out);
-    else find_multi_host<4>(keys, q_keys, from, to, nq, pos_out, hit_out);
-    return DSA_OK;
-    DSA_CATCH
-}
 int64_t dsa_spread_rank(int64_t c, int64_t m, int64_t p) { return spread_rank_at(spread_make(c, m), p); }
 int64_t dsa_colmap_plan(const int64_t* slot_key, const uint8_t* slot_live, int64_t nslots, const int64_t* new_keys, int64_t nnew,
                         int64_t* out_key, uint8_t* out_live, int64_t* out_old) {
@@ -651,14 +621,7 @@ int dsa_vec_get_batch(dsa_vec_t* v, const int64_t* keys, int64_t n, double* out)
     cudaStream_t st = v->sh.st;
     int64_t* dk = h2d(v->stg.a, keys, n, st);
     double* dout = v->stg.out.ensure((size_t)n);
-    if (ilp_items() == 4)   // EXPERIMENTAL: 4 finds per thread in lock step (ilp.cuh)
-        DSA_LAUNCH("get", k_get_ilp<4>, grid_for(n, 1024), 256, 0, st, v->pma.keys.p, v->pma.vals.p, v->pma.g.capacity, (const int32_t*)nullptr,
-                   dk, n, (const int64_t*)nullptr, (const int32_t*)nullptr, dout);
-    else if (ilp_items() == 2)
-        DSA_LAUNCH("get", k_get_ilp<2>, grid_for(n, 512), 256, 0, st, v->pma.keys.p, v->pma.vals.p, v->pma.g.capacity, (const int32_t*)nullptr,
-                   dk, n, (const int64_t*)nullptr, (const int32_t*)nullptr, dout);
-    else
-        DSA_LAUNCH("get", k_get, grid_for(n, 256), 256, 0, st, v->pma.keys.p, v->pma.vals.p, v->pma.g.capacity, (const int32_t*)nullptr, dk, n,
+    DSA_LAUNCH("get", k_get, grid_for(n, 256), 256, 0, st, v->pma.keys.p, v->pma.vals.p, v->pma.g.capacity, (const int32_t*)nullptr, dk, n,
                    (const int64_t*)nullptr, (const int32_t*)nullptr, dout);
     DSA_CUDA(cudaMemcpyAsync(out, dout, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     DSA_CUDA(cudaStreamSynchronize(st));

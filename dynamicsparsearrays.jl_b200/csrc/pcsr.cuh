@@ -211,9 +211,6 @@ __global__ void __launch_bounds__(256) k_bucket_rank(const BucketRec* __restrict
     u_dead[r] = dead ? 1 : 0;
 }
 
-}  // namespace dsa
-#include "ilp_pcsr.cuh"
-namespace dsa {
 
 // plain PMA: sort key = key - min
 __global__ void __launch_bounds__(256) k_make_sortkeys_vec(const int64_t* __restrict__ keys, int64_t n, int64_t mink,
@@ -507,9 +504,6 @@ __global__ void __launch_bounds__(256) k_spmv_fixup(double* __restrict__ yslot, 
     ycnt[slot] = n;
 }
 
-}  // namespace dsa
-#include "spmv_bulk.cuh"
-namespace dsa {
 
 // y by slot -> dense y indexed by partition key (1..ny)
 __global__ void __launch_bounds__(256) k_spmv_to_dense(const double* __restrict__ yslot, const int64_t* __restrict__ sem,
@@ -664,14 +658,7 @@ struct Pcsr {
         DSA_LAUNCH("colstat_init", k_colstat_init, 1, 1, 0, st, cs);
         DSA_LAUNCH("col_lookup", k_col_lookup, lookup_grid(n), 256, 0, st, d_partkeys, (const int64_t*)nullptr, (const double*)nullptr, n,
                    (const int64_t*)nullptr, d_live_keys.p, d_live_slot.p, nlive(), keymap(), keymap_min, keymap_len, op_slot, cs, (int32_t*)nullptr, (int32_t*)nullptr);
-        if (ilp_items() == 4)   // EXPERIMENTAL: 4 finds per thread in lock step (ilp.cuh)
-            DSA_LAUNCH("get", k_get_ilp<4>, grid_for(n, 1024), 256, 0, st, pma.keys.p, pma.vals.p, pma.g.capacity, op_slot, d_inkeys, n,
-                       d_sem.p, d_next_slot.p, d_out);
-        else if (ilp_items() == 2)
-            DSA_LAUNCH("get", k_get_ilp<2>, grid_for(n, 512), 256, 0, st, pma.keys.p, pma.vals.p, pma.g.capacity, op_slot, d_inkeys, n,
-                       d_sem.p, d_next_slot.p, d_out);
-        else
-            DSA_LAUNCH("get", k_get, grid_for(n, 256), 256, 0, st, pma.keys.p, pma.vals.p, pma.g.capacity, op_slot, d_inkeys, n, d_sem.p,
+        DSA_LAUNCH("get", k_get, grid_for(n, 256), 256, 0, st, pma.keys.p, pma.vals.p, pma.g.capacity, op_slot, d_inkeys, n, d_sem.p,
                        d_next_slot.p, d_out);
     }
 
@@ -730,102 +717,12 @@ struct Pcsr {
                        carry, ccnt, clast, nchunks);
         DSA_LAUNCH("spmv_fixup", k_spmv_fixup, grid_for(nchunks, 256), 256, 0, st, yslot, ycnt, carry, ccnt, clast, nchunks);
     }
-    // EXPERIMENTAL (DSA_SPMV_BULK=1..5): same chunks and arithmetic as spmv_launch<4>, the stream staged through shared memory by
-    // cp.async.bulk (spmv_bulk.cuh).  Returns false when the geometry does not fit (capacity not a multiple of the tile).
-    template <int TILE, int STAGES, int NCONS>
-    bool spmv_launch_bulk(PcsrWorkspace& ws, const double* d_x, const uint8_t* d_xmask, int64_t nx, int ctas_per_sm, cudaStream_t st) {
-        const int64_t cap = pma.g.capacity;
-        if (cap < TILE || cap % TILE != 0) return false;
-        const int64_t ntiles = cap / TILE;
-        const int64_t nchunks = cap / 128;
-        const int64_t ns = nslots();
-        double* yslot = ws.yslot.ensure((size_t)ns + 1);
-        int32_t* ycnt = ws.ycnt.ensure((size_t)ns + 1);
-        double* carry = ws.carry.ensure((size_t)nchunks);
-        int32_t* ccnt = ws.carry_cnt.ensure((size_t)nchunks);
-        int32_t* clast = ws.chunk_last.ensure((size_t)nchunks);
-        constexpr size_t smem = (size_t)STAGES * TILE * 16;
-        static int n_sm = 0;
-        if (n_sm == 0) {
-            int dev = 0;
-            DSA_CUDA(cudaGetDevice(&dev));
-            DSA_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-            DSA_CUDA(cudaFuncSetAttribute(k_spmv_bulk<true, TILE, STAGES, NCONS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            DSA_CUDA(cudaFuncSetAttribute(k_spmv_bulk<false, TILE, STAGES, NCONS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        }
-        const unsigned gr = (unsigned)std::min<int64_t>(ntiles, (int64_t)n_sm * ctas_per_sm);
-        constexpr int threads = (NCONS + 1) * 32;
-        if (d_xmask)
-            DSA_LAUNCH("spmv_bulk", (k_spmv_bulk<true, TILE, STAGES, NCONS>), gr, threads, smem, st, pma.keys.p, pma.vals.p, ntiles, d_x, d_xmask,
-                       nx, yslot, ycnt, carry, ccnt, clast);
-        else
-            DSA_LAUNCH("spmv_bulk", (k_spmv_bulk<false, TILE, STAGES, NCONS>), gr, threads, smem, st, pma.keys.p, pma.vals.p, ntiles, d_x, d_xmask,
-                       nx, yslot, ycnt, carry, ccnt, clast);
-        DSA_LAUNCH("spmv_fixup", k_spmv_fixup, grid_for(nchunks, 256), 256, 0, st, yslot, ycnt, carry, ccnt, clast, nchunks);
-        return true;
-    }
-    // EXPERIMENTAL (DSA_SPMV_BULK=8): x spread over the shared memory of 8-CTA clusters, gathers through DSMEM (spmv_bulk.cuh).
-    // Dense x only, 8 x 2^slice_lg >= nx with a slice of at most 128 KB; otherwise false (the flat kernel runs).
-    bool spmv_launch_dsmem(PcsrWorkspace& ws, const double* d_x, const uint8_t* d_xmask, int64_t nx, cudaStream_t st) {
-        constexpr int CL = 8;
-        if (d_xmask || nx <= 0) return false;
-        int slice_lg = 4;
-        while ((int64_t(CL) << slice_lg) < nx) ++slice_lg;
-        if (slice_lg > 14) return false;   // 2^14 doubles = 128 KB per CTA
-        const int64_t cap = pma.g.capacity;
-        const int64_t nchunks = (cap + 127) / 128;
-        const int64_t ns = nslots();
-        double* yslot = ws.yslot.ensure((size_t)ns + 1);
-        int32_t* ycnt = ws.ycnt.ensure((size_t)ns + 1);
-        double* carry = ws.carry.ensure((size_t)nchunks);
-        int32_t* ccnt = ws.carry_cnt.ensure((size_t)nchunks);
-        int32_t* clast = ws.chunk_last.ensure((size_t)nchunks);
-        const size_t smem = (size_t)8 << slice_lg;
-        static int n_clusters = 0;
-        if (n_clusters == 0) {
-            DSA_CUDA(cudaFuncSetAttribute(k_spmv_dsmem<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(CL * 16);
-            cfg.blockDim = dim3(1024);
-            cfg.dynamicSmemBytes = 128 * 1024;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = CL;
-            at[0].val.clusterDim.y = 1;
-            at[0].val.clusterDim.z = 1;
-            cfg.attrs = at;
-            cfg.numAttrs = 1;
-            int nc = 0;
-            if (cudaOccupancyMaxActiveClusters(&nc, k_spmv_dsmem<CL>, &cfg) != cudaSuccess || nc <= 0) {
-                cudaGetLastError();
-                n_clusters = -1;
-            } else {
-                n_clusters = nc;
-            }
-        }
-        if (n_clusters <= 0) return false;
-        const unsigned gr = (unsigned)(n_clusters * CL);   // one resident wave of clusters, persistent warps
-        DSA_LAUNCH("spmv_dsmem", (k_spmv_dsmem<CL>), gr, 1024, smem, st, pma.keys.p, pma.vals.p, cap, d_x, nx, slice_lg, yslot, ycnt, carry, ccnt,
-                   clast, nchunks);
-        DSA_LAUNCH("spmv_fixup", k_spmv_fixup, grid_for(nchunks, 256), 256, 0, st, yslot, ycnt, carry, ccnt, clast, nchunks);
-        return true;
-    }
     // flat SpMV; results by slot in ws.yslot / ws.ycnt
     void spmv_slots(PcsrWorkspace& ws, const double* d_x, const uint8_t* d_xmask, int64_t nx, cudaStream_t st) {
         static const int steps = [] {
             const char* e = getenv("DSA_SPMV_STEPS");
             return e ? atoi(e) : SPMV_STEPS_DEFAULT;
         }();
-        static const int bulk = [] {
-            const char* e = getenv("DSA_SPMV_BULK");   // experimental, off unless asked for
-            return e ? atoi(e) : 0;
-        }();
-        if (bulk == 1 && spmv_launch_bulk<2048, 4, 16>(ws, d_x, d_xmask, nx, 1, st)) return;   // 128 KB in flight per SM, 16 consumer warps
-        if (bulk == 2 && spmv_launch_bulk<2048, 3, 8>(ws, d_x, d_xmask, nx, 2, st)) return;    // 2 CTAs per SM x 96 KB
-        if (bulk == 3 && spmv_launch_bulk<4096, 3, 16>(ws, d_x, d_xmask, nx, 1, st)) return;   // 192 KB in flight per SM
-        if (bulk == 4 && spmv_launch_bulk<2048, 3, 16>(ws, d_x, d_xmask, nx, 2, st)) return;   // 2 CTAs per SM x 96 KB, 32 consumer warps (register-limited)
-        if (bulk == 5 && spmv_launch_bulk<1024, 4, 8>(ws, d_x, d_xmask, nx, 3, st)) return;    // 3 CTAs per SM x 64 KB, small tiles
-        if (bulk == 8 && spmv_launch_dsmem(ws, d_x, d_xmask, nx, st)) return;                  // x in cluster shared memory
         if (steps == 8) spmv_launch<8>(ws, d_x, d_xmask, nx, st);
         else if (steps == 2) spmv_launch<2>(ws, d_x, d_xmask, nx, st);
         else spmv_launch<4>(ws, d_x, d_xmask, nx, st);

@@ -248,9 +248,6 @@ __global__ void __launch_bounds__(256) k_insert_leaf_info(const int64_t* __restr
     act[slot] = ActiveLeaf{(int32_t)leaf, cnt, (int32_t)j, 0};
 }
 
-}  // namespace dsa
-#include "ilp.cuh"
-namespace dsa {
 
 // ---------------------------------------------------------------------------------------------
 // K3 density tree: post[0][l] = leafcnt[l] + inscnt[l]; 10 levels per block in shared memory, upper levels by one block
@@ -965,45 +962,18 @@ struct PmaCore {
         const int lgS = ilog2_i64(g.segment_capacity);
         if (nops > 0) {
             const unsigned gr = grid_for(nops, 256);
-            const int ilp = ilp_items();   // EXPERIMENTAL: several ops per thread (ilp.cuh); 0 = the validated one-op kernels
-            const unsigned gri = ilp ? grid_for(nops, 256 * ilp) : gr;
-            if (ilp == 4)
-                DSA_LAUNCH("locate", k_locate_ilp<4>, gri, 256, 0, st, keys.p, g.capacity, op_pid, op_key, op_val, nops, d_sem, d_next_slot,
-                           ws.op_pos.p, ws.op_flag.p, n_dev, op_dead);
-            else if (ilp == 2)
-                DSA_LAUNCH("locate", k_locate_ilp<2>, gri, 256, 0, st, keys.p, g.capacity, op_pid, op_key, op_val, nops, d_sem, d_next_slot,
-                           ws.op_pos.p, ws.op_flag.p, n_dev, op_dead);
-            else
-                DSA_LAUNCH("locate", k_locate, gr, 256, 0, st, keys.p, g.capacity, op_pid, op_key, op_val, nops, d_sem, d_next_slot,
-                           ws.op_pos.p, ws.op_flag.p, n_dev, op_dead);
+            DSA_LAUNCH("locate", k_locate, gr, 256, 0, st, keys.p, g.capacity, op_pid, op_key, op_val, nops, d_sem, d_next_slot,
+                       ws.op_pos.p, ws.op_flag.p, n_dev, op_dead);
             // hits are applied; ins_idx = exclusive scan of the insert flags written by the same kernel
             int32_t* f32 = ws.flag32.ensure((size_t)nops);
-            if (ilp == 4)
-                DSA_LAUNCH("apply_hits", k_apply_hits_ilp<4>, gri, 256, 0, st, keys.p, vals.p, ws.op_pos.p, ws.op_flag.p, op_val, nops,
-                           leafcnt.p, ws.touched, lgS, n_dev, f32);
-            else if (ilp == 2)
-                DSA_LAUNCH("apply_hits", k_apply_hits_ilp<2>, gri, 256, 0, st, keys.p, vals.p, ws.op_pos.p, ws.op_flag.p, op_val, nops,
-                           leafcnt.p, ws.touched, lgS, n_dev, f32);
-            else
-                DSA_LAUNCH("apply_hits", k_apply_hits, gr, 256, 0, st, keys.p, vals.p, ws.op_pos.p, ws.op_flag.p, op_val, nops,
-                           leafcnt.p, ws.touched, lgS, n_dev, f32);
+            DSA_LAUNCH("apply_hits", k_apply_hits, gr, 256, 0, st, keys.p, vals.p, ws.op_pos.p, ws.op_flag.p, op_val, nops,
+                       leafcnt.p, ws.touched, lgS, n_dev, f32);
             exclusive_scan_i32<int32_t>(ws.scan, f32, ws.ins_idx.p, nops, ws.status + ST_NINS, st);
-            if (ilp == 4)
-                DSA_LAUNCH("compact_inserts", k_compact_inserts_ilp<4>, gri, 256, 0, st, op_key, op_val, ws.op_pos.p, ws.op_flag.p,
-                           ws.ins_idx.p, nops, ws.ins_key.p, ws.ins_val.p, ws.ins_pos.p, n_dev);
-            else if (ilp == 2)
-                DSA_LAUNCH("compact_inserts", k_compact_inserts_ilp<2>, gri, 256, 0, st, op_key, op_val, ws.op_pos.p, ws.op_flag.p,
-                           ws.ins_idx.p, nops, ws.ins_key.p, ws.ins_val.p, ws.ins_pos.p, n_dev);
-            else
-                DSA_LAUNCH("compact_inserts", k_compact_inserts, gr, 256, 0, st, op_key, op_val, ws.op_pos.p, ws.op_flag.p, ws.ins_idx.p,
-                           nops, ws.ins_key.p, ws.ins_val.p, ws.ins_pos.p, n_dev);
+            DSA_LAUNCH("compact_inserts", k_compact_inserts, gr, 256, 0, st, op_key, op_val, ws.op_pos.p, ws.op_flag.p, ws.ins_idx.p,
+                       nops, ws.ins_key.p, ws.ins_val.p, ws.ins_pos.p, n_dev);
             ActiveLeaf* act = ws.act.ensure((size_t)std::min<int64_t>(nops, g.nb_segments) + 1);
-            if (ilp)
-                DSA_LAUNCH("insert_leaf_info", k_insert_leaf_info_gallop, gr, 256, 0, st, ws.ins_pos.p, ws.status + ST_NINS, ws.inscnt,
-                           ws.ins_first.p, ws.touched, lgS, act, ws.status + ST_NACT);
-            else
-                DSA_LAUNCH("insert_leaf_info", k_insert_leaf_info, gr, 256, 0, st, ws.ins_pos.p, ws.status + ST_NINS, ws.inscnt,
-                           ws.ins_first.p, ws.touched, lgS, act, ws.status + ST_NACT);
+            DSA_LAUNCH("insert_leaf_info", k_insert_leaf_info, gr, 256, 0, st, ws.ins_pos.p, ws.status + ST_NINS, ws.inscnt,
+                       ws.ins_first.p, ws.touched, lgS, act, ws.status + ST_NACT);
         }
         rebalance_launch(ws, st);
         if (!launch_only) {

@@ -66,12 +66,6 @@ int dsa_pma_geometry(int64_t nb_elements, int64_t* out4);
 int dsa_level_bounds(int64_t segment_capacity, int64_t height, int64_t* mn, int64_t* mx);
 /* closed form of spread! (moves.jl:120-172): 0-based offset of the element of rank r in a window of c cells holding m elements */
 int64_t dsa_spread_dest(int64_t c, int64_t m, int64_t r);
-/* Host execution of the lock-step multi-search used by the experimental several-ops-per-thread locate kernel (csrc/ilp.cuh):
- * queries are processed in groups of `items` (2 or 4) through the same state machine the kernel runs.  keys[cap] uses INT64_MIN
- * for gaps; from/to are 0-based inclusive ranges (from > to allowed); pos_out = position of the hit or of the predecessor (-1 =
- * none), hit_out = 1 on an exact hit: what find (finds.jl:29-61) returns.  Test hook, no device involved. */
-int dsa_find_multi_host(const int64_t* keys, int64_t cap, const int64_t* q_keys, const int64_t* from, const int64_t* to, int64_t nq,
-                        int items, int64_t* pos_out, uint8_t* hit_out);
 /* inverse: rank of the element stored at 0-based offset p, or -1 if spread! leaves a gap there */
 int64_t dsa_spread_rank(int64_t c, int64_t m, int64_t p);
 /* column-map planning of a batch (addcolumn! slot logic, pcsr.jl:148-169, replayed in arrival order).

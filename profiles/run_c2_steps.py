@@ -1,8 +1,8 @@
-"""Helper of tests/test_zz_experimental.py (not collected): config-2 style update steps with device-resident batches under
-whatever experimental switches the environment sets (DSA_ILP, DSA_TWO_STREAMS, DSA_SCAN_ONEPASS, DSA_SPMV_BULK are read once per process).  Prints the
-time per step and saves a digest of the final layouts, so variants can be compared for bit-identical state.
+"""Config-2 style update steps with device-resident batches, for profiling (profiles/capture_ncu.sh) and for comparing kernel
+switches (DSA_* environment variables are read once per process): prints the time per step and saves a digest of the final
+layouts, so that two runs can be compared for bit-identical state.
 Device memory comes from libcudart through ctypes (no torch import: keeps the run short).
-usage: python tests/run_update_variant.py OUT.npz [m nnz batch steps]"""
+usage: python profiles/run_c2_steps.py OUT.npz [m nnz batch steps]"""
 import ctypes as C
 import hashlib
 import os
@@ -85,9 +85,8 @@ def main():
     yh = np.zeros(m)
     assert rt.cudaMemcpy(yh.ctypes.data_as(C.c_void_p), y, C.c_size_t(yh.nbytes), C.c_int(2)) == 0
     np.savez(out, ms=ms, col=digest["col"], row=digest["row"], y=yh, nnz=D.nnz(A))
-    print(f"variant ILP={os.environ.get('DSA_ILP', '0')} TWO_STREAMS={os.environ.get('DSA_TWO_STREAMS', '1')} "
-          f"SCAN_ONEPASS={os.environ.get('DSA_SCAN_ONEPASS', '1')} "
-          f"BULK={os.environ.get('DSA_SPMV_BULK', '0')}: "
+    sw = {k: v for k, v in sorted(os.environ.items()) if k.startswith("DSA_")}
+    print(f"switches {sw}: col {digest['col'][:12]} row {digest['row'][:12]} "
           f"{ms:.3f} ms per step (wall clock, {batch} updates + SpMV) = {batch / ms / 1e3:.0f} Mupdates/s, nnz {D.nnz(A)}")
 
 

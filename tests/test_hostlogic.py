@@ -175,35 +175,3 @@ def test_python_buffer_matches_reference_semantics():   # buffer.jl:10-50
                                                                       (5, 9, 1.0)])
 
 
-@pytest.mark.parametrize("items", [2, 4])
-@pytest.mark.parametrize("seed", [0, 1, 2])
-def test_lockstep_multi_search_equals_reference_find(items, seed):   # finds.jl:29-61; csrc/ilp.cuh gapped_find_multi
-    """The several-ops-per-thread locate kernel advances ITEMS gapped binary searches in lock step.  The same state machine, run
-    on the host through dsa_find_multi_host, must return what the reference's find returns for every query: whole array,
-    sub-ranges, ranges that start in a run of gaps, empty ranges, keys below / above / between / equal to stored keys."""
-    rng = np.random.default_rng(seed)
-    GAP = np.iinfo(np.int64).min
-    for cap, density in [(8, 0.5), (64, 0.3), (256, 0.7), (1024, 0.05), (64, 1.0), (32, 0.0)]:
-        live = rng.random(cap) < density
-        vals = np.sort(rng.choice(np.arange(1, 10 * cap), int(live.sum()), replace=False))
-        keys = np.full(cap, GAP, np.int64)
-        keys[live] = vals
-        cells = Cells([None if k == GAP else (int(k), 1.0) for k in keys])
-        nq = 200
-        q = rng.integers(0, 10 * cap + 2, nq)
-        if len(vals):
-            q[: nq // 3] = rng.choice(vals, nq // 3)            # exact hits
-        frm = rng.integers(0, cap, nq)
-        to = np.minimum(cap - 1, frm + rng.integers(-1, cap, nq))   # includes empty ranges (to = from - 1)
-        frm[: nq // 4], to[: nq // 4] = 0, cap - 1              # whole-array searches
-        pos = np.full(nq, -7, np.int64)
-        hit = np.full(nq, 7, np.uint8)
-        rc = D.lib().dsa_find_multi_host(_p(keys), C.c_int64(cap), _p(np.ascontiguousarray(q)), _p(np.ascontiguousarray(frm)),
-                                         _p(np.ascontiguousarray(to)), C.c_int64(nq), C.c_int(items), _p(pos), _p(hit))
-        assert rc == 0
-        for j in range(nq):
-            p_ref, cell = O.find(cells, int(q[j]), int(frm[j]) + 1, int(to[j]) + 1)     # the oracle is 1-based
-            assert pos[j] == p_ref - 1, (cap, density, j, int(q[j]), int(frm[j]), int(to[j]), int(pos[j]), p_ref)
-            assert hit[j] == (1 if cell is not None and cell[0] == q[j] and p_ref - 1 >= frm[j] else 0), (cap, j)
-    bad = D.lib().dsa_find_multi_host(_p(keys), C.c_int64(cap), _p(q), _p(frm), _p(to), C.c_int64(1), C.c_int(3), _p(pos), _p(hit))
-    assert bad == D._lib.DSA_ERR_ARGUMENT
