@@ -23,7 +23,7 @@ def _block(torch, dev, seed, a, b, lo_r, hi_r, lo_c, hi_c, nnz, parity):
     """entries of global block (row range a, col range b): the same device-side stream on every rank.  (i + j) has the given
     parity, so that later inserts (opposite parity) can never collide with an initial entry."""
     g = torch.Generator(device=dev)
-    g.manual_seed((seed * 1_000_003 + a) * 1_000_003 + b)
+    g.manual_seed(((seed * 1_000_003 + a) * 1_000_003 + b) % (1 << 62))
     I = torch.randint(lo_r, hi_r, (nnz,), generator=g, device=dev, dtype=torch.int64)
     J = torch.randint(lo_c, hi_c, (nnz,), generator=g, device=dev, dtype=torch.int64)
     fix = ((I + J) & 1) != parity
@@ -100,7 +100,7 @@ def main_dist(args, rank, world, local_rank):
     # a CYCLE of P shares per rank: share k inserts S_k (new entries) and deletes S_{k-1}; S_{P-1} is inserted before the
     # warm-up, so the chain is periodic and the structure stays at ~1e7 nnz per shard however many repeats are timed
     g = torch.Generator(device=dev)
-    g.manual_seed(B.SEED * 7 + rank)
+    g.manual_seed((B.SEED * 7 + rank) % (1 << 62))
     half = B.BATCH // 2
     S = [_fresh(torch, dev, g, m, n, half) for _ in range(P)]
     shares = []
@@ -264,7 +264,7 @@ def run_c4(torch, dist, B, D, ctx, dev, stream, rank, world, parity):
     t_build = time.perf_counter() - t_build
     inf0 = A.local.info(1)
     g = torch.Generator(device=dev)
-    g.manual_seed((B.SEED + 4) * 7 + rank)
+    g.manual_seed(((B.SEED + 4) * 7 + rank) % (1 << 62))
     n_del = share // 10
     n_ins = share - n_del
     x = torch.rand(n, device=dev, dtype=torch.float64, generator=torch.Generator(device=dev).manual_seed(B.SEED + 13))

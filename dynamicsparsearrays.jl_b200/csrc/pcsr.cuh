@@ -485,7 +485,142 @@ __global__ void __launch_bounds__(256) k_spmv_flat(const int64_t* __restrict__ k
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K7, blocked variant (the default): every lane owns C CONTIGUOUS cells (one 256-bit load of keys, one of values, both
+// L1::no_allocate so that x keeps the L1), reduces them sequentially — heads inside the lane close their partition in
+// registers — and the warp then needs ONE segmented scan over the 32 lane aggregates per chunk, whatever the number of heads.
+// k_spmv_flat pays ~40 shuffles per 32-cell step that contains a head (77 % of the chunks at config 2) and ran at 86 us where
+// the same loads + gathers without the reduction take 50 us (profiles/gather_probe.cu); this one needs 13 shuffles per
+// 32*C cells.  Same carry / fix-up protocol and the same per-partition order (ascending cells); the association differs
+// (sequential inside a lane, tree across lanes), within the 1e-12 bar and exact for integer-valued data.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldg_stream4(const int64_t* p, int64_t& a, int64_t& b, int64_t& c, int64_t& d) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+}
+__device__ __forceinline__ void ldg_stream4(const double* p, double& a, double& b, double& c, double& d) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
+template <bool SPARSE_X, int C>
+__global__ void __launch_bounds__(256) k_spmv_blocked(const int64_t* __restrict__ keys, const double* __restrict__ vals, int64_t cap,
+                                                       const double* __restrict__ x, const uint8_t* __restrict__ xmask, int64_t nx,
+                                                       double* __restrict__ yslot, int32_t* __restrict__ ycnt,
+                                                       double* __restrict__ carry, int32_t* __restrict__ carry_cnt,
+                                                       int32_t* __restrict__ chunk_last_slot, int64_t nchunks) {
+    static_assert(C % 4 == 0, "a lane loads its cells in groups of 4 (256 bits)");
+    const int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (chunk >= nchunks) return;
+    const unsigned lt = lanemask_lt();
+    const int64_t p0 = chunk * (32 * C) + (int64_t)lane * C;
+    int64_t k[C];
+    double t[C];
+#pragma unroll
+    for (int c = 0; c < C; c += 4) {
+        if (p0 + c + 4 <= cap) {
+            ldg_stream4(keys + p0 + c, k[c], k[c + 1], k[c + 2], k[c + 3]);
+            ldg_stream4(vals + p0 + c, t[c], t[c + 1], t[c + 2], t[c + 3]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int64_t p = p0 + c + e;
+                k[c + e] = p < cap ? keys[p] : GAP_KEY;
+                t[c + e] = p < cap ? vals[p] : 0.0;
+            }
+        }
+    }
+    // the C gathers of x are independent: all in flight together.  t = x[key] * value (separate rounding, operations.jl:101);
+    // heads keep their value (the partition id) in t
+    int tcn[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        tcn[c] = 0;
+        const int64_t kk = k[c];
+        if (kk > 0) {
+            bool present = kk <= nx;
+            if (SPARSE_X) present = present && xmask[kk - 1] != 0;
+            double xv = 0.0;
+            if (present) xv = __ldg(x + (kk - 1));
+            t[c] = present ? __dmul_rn(xv, t[c]) : 0.0;
+            tcn[c] = present ? 1 : 0;
+        }
+    }
+    // sequential reduction of the lane's cells
+    double run = 0.0, pre = 0.0;   // run: sum since the lane's last head (or lane start); pre: cells before its first head
+    int runc = 0, prec = 0;
+    bool has_head = false;
+    int32_t lastslot = -1;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        if (k[c] == 0) {
+            if (!has_head) {
+                pre = run;
+                prec = runc;
+            } else {   // a whole partition inside this lane
+                yslot[lastslot] = run;
+                if (SPARSE_X) ycnt[lastslot] = runc;
+            }
+            has_head = true;
+            lastslot = (int32_t)t[c] - 1;
+            run = 0.0;
+            runc = 0;
+        } else if (k[c] > 0) {
+            run = __dadd_rn(run, t[c]);
+            runc += tcn[c];
+        }
+    }
+    // segmented inclusive scan over the lanes: a lane with a head starts a new segment with its tail (run)
+    const unsigned hb = __ballot_sync(0xffffffffu, has_head);
+    const unsigned hle = hb & (lt | (1u << lane));
+    const int seg_lo = hle ? 31 - __clz(hle) : 0;
+    double inc = run;
+    int incc = runc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double u = __shfl_up_sync(0xffffffffu, inc, o);
+        int uc = 0;
+        if (SPARSE_X) uc = __shfl_up_sync(0xffffffffu, incc, o);
+        if (lane >= o && lane - o >= seg_lo) {
+            inc = __dadd_rn(u, inc);
+            incc += uc;
+        }
+    }
+    double cin = __shfl_up_sync(0xffffffffu, inc, 1);   // open partition's partial over the lanes before this one
+    int cinc = 0;
+    if (SPARSE_X) cinc = __shfl_up_sync(0xffffffffu, incc, 1);
+    if (lane == 0) {
+        cin = 0.0;
+        cinc = 0;
+    }
+    const unsigned hlt = hb & lt;
+    const int32_t prev_slot = __shfl_sync(0xffffffffu, lastslot, hlt ? 31 - __clz(hlt) : 0);
+    if (has_head) {   // this lane's first head closes the partition that was open before it
+        const double tot = __dadd_rn(cin, pre);
+        const int totc = cinc + prec;
+        if (hlt) {
+            yslot[prev_slot] = tot;
+            if (SPARSE_X) ycnt[prev_slot] = totc;
+        } else {   // it started in an earlier chunk: the fix-up adds this prefix to that chunk's open partition
+            carry[chunk] = tot;
+            if (SPARSE_X) carry_cnt[chunk] = totc;
+        }
+    }
+    const int32_t end_slot = __shfl_sync(0xffffffffu, lastslot, hb ? 31 - __clz(hb) : 0);
+    if (lane == 31) {
+        if (hb) {   // open partition at the end of the chunk: partial, completed by the fix-up
+            yslot[end_slot] = inc;
+            if (SPARSE_X) ycnt[end_slot] = incc;
+            chunk_last_slot[chunk] = end_slot;
+        } else {    // no head in the whole chunk
+            carry[chunk] = inc;
+            if (SPARSE_X) carry_cnt[chunk] = incc;
+            chunk_last_slot[chunk] = -1;
+        }
+    }
+}
+
 // chunk c with a head: y[last partition of c] += carry[c+1] + carry[c+2] + ... up to and including the first chunk that has a head
+template <bool COUNTS>
 __global__ void __launch_bounds__(256) k_spmv_fixup(double* __restrict__ yslot, int32_t* __restrict__ ycnt, const double* __restrict__ carry,
                                                      const int32_t* __restrict__ carry_cnt, const int32_t* __restrict__ chunk_last_slot,
                                                      int64_t nchunks) {
@@ -493,15 +628,16 @@ __global__ void __launch_bounds__(256) k_spmv_fixup(double* __restrict__ yslot, 
     if (c >= nchunks) return;
     const int32_t slot = chunk_last_slot[c];
     if (slot < 0) return;
+    if (c + 1 >= nchunks) return;
     double a = yslot[slot];
-    int32_t n = ycnt[slot];
+    int32_t n = COUNTS ? ycnt[slot] : 0;
     for (int64_t d = c + 1; d < nchunks; ++d) {
         a = __dadd_rn(a, carry[d]);
-        n += carry_cnt[d];
+        if (COUNTS) n += carry_cnt[d];
         if (chunk_last_slot[d] >= 0) break;
     }
     yslot[slot] = a;
-    ycnt[slot] = n;
+    if (COUNTS) ycnt[slot] = n;
 }
 
 
@@ -715,15 +851,45 @@ struct Pcsr {
         else
             DSA_LAUNCH("spmv_flat", (k_spmv_flat<false, STEPS>), gr, 256, 0, st, pma.keys.p, pma.vals.p, cap, d_x, d_xmask, nx, yslot, ycnt,
                        carry, ccnt, clast, nchunks);
-        DSA_LAUNCH("spmv_fixup", k_spmv_fixup, grid_for(nchunks, 256), 256, 0, st, yslot, ycnt, carry, ccnt, clast, nchunks);
+        DSA_LAUNCH("spmv_fixup", k_spmv_fixup<true>, grid_for(nchunks, 256), 256, 0, st, yslot, ycnt, carry, ccnt, clast, nchunks);
     }
-    // flat SpMV; results by slot in ws.yslot / ws.ycnt
+    // blocked SpMV (default).  Dense x: the product counts (only the sparse output needs them) are not computed.
+    template <int C>
+    void spmv_launch_blocked(PcsrWorkspace& ws, const double* d_x, const uint8_t* d_xmask, int64_t nx, cudaStream_t st) {
+        const int64_t cap = pma.g.capacity;
+        const int64_t nchunks = (cap + 32 * C - 1) / (32 * C);
+        const int64_t ns = nslots();
+        double* yslot = ws.yslot.ensure((size_t)ns + 1);
+        int32_t* ycnt = ws.ycnt.ensure((size_t)ns + 1);
+        double* carry = ws.carry.ensure((size_t)nchunks);
+        int32_t* ccnt = ws.carry_cnt.ensure((size_t)nchunks);
+        int32_t* clast = ws.chunk_last.ensure((size_t)nchunks);
+        const unsigned gr = grid_for(nchunks * 32, 256);
+        if (d_xmask) {
+            DSA_LAUNCH("spmv_blocked", (k_spmv_blocked<true, C>), gr, 256, 0, st, pma.keys.p, pma.vals.p, cap, d_x, d_xmask, nx, yslot, ycnt,
+                       carry, ccnt, clast, nchunks);
+            DSA_LAUNCH("spmv_fixup", k_spmv_fixup<true>, grid_for(nchunks, 256), 256, 0, st, yslot, ycnt, carry, ccnt, clast, nchunks);
+        } else {
+            DSA_LAUNCH("spmv_blocked", (k_spmv_blocked<false, C>), gr, 256, 0, st, pma.keys.p, pma.vals.p, cap, d_x, d_xmask, nx, yslot, ycnt,
+                       carry, ccnt, clast, nchunks);
+            DSA_LAUNCH("spmv_fixup", k_spmv_fixup<false>, grid_for(nchunks, 256), 256, 0, st, yslot, ycnt, carry, ccnt, clast, nchunks);
+        }
+    }
+    // SpMV; results by slot in ws.yslot / ws.ycnt
     void spmv_slots(PcsrWorkspace& ws, const double* d_x, const uint8_t* d_xmask, int64_t nx, cudaStream_t st) {
         static const int steps = [] {
             const char* e = getenv("DSA_SPMV_STEPS");
             return e ? atoi(e) : SPMV_STEPS_DEFAULT;
         }();
-        if (steps == 8) spmv_launch<8>(ws, d_x, d_xmask, nx, st);
+        static const int kind = [] {   // DSA_SPMV=flat: the round-1 kernel (strided cells, segmented scan per 32-cell step)
+            const char* e = getenv("DSA_SPMV");
+            if (e && std::string(e) == "flat") return 0;
+            if (e && std::string(e) == "blocked8") return 8;
+            return 4;
+        }();
+        if (kind == 4) spmv_launch_blocked<4>(ws, d_x, d_xmask, nx, st);
+        else if (kind == 8) spmv_launch_blocked<8>(ws, d_x, d_xmask, nx, st);
+        else if (steps == 8) spmv_launch<8>(ws, d_x, d_xmask, nx, st);
         else if (steps == 2) spmv_launch<2>(ws, d_x, d_xmask, nx, st);
         else spmv_launch<4>(ws, d_x, d_xmask, nx, st);
     }

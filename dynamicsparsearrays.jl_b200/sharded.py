@@ -116,6 +116,10 @@ class DistMatrix:
         self._h = C.c_void_p()
         check(lib().dsa_dmatrix_create(ctx._h, C.c_int64(self.m), C.c_int64(self.n), _hp(rs), _hp(cs), C.c_int64(int(max_share)),
                                        C.byref(self._h)))
+        # Work is enqueued on `stream` (a raw cudaStream_t).  Default: torch's current stream, so that torch tensors handed to
+        # set_batch / spmv and the results they read back are ordered with the library's kernels without extra synchronisation.
+        if stream is None and torch.cuda.is_available():
+            stream = torch.cuda.current_stream().cuda_stream
         if stream is not None:
             check(lib().dsa_dmatrix_set_stream(self._h, C.c_void_p(stream)))
 

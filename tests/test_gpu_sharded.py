@@ -26,6 +26,9 @@ def _launch(nproc, extra_env=None):
            "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "run_sharded_gpu.py")]
     r = subprocess.run(cmd, env=env, cwd=ROOT, timeout=900, capture_output=True, text=True)
     tail = (r.stdout[-3000:] + "\n" + r.stderr[-6000:])
+    if r.returncode != 0 and os.path.isdir(os.path.join(ROOT, "gpurun_out")):   # the whole worker output, for the post-mortem
+        with open(os.path.join(ROOT, "gpurun_out", f"sharded_worker_n{nproc}.log"), "w") as f:
+            f.write(r.stdout + "\n=====STDERR=====\n" + r.stderr)
     assert r.returncode == 0, tail
     assert f"sharded parity ok on {nproc} GPU(s)" in r.stdout, tail
     return r.stdout
