@@ -371,7 +371,7 @@ def main():
     peak, peak_src = measured_peak_gbs()
     spmv_alg_bytes = 16 * (inf["nnz"] + inf["nb_partitions"]) + 8 * (N_COLS + M_ROWS)
     spmv_phys_bytes = 16 * inf["capacity"] + 8 * (N_COLS + M_ROWS)
-    spmv_name = next((k for k in ("spmv_narrow", "spmv_flat") if k in kernels), "spmv_flat")
+    spmv_name = next((k for k in ("spmv_blocked", "spmv_flat") if k in kernels), "spmv_flat")
     spmv_us = kernels.get(spmv_name, {}).get("avg_us")
     spmv = None
     if spmv_us:

@@ -205,7 +205,7 @@ def main_dist(args, rank, world, local_rank):
         kernels[name] = {"launches_per_step": int(cnt) / 3, "ms_per_step": float(tms) / 3, "avg_us": 1e3 * float(tms) / int(cnt)}
     inf_local = A.local.info(1)
     spmv = None
-    spmv_name = next((k for k in ("spmv_narrow", "spmv_flat") if k in kernels), None)
+    spmv_name = next((k for k in ("spmv_blocked", "spmv_flat") if k in kernels), None)
     if spmv_name:
         us = kernels[spmv_name]["avg_us"]
         peak, src = B.measured_peak_gbs()

@@ -223,7 +223,11 @@ __global__ void __launch_bounds__(RT_THREADS) k_route_push(const int64_t* __rest
             dst[2 * region_cap] = __double_as_longlong(v_[j]);
         }
     }
-    __threadfence_system();
+    // One system-scope fence per CTA (cumulative over the CTA's stores through the barrier), not one per thread: a fence waits
+    // for the NVLink acknowledgements of the thread's outstanding peer stores, and 256 of them per CTA kept the CTAs resident
+    // for the round trip (75 us per launch at 2 GPUs).  Kernel completion + the count all-gather order the rest.
+    __syncthreads();
+    if (threadIdx.x == 0) __threadfence_system();
 }
 
 // counts[src * row_stride + o * world + dst] (all-gathered).  The receiver's dense arrays: ops of source 0 first, then source 1, ... (rank-major,

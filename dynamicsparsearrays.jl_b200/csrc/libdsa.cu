@@ -44,13 +44,14 @@ struct BatchCtx {
 
 static void phase1_launch(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t st) {
     int32_t* op_slot = ws.op_slot.ensure((size_t)c.n);
-    int64_t* cs = ws.cs.ensure(CS_WORDS);
     int64_t* hcs = ws.h_cs.ensure(CS_WORDS);
-    DSA_LAUNCH("colstat_init", k_colstat_init, 1, 1, 0, st, cs);
     const int64_t ns = P.nslots();
-    int32_t* bcnt = ws.bcnt.ensure((size_t)ns + 1);
+    // one block, one memset: [batch statistics (zero = neutral, pcsr.cuh cs_code)][per-partition bucket counters]
+    int32_t* blk = ws.bcnt.ensure((size_t)ns + 1 + 2 * CS_WORDS);
+    int64_t* cs = (int64_t*)blk;
+    int32_t* bcnt = blk + 2 * CS_WORDS;
     int32_t* lidx = ws.lidx.ensure((size_t)c.n);
-    DSA_CUDA(cudaMemsetAsync(bcnt, 0, ((size_t)ns + 1) * 4, st));
+    DSA_CUDA(cudaMemsetAsync(blk, 0, ((size_t)ns + 1 + 2 * CS_WORDS) * 4, st));
     DSA_LAUNCH("col_lookup", k_col_lookup, lookup_grid(c.n), 256, 0, st, c.partkeys, c.inkeys, c.vals, c.n, c.n_dev, P.d_live_keys.p,
                P.d_live_slot.p, P.nlive(), P.keymap(), P.keymap_min, P.keymap_len, op_slot, cs, bcnt, lidx);
     DSA_CUDA(cudaMemcpyAsync(hcs, cs, CS_WORDS * 8, cudaMemcpyDeviceToHost, st));
@@ -58,7 +59,8 @@ static void phase1_launch(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t 
 
 static void phase1_read(PcsrWorkspace& ws, BatchCtx& c) {
     const int64_t* hcs = ws.h_cs.p;
-    c.bs = BatchStats{hcs[CS_MISSING], hcs[CS_MINKEY], hcs[CS_MAXKEY], hcs[CS_MAXPART_NZ], hcs[CS_MAXKEY_NZ], hcs[CS_MINPART], hcs[CS_MAXBUCKET]};
+    c.bs = BatchStats{hcs[CS_MISSING], cs_min_decode(hcs[CS_MINKEY]), cs_max_decode(hcs[CS_MAXKEY]), cs_max_decode(hcs[CS_MAXPART_NZ]),
+                      cs_max_decode(hcs[CS_MAXKEY_NZ]), cs_min_decode(hcs[CS_MINPART]), hcs[CS_MAXBUCKET]};
     if (c.n_dev) {   // the count the kernels used is now known to the host: the remaining phases run on the exact size
         c.n = hcs[CS_N];
         c.n_dev = nullptr;
@@ -118,8 +120,7 @@ static void phase1_finish(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t 
         P.nb_partitions += (int64_t)distinct.size();
         P.rebuild_live_and_upload(st, &c.new_slots_h);
         // slots changed: look every op up again
-        int64_t* cs = ws.cs.ensure(CS_WORDS);
-        DSA_LAUNCH("colstat_init", k_colstat_init, 1, 1, 0, st, cs);
+        int64_t* cs = ws.cs.ensure(CS_WORDS);   // statistics were already taken
         DSA_LAUNCH("col_lookup", k_col_lookup, lookup_grid(n), 256, 0, st, c.partkeys, (const int64_t*)nullptr, (const double*)nullptr, n,
                    (const int64_t*)nullptr, P.d_live_keys.p, P.d_live_slot.p, P.nlive(), P.keymap(), P.keymap_min, P.keymap_len, ws.op_slot.p, cs,
                    (int32_t*)nullptr, (int32_t*)nullptr);
@@ -144,11 +145,16 @@ static void phase2_launch(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t 
         const int64_t ns = P.nslots();
         int32_t* boff = ws.boff.ensure((size_t)ns + 1);
         BucketRec* rec = ws.brec.ensure((size_t)n);
-        uint8_t* dead = ws.u_dead.ensure((size_t)n);
-        exclusive_scan_i32<int32_t>(ws.batch.scan, ws.bcnt.p, boff, ns, nullptr, st);
+        int32_t* bcnt = ws.bcnt.p + 2 * CS_WORDS;
+        exclusive_scan_i32<int32_t>(ws.batch.scan, bcnt, boff, ns, nullptr, st);
         DSA_LAUNCH("bucket_scatter", k_bucket_scatter, grt, 256, 0, st, ws.op_slot.p, ws.lidx.p, c.inkeys, n, boff, rec);
-        DSA_LAUNCH("bucket_rank", k_bucket_rank, grt, 256, 0, st, rec, boff, ws.bcnt.p, n, c.vals, u_pid, u_key, u_val, dead);
-        P.pma.apply_sorted_ops(ws.batch, u_pid, u_key, u_val, n, P.d_sem.p, P.d_next_slot.p, st, false, nullptr, /*launch_only=*/true, dead);
+        // rank inside the bucket + locate + overwrite in one kernel, then the shared tail (deletes, insert compaction, density tree)
+        P.pma.prepare_batch_scratch(ws.batch, n, st);
+        int32_t* f32 = ws.batch.flag32.ensure((size_t)n);
+        DSA_LAUNCH("bucket_rank_locate", k_bucket_rank_locate, grt, 256, 0, st, rec, boff, bcnt, n, c.vals, P.pma.keys.p, P.pma.vals.p,
+                   P.pma.g.capacity, P.d_sem.p, P.d_next_slot.p, u_key, u_val, ws.batch.op_pos.p, ws.batch.op_flag.p, f32);
+        P.pma.apply_located_ops<false>(ws.batch, u_key, u_val, n, st);
+        P.pma.rebalance_launch(ws.batch, st);
         return;
     }
     uint64_t* sk = ws.sk.ensure((size_t)ntot);

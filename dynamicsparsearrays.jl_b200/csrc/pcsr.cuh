@@ -15,15 +15,11 @@ namespace dsa {
 // ---------------------------------------------------------------------------------------------
 enum { CS_MISSING = 0, CS_MINKEY = 1, CS_MAXKEY = 2, CS_MAXPART_NZ = 3, CS_MAXKEY_NZ = 4, CS_MINPART = 5, CS_MAXBUCKET = 6, CS_N = 7, CS_WORDS = 8 };
 
-__global__ void k_colstat_init(int64_t* cs) {
-    cs[CS_MISSING] = 0;
-    cs[CS_MINKEY] = INT64_MAX;
-    cs[CS_MAXKEY] = INT64_MIN;
-    cs[CS_MAXPART_NZ] = INT64_MIN;
-    cs[CS_MAXKEY_NZ] = INT64_MIN;
-    cs[CS_MINPART] = INT64_MAX;
-    cs[CS_MAXBUCKET] = 0;
-}
+// The statistics block starts a batch as ZEROS (it shares the memset of the bucket counters): maxima are kept as
+// order-preserving unsigned codes (0 = "none yet" = INT64_MIN), minima as the complement of the code (0 = INT64_MAX).
+__host__ __device__ __forceinline__ unsigned long long cs_code(int64_t v) { return (unsigned long long)v ^ 0x8000000000000000ull; }
+__host__ __device__ __forceinline__ int64_t cs_max_decode(int64_t stored) { return (int64_t)((unsigned long long)stored ^ 0x8000000000000000ull); }
+__host__ __device__ __forceinline__ int64_t cs_min_decode(int64_t stored) { return (int64_t)(~(unsigned long long)stored ^ 0x8000000000000000ull); }
 
 // grid of the (grid-stride) column lookup: one op per thread up to 16 CTAs per SM of a 148-SM part, then strided
 inline unsigned lookup_grid(int64_t n) { return (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148 * 16)); }
@@ -111,13 +107,14 @@ __global__ void __launch_bounds__(256) k_col_lookup(const int64_t* __restrict__ 
             miss += shm[w];
             bmax = shb[w] > bmax ? shb[w] : bmax;
         }
+        unsigned long long* u = (unsigned long long*)cs;
         if (bmax) atomicMax((long long*)&cs[CS_MAXBUCKET], (long long)bmax);
-        if (miss) atomicAdd((unsigned long long*)&cs[CS_MISSING], (unsigned long long)miss);
-        if (mink != INT64_MAX) atomicMin((long long*)&cs[CS_MINKEY], (long long)mink);
-        if (maxk != INT64_MIN) atomicMax((long long*)&cs[CS_MAXKEY], (long long)maxk);
-        if (maxp != INT64_MIN) atomicMax((long long*)&cs[CS_MAXPART_NZ], (long long)maxp);
-        if (maxknz != INT64_MIN) atomicMax((long long*)&cs[CS_MAXKEY_NZ], (long long)maxknz);
-        if (minp != INT64_MAX) atomicMin((long long*)&cs[CS_MINPART], (long long)minp);
+        if (miss) atomicAdd(&u[CS_MISSING], (unsigned long long)miss);
+        if (mink != INT64_MAX) atomicMax(&u[CS_MINKEY], ~cs_code(mink));
+        if (maxk != INT64_MIN) atomicMax(&u[CS_MAXKEY], cs_code(maxk));
+        if (maxp != INT64_MIN) atomicMax(&u[CS_MAXPART_NZ], cs_code(maxp));
+        if (maxknz != INT64_MIN) atomicMax(&u[CS_MAXKEY_NZ], cs_code(maxknz));
+        if (minp != INT64_MAX) atomicMax(&u[CS_MINPART], ~cs_code(minp));
     }
 }
 
@@ -188,15 +185,22 @@ __global__ void __launch_bounds__(256) k_bucket_scatter(const int32_t* __restric
     const int64_t pos = (int64_t)boff[s] + lidx[i];
     rec[pos] = BucketRec{inkeys[i], (uint32_t)i, s};   // one 16 B store per op
 }
-// Every op ranks itself inside its bucket by (key, arrival) and lands, fully formed, at its sorted position; an op that is
-// followed by a later write to the same (partition, key) is marked dead (last writer wins) instead of being compacted away.
-__global__ void __launch_bounds__(256) k_bucket_rank(const BucketRec* __restrict__ rec, const int32_t* __restrict__ boff,
-                                                      const int32_t* __restrict__ bcnt, int64_t n, const double* __restrict__ vals,
-                                                      int32_t* __restrict__ u_pid, int64_t* __restrict__ u_key, double* __restrict__ u_val,
-                                                      uint8_t* __restrict__ u_dead) {
+// Every op ranks itself inside its bucket by (key, arrival) — its index in the batch's (partition, key, arrival) order — and is
+// LOCATED right there (K6, finds.jl:29-57 inside the partition span): the sorted op, its position, its flag and its insert flag
+// land at the sorted index.  An op followed by a later write to the same (partition, key) is dead (last writer wins).
+// Overwrites store their value at once (a search reads keys only); deletes are applied by k_apply_compact, after every op
+// of the batch has been located.
+__global__ void __launch_bounds__(256) k_bucket_rank_locate(const BucketRec* __restrict__ rec, const int32_t* __restrict__ boff,
+                                                             const int32_t* __restrict__ bcnt, int64_t n, const double* __restrict__ vals,
+                                                             const int64_t* __restrict__ keys, double* __restrict__ cell_vals, int64_t cap,
+                                                             const int64_t* __restrict__ sem, const int32_t* __restrict__ next_slot,
+                                                             int64_t* __restrict__ u_key, double* __restrict__ u_val,
+                                                             int64_t* __restrict__ op_pos, uint8_t* __restrict__ op_flag,
+                                                             int32_t* __restrict__ ins_flag) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const BucketRec me = rec[p];
+    const double val = vals[me.arr];
     const int64_t lo = boff[me.slot], hi = lo + bcnt[me.slot];
     int64_t r = lo;
     bool dead = false;
@@ -205,12 +209,18 @@ __global__ void __launch_bounds__(256) k_bucket_rank(const BucketRec* __restrict
         r += (o.key < me.key) || (o.key == me.key && o.arr < me.arr);
         dead |= (o.key == me.key && o.arr > me.arr);
     }
-    u_pid[r] = me.slot;
-    u_key[r] = me.key;
-    u_val[r] = vals[me.arr];
-    u_dead[r] = dead ? 1 : 0;
+    uint8_t f = 0;
+    if (!dead) {
+        int64_t pos;
+        f = locate_one(keys, cap, true, me.slot, me.key, val != 0.0, sem, next_slot, &pos);
+        op_pos[r] = pos;
+        if (f == FL_OVERWRITE) cell_vals[pos] = val;   // writes.jl:16-19
+        u_key[r] = me.key;
+        u_val[r] = val;
+    }
+    op_flag[r] = f;
+    ins_flag[r] = f == FL_INSERT ? 1 : 0;
 }
-
 
 // plain PMA: sort key = key - min
 __global__ void __launch_bounds__(256) k_make_sortkeys_vec(const int64_t* __restrict__ keys, int64_t n, int64_t mink,
@@ -339,160 +349,24 @@ __global__ void __launch_bounds__(256) k_clear_sems(int64_t* __restrict__ sem, c
 }
 
 // ---------------------------------------------------------------------------------------------
-// K7 SpMV over the gapped array — flat, cell-parallel, deterministic.
+// K7 SpMV over the gapped array — cell-parallel, deterministic.
 // y[key(partition)] = sum over the partition's cells of x[cell key] * cell value, cells in ascending key order, i.e. the
 // per-output summation order of _mul_dyn_mat_col_loop! (operations.jl:97-103) when the twin orientation is scanned.
-// A warp streams a chunk of SPMV_CHUNK consecutive cells (coalesced 8 B lanes for keys and values), does a segmented
-// scan with the semaphore cells as in-band segment heads, writes every partition that ends inside the chunk, and leaves
-// (a) the partial of the cells before its first head in carry[chunk] and (b) the open partial of its last partition in y.
-// k_spmv_fixup then adds, per chunk with a head, the carries of the following head-less chunks in chunk order.
-// No atomics: the result is bit-reproducible.  mul and add are separate roundings (no FMA), as in the reference.
+// A warp streams a chunk of consecutive cells, does a segmented reduction with the semaphore cells as in-band segment heads,
+// writes every partition that ends inside the chunk, and leaves (a) the partial of the cells before its first head in
+// carry[chunk] and (b) the open partial of its last partition in y.  k_spmv_fixup then adds, per chunk with a head, the
+// carries of the following head-less chunks in chunk order.  No atomics: the result is bit-reproducible.  mul and add are
+// separate roundings (no FMA), as in the reference.
 // ---------------------------------------------------------------------------------------------
-constexpr int SPMV_STEPS_DEFAULT = 4;   // 32-cell steps per warp chunk (4 keeps the kernel at 48 warps/SM; see profiles/)
-
-__device__ __forceinline__ double warp_sum_f64(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-__device__ __forceinline__ int warp_sum_i32(int v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-template <bool SPARSE_X, int SPMV_STEPS>
-__global__ void __launch_bounds__(256) k_spmv_flat(const int64_t* __restrict__ keys, const double* __restrict__ vals, int64_t cap,
-                                                    const double* __restrict__ x, const uint8_t* __restrict__ xmask, int64_t nx,
-                                                    double* __restrict__ yslot, int32_t* __restrict__ ycnt,
-                                                    double* __restrict__ carry, int32_t* __restrict__ carry_cnt,
-                                                    int32_t* __restrict__ chunk_last_slot, int64_t nchunks) {
-    const int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (chunk >= nchunks) return;
-    const unsigned lt = lanemask_lt();
-    constexpr int SPMV_CHUNK = 32 * SPMV_STEPS;
-    const int64_t base = chunk * SPMV_CHUNK;
-    // all loads of the chunk in flight together: 8 x (key, value), then 8 independent gathers of x
-    int64_t k[SPMV_STEPS];
-    double t[SPMV_STEPS];
-    int32_t tc[SPMV_STEPS];
-#pragma unroll
-    for (int s = 0; s < SPMV_STEPS; ++s) {
-        const int64_t p = base + s * 32 + lane;
-        k[s] = GAP_KEY;
-        t[s] = 0.0;
-        if (p < cap) {   // streamed once: evict-first, so the array does not push x out of L1/L2
-            k[s] = __ldcs(keys + p);
-            t[s] = __ldcs(vals + p);
-        }
-    }
-#pragma unroll
-    for (int s = 0; s < SPMV_STEPS; ++s) {
-        tc[s] = 0;
-        const int64_t kk = k[s];
-        if (kk > 0) {   // element: t = x[key] * value (separate rounding, operations.jl:101)
-            double xv = 0.0;
-            bool present = kk <= nx;
-            if (SPARSE_X) present = present && xmask[kk - 1] != 0;
-            if (present) {
-                xv = __ldg(x + (kk - 1));
-                tc[s] = 1;
-            }
-            t[s] = present ? __dmul_rn(xv, t[s]) : 0.0;
-        } else if (kk != 0) {
-            t[s] = 0.0;   // gap
-        }
-        // heads keep their value (partition id) in t[s]
-    }
-    int32_t cur_slot = -1;    // open partition (uniform across the warp)
-    double acc = 0.0;         // its partial up to the last head-carrying step
-    int32_t acc_cnt = 0;
-    double lacc = 0.0;        // per-lane partial of the open partition over head-less steps
-    int32_t lcnt = 0;
-    bool prefix_open = true;  // no head seen yet in this chunk
-#pragma unroll
-    for (int s = 0; s < SPMV_STEPS; ++s) {
-        const bool head = k[s] == 0;
-        const unsigned hb = __ballot_sync(0xffffffffu, head);
-        if (hb == 0) {   // common case (rows longer than a step): no shuffles at all
-            lacc = __dadd_rn(lacc, t[s]);
-            lcnt += tc[s];
-            continue;
-        }
-        // fold the lane partials into the open partition, then a segmented scan over this step
-        acc = __dadd_rn(acc, warp_sum_f64(lacc));
-        acc_cnt += warp_sum_i32(lcnt);
-        lacc = 0.0;
-        lcnt = 0;
-        const double tv = head ? 0.0 : t[s];
-        const unsigned hle = hb & (lt | (1u << lane));
-        const int seg_lo = hle ? 31 - __clz(hle) : 0;
-        double st = tv;
-        int32_t sc = tc[s];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const double ot = __shfl_up_sync(0xffffffffu, st, o);
-            const int32_t oc = __shfl_up_sync(0xffffffffu, sc, o);
-            if (lane >= o && lane - o >= seg_lo) {
-                st = __dadd_rn(ot, st);
-                sc += oc;
-            }
-        }
-        // every head closes the partition that was open before it
-        const double prev_t = __shfl_up_sync(0xffffffffu, st, 1);
-        const int32_t prev_c = __shfl_up_sync(0xffffffffu, sc, 1);
-        const unsigned hlt = hb & lt;
-        const int prev_head_lane = hlt ? 31 - __clz(hlt) : -1;
-        const int32_t my_slot = head ? (int32_t)t[s] - 1 : -1;
-        const int32_t prev_head_slot = __shfl_sync(0xffffffffu, my_slot, prev_head_lane < 0 ? 0 : prev_head_lane);
-        if (head) {
-            double tot = lane > 0 ? prev_t : 0.0;
-            int32_t totc = lane > 0 ? prev_c : 0;
-            if (prev_head_lane < 0) {   // the closing partition started before this step
-                tot = lane > 0 ? __dadd_rn(acc, tot) : acc;
-                totc += acc_cnt;
-                if (cur_slot >= 0) {
-                    yslot[cur_slot] = tot;
-                    ycnt[cur_slot] = totc;
-                } else if (prefix_open) {
-                    carry[chunk] = tot;
-                    carry_cnt[chunk] = totc;
-                }
-            } else {
-                yslot[prev_head_slot] = tot;
-                ycnt[prev_head_slot] = totc;
-            }
-        }
-        // the segment open at lane 31 carries into the next step
-        const int last_head_lane = 31 - __clz(hb);
-        cur_slot = __shfl_sync(0xffffffffu, my_slot, last_head_lane);
-        acc = __shfl_sync(0xffffffffu, st, 31);
-        acc_cnt = __shfl_sync(0xffffffffu, sc, 31);
-        prefix_open = false;
-    }
-    acc = __dadd_rn(acc, warp_sum_f64(lacc));
-    acc_cnt += warp_sum_i32(lcnt);
-    if (lane == 0) {
-        if (cur_slot >= 0) {   // open partition at the end of the chunk: partial, completed by the fix-up
-            yslot[cur_slot] = acc;
-            ycnt[cur_slot] = acc_cnt;
-        } else {               // no head in the whole chunk
-            carry[chunk] = acc;
-            carry_cnt[chunk] = acc_cnt;
-        }
-        chunk_last_slot[chunk] = cur_slot;
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
-// K7, blocked variant (the default): every lane owns C CONTIGUOUS cells (one 256-bit load of keys, one of values, both
-// L1::no_allocate so that x keeps the L1), reduces them sequentially — heads inside the lane close their partition in
-// registers — and the warp then needs ONE segmented scan over the 32 lane aggregates per chunk, whatever the number of heads.
-// k_spmv_flat pays ~40 shuffles per 32-cell step that contains a head (77 % of the chunks at config 2) and ran at 86 us where
-// the same loads + gathers without the reduction take 50 us (profiles/gather_probe.cu); this one needs 13 shuffles per
-// 32*C cells.  Same carry / fix-up protocol and the same per-partition order (ascending cells); the association differs
-// (sequential inside a lane, tree across lanes), within the 1e-12 bar and exact for integer-valued data.
+// Every lane owns C CONTIGUOUS cells (one 256-bit load of keys, one of values, both L1::no_allocate so that x keeps the L1),
+// reduces them sequentially — heads inside the lane close their partition in registers — and the warp then needs ONE
+// segmented scan over the 32 lane aggregates per chunk, whatever the number of heads (13 shuffles per 32*C cells; round 1's
+// strided kernel paid ~40 per 32-cell step with a head and ran at 83 us on the same data, profiles/gather_probe.cu).
+// The C gathers of x are UNCONDITIONAL loads (gap / head lanes read x[0]): a gather under a data-dependent branch is followed
+// by a reconvergence point, which serialised the four L2 round trips of a lane (73 us -> see profiles/).
+// Per-partition order = ascending cells; association: sequential inside a lane, tree across lanes (within the 1e-12 bar,
+// exact for integer-valued data).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void ldg_stream4(const int64_t* p, int64_t& a, int64_t& b, int64_t& c, int64_t& d) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.s64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
@@ -529,21 +403,31 @@ __global__ void __launch_bounds__(256) k_spmv_blocked(const int64_t* __restrict_
             }
         }
     }
-    // the C gathers of x are independent: all in flight together.  t = x[key] * value (separate rounding, operations.jl:101);
-    // heads keep their value (the partition id) in t
+    // the C gathers of x: independent, branch-free, all in flight together.  t = x[key] * value (separate rounding,
+    // operations.jl:101); heads keep their value (the partition id) in t
+    double xv[C];
+    uint8_t xm[C];
     int tcn[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        tcn[c] = 0;
-        const int64_t kk = k[c];
-        if (kk > 0) {
-            bool present = kk <= nx;
-            if (SPARSE_X) present = present && xmask[kk - 1] != 0;
-            double xv = 0.0;
-            if (present) xv = __ldg(x + (kk - 1));
-            t[c] = present ? __dmul_rn(xv, t[c]) : 0.0;
-            tcn[c] = present ? 1 : 0;
+        xv[c] = 0.0;
+        xm[c] = 1;
+    }
+    if (nx > 0) {   // warp-uniform
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int64_t kk = k[c];
+            const int64_t idx = (kk > 0 && kk <= nx) ? kk - 1 : 0;
+            xv[c] = __ldg(x + idx);
+            if (SPARSE_X) xm[c] = __ldg(xmask + idx);
         }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const int64_t kk = k[c];
+        const bool present = kk > 0 && kk <= nx && xm[c] != 0;
+        tcn[c] = present ? 1 : 0;
+        if (kk > 0) t[c] = present ? __dmul_rn(xv[c], t[c]) : 0.0;
     }
     // sequential reduction of the lane's cells
     double run = 0.0, pre = 0.0;   // run: sum since the lane's last head (or lane start); pre: cells before its first head
@@ -790,8 +674,7 @@ struct Pcsr {
     void get_batch_d(PcsrWorkspace& ws, const int64_t* d_inkeys, const int64_t* d_partkeys, int64_t n, double* d_out, cudaStream_t st) {
         if (n <= 0) return;
         int32_t* op_slot = ws.op_slot.ensure((size_t)n);
-        int64_t* cs = ws.cs.ensure(CS_WORDS);
-        DSA_LAUNCH("colstat_init", k_colstat_init, 1, 1, 0, st, cs);
+        int64_t* cs = ws.cs.ensure(CS_WORDS);   // statistics are not used by reads
         DSA_LAUNCH("col_lookup", k_col_lookup, lookup_grid(n), 256, 0, st, d_partkeys, (const int64_t*)nullptr, (const double*)nullptr, n,
                    (const int64_t*)nullptr, d_live_keys.p, d_live_slot.p, nlive(), keymap(), keymap_min, keymap_len, op_slot, cs, (int32_t*)nullptr, (int32_t*)nullptr);
         DSA_LAUNCH("get", k_get, grid_for(n, 256), 256, 0, st, pma.keys.p, pma.vals.p, pma.g.capacity, op_slot, d_inkeys, n, d_sem.p,
@@ -833,27 +716,7 @@ struct Pcsr {
         rebuild_live_and_upload(st);
     }
 
-    // flat SpMV; results by slot in ws.yslot / ws.ycnt
-    template <int STEPS>
-    void spmv_launch(PcsrWorkspace& ws, const double* d_x, const uint8_t* d_xmask, int64_t nx, cudaStream_t st) {
-        const int64_t cap = pma.g.capacity;
-        const int64_t nchunks = (cap + 32 * STEPS - 1) / (32 * STEPS);
-        const int64_t ns = nslots();
-        double* yslot = ws.yslot.ensure((size_t)ns + 1);
-        int32_t* ycnt = ws.ycnt.ensure((size_t)ns + 1);
-        double* carry = ws.carry.ensure((size_t)nchunks);
-        int32_t* ccnt = ws.carry_cnt.ensure((size_t)nchunks);
-        int32_t* clast = ws.chunk_last.ensure((size_t)nchunks);
-        const unsigned gr = grid_for(nchunks * 32, 256);
-        if (d_xmask)
-            DSA_LAUNCH("spmv_flat", (k_spmv_flat<true, STEPS>), gr, 256, 0, st, pma.keys.p, pma.vals.p, cap, d_x, d_xmask, nx, yslot, ycnt,
-                       carry, ccnt, clast, nchunks);
-        else
-            DSA_LAUNCH("spmv_flat", (k_spmv_flat<false, STEPS>), gr, 256, 0, st, pma.keys.p, pma.vals.p, cap, d_x, d_xmask, nx, yslot, ycnt,
-                       carry, ccnt, clast, nchunks);
-        DSA_LAUNCH("spmv_fixup", k_spmv_fixup<true>, grid_for(nchunks, 256), 256, 0, st, yslot, ycnt, carry, ccnt, clast, nchunks);
-    }
-    // blocked SpMV (default).  Dense x: the product counts (only the sparse output needs them) are not computed.
+    // Dense x: the product counts (only the sparse output needs them) are not computed.
     template <int C>
     void spmv_launch_blocked(PcsrWorkspace& ws, const double* d_x, const uint8_t* d_xmask, int64_t nx, cudaStream_t st) {
         const int64_t cap = pma.g.capacity;
@@ -877,21 +740,7 @@ struct Pcsr {
     }
     // SpMV; results by slot in ws.yslot / ws.ycnt
     void spmv_slots(PcsrWorkspace& ws, const double* d_x, const uint8_t* d_xmask, int64_t nx, cudaStream_t st) {
-        static const int steps = [] {
-            const char* e = getenv("DSA_SPMV_STEPS");
-            return e ? atoi(e) : SPMV_STEPS_DEFAULT;
-        }();
-        static const int kind = [] {   // DSA_SPMV=flat: the round-1 kernel (strided cells, segmented scan per 32-cell step)
-            const char* e = getenv("DSA_SPMV");
-            if (e && std::string(e) == "flat") return 0;
-            if (e && std::string(e) == "blocked8") return 8;
-            return 4;
-        }();
-        if (kind == 4) spmv_launch_blocked<4>(ws, d_x, d_xmask, nx, st);
-        else if (kind == 8) spmv_launch_blocked<8>(ws, d_x, d_xmask, nx, st);
-        else if (steps == 8) spmv_launch<8>(ws, d_x, d_xmask, nx, st);
-        else if (steps == 2) spmv_launch<2>(ws, d_x, d_xmask, nx, st);
-        else spmv_launch<4>(ws, d_x, d_xmask, nx, st);
+        spmv_launch_blocked<4>(ws, d_x, d_xmask, nx, st);
     }
 
     void clone_from(const Pcsr& o, cudaStream_t st) {

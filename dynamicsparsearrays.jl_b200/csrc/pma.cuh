@@ -27,7 +27,8 @@ struct Levels {
 constexpr int SMALL_CELLS = 2048;
 
 enum : uint8_t { FL_OVERWRITE = 1, FL_DELETE = 2, FL_INSERT = 4 };
-enum { ST_OVER = 0, ST_UNDER = 1, ST_NINS = 2, ST_ROOT = 3, ST_NHIGH = 4, ST_ANYBIG = 5, ST_NACT = 6, ST_ANYHIGH = 7, ST_WORDS = 16 };
+enum { ST_OVER = 0, ST_UNDER = 1, ST_NINS = 2, ST_ROOT = 3, ST_NHIGH = 4, ST_ANYBIG = 5, ST_NACT = 6, ST_ANYHIGH = 7, ST_TICKET = 8, ST_NPEND = 9,
+       ST_WORDS = 16 };
 
 __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;
@@ -121,23 +122,13 @@ __device__ __forceinline__ int64_t span_end(const int64_t* __restrict__ sem, con
 // Locate every (sorted, unique) op.  pid == nullptr: plain PMA, search the whole array.  Otherwise the partition span is
 // [sem[pid], next_sem[pid]) and, like pcsr.jl:305-307, inserts search (sem, end] while deletes search [sem, end].
 // sem[pid] < 0 marks a partition created by this batch: everything goes right before the next live semaphore.
-__global__ void __launch_bounds__(256) k_locate(const int64_t* __restrict__ keys, int64_t cap, const int32_t* __restrict__ op_pid,
-                                                 const int64_t* __restrict__ op_key, const double* __restrict__ op_val, int64_t nops,
-                                                 const int64_t* __restrict__ sem, const int32_t* __restrict__ next_slot,
-                                                 int64_t* __restrict__ op_pos, uint8_t* __restrict__ op_flag,
-                                                 const int64_t* __restrict__ n_dev, const uint8_t* __restrict__ op_dead) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (n_dev ? *n_dev : nops)) return;
-    if (op_dead && op_dead[i]) {   // overwritten by a later op of the same batch (last writer wins)
-        op_flag[i] = 0;
-        return;
-    }
-    const int64_t key = op_key[i];
-    const bool is_set = op_val[i] != 0.0;   // pma.jl:197, pcsr.jl:301
+// one op: position of the hit or of the predecessor, and what the op turns into
+__device__ __forceinline__ uint8_t locate_one(const int64_t* __restrict__ keys, int64_t cap, bool partitioned, int32_t pid, int64_t key,
+                                              bool is_set, const int64_t* __restrict__ sem, const int32_t* __restrict__ next_slot,
+                                              int64_t* pos_out) {
     int64_t pos;
     bool hit = false;
-    if (op_pid) {
-        const int32_t pid = op_pid[i];
+    if (partitioned) {
         const int64_t s = sem[pid];
         const int64_t e = span_end(sem, next_slot, pid, cap);
         if (s < 0 || key == 0) {
@@ -148,8 +139,29 @@ __global__ void __launch_bounds__(256) k_locate(const int64_t* __restrict__ keys
     } else {
         pos = gapped_find(keys, key, 0, cap - 1, &hit);
     }
+    *pos_out = pos;
+    return hit ? (is_set ? FL_OVERWRITE : FL_DELETE) : ((is_set || (partitioned && key == 0)) ? FL_INSERT : 0);
+}
+
+__global__ void __launch_bounds__(256) k_locate(const int64_t* __restrict__ keys, int64_t cap, const int32_t* __restrict__ op_pid,
+                                                 const int64_t* __restrict__ op_key, const double* __restrict__ op_val, int64_t nops,
+                                                 const int64_t* __restrict__ sem, const int32_t* __restrict__ next_slot,
+                                                 int64_t* __restrict__ op_pos, uint8_t* __restrict__ op_flag,
+                                                 const int64_t* __restrict__ n_dev, const uint8_t* __restrict__ op_dead,
+                                                 int32_t* __restrict__ ins_flag) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nops) return;
+    if (i >= (n_dev ? *n_dev : nops) || (op_dead && op_dead[i])) {   // beyond the unique ops / overwritten by a later op of the batch
+        op_flag[i] = 0;
+        ins_flag[i] = 0;
+        return;
+    }
+    int64_t pos;
+    const uint8_t f = locate_one(keys, cap, op_pid != nullptr, op_pid ? op_pid[i] : 0, op_key[i], op_val[i] != 0.0 /* pma.jl:197, pcsr.jl:301 */,
+                                 sem, next_slot, &pos);
     op_pos[i] = pos;
-    op_flag[i] = hit ? (is_set ? FL_OVERWRITE : FL_DELETE) : ((is_set || (op_pid && key == 0)) ? FL_INSERT : 0);
+    op_flag[i] = f;
+    ins_flag[i] = f == FL_INSERT ? 1 : 0;
 }
 
 // batched getindex (pma.jl:189-193 / pcsr.jl:228-232): value or 0.0.  pid < 0 = column absent (pcsr.jl:263-265).
@@ -170,48 +182,34 @@ __global__ void __launch_bounds__(256) k_get(const int64_t* __restrict__ keys, c
     out[i] = hit ? vals[pos] : 0.0;
 }
 
-// hits: overwrite in place (writes.jl:16-19) or blank the cell (writes.jl:65-68); misses with a value become inserts
-__global__ void __launch_bounds__(256) k_apply_hits(int64_t* __restrict__ keys, double* __restrict__ vals,
-                                                     const int64_t* __restrict__ op_pos, const uint8_t* __restrict__ op_flag,
-                                                     const double* __restrict__ op_val, int64_t nops, int32_t* __restrict__ leafcnt,
-                                                     uint8_t* __restrict__ touched, int lgS, const int64_t* __restrict__ n_dev,
-                                                     int32_t* __restrict__ ins_flag) {
+// Located ops -> effects, one kernel: hits overwrite in place (writes.jl:16-19) or blank the cell (writes.jl:65-68; leaf count
+// and touched flag follow); misses with a value are compacted, order-preserving, into the insert arrays (ins_idx = exclusive
+// scan of the insert flags).  Runs after ALL ops are located: a delete must not change what another op's search sees.
+// OVERWRITES = false when the locating kernel already stored the new values (bucket path).
+template <bool OVERWRITES>
+__global__ void __launch_bounds__(256) k_apply_compact(int64_t* __restrict__ keys, double* __restrict__ vals,
+                                                        const int64_t* __restrict__ op_key, const double* __restrict__ op_val,
+                                                        const int64_t* __restrict__ op_pos, const uint8_t* __restrict__ op_flag,
+                                                        const int32_t* __restrict__ ins_idx, int64_t nops, int32_t* __restrict__ leafcnt,
+                                                        uint8_t* __restrict__ touched, int lgS, int64_t* __restrict__ ins_key,
+                                                        double* __restrict__ ins_val, int64_t* __restrict__ ins_pos) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nops) return;
-    if (i >= (n_dev ? *n_dev : nops)) {
-        ins_flag[i] = 0;
-        return;
-    }
     const uint8_t f = op_flag[i];
-    ins_flag[i] = f == FL_INSERT ? 1 : 0;
-    if (f == FL_OVERWRITE) {
-        vals[op_pos[i]] = op_val[i];
+    if (f == 0) return;
+    const int64_t p = op_pos[i];
+    if (f == FL_INSERT) {
+        const int32_t j = ins_idx[i];
+        ins_key[j] = op_key[i];
+        ins_val[j] = op_val[i];
+        ins_pos[j] = p;
     } else if (f == FL_DELETE) {
-        const int64_t p = op_pos[i];
         keys[p] = GAP_KEY;   // the value of a gap cell is never read (exports and SpMV mask by the key)
         atomicSub(&leafcnt[p >> lgS], 1);
         touched[p >> lgS] = 1;
+    } else if (OVERWRITES) {
+        vals[p] = op_val[i];
     }
-}
-
-// order-preserving compaction of the inserts (ins_idx = exclusive scan of the insert flags)
-__global__ void __launch_bounds__(256) k_flag_eq(const uint8_t* __restrict__ f, int64_t n, uint8_t what, int32_t* __restrict__ out,
-                                                  const int64_t* __restrict__ n_dev) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (i < (n_dev ? *n_dev : n) && f[i] == what) ? 1 : 0;
-}
-__global__ void __launch_bounds__(256) k_compact_inserts(const int64_t* __restrict__ op_key, const double* __restrict__ op_val,
-                                                          const int64_t* __restrict__ op_pos, const uint8_t* __restrict__ op_flag,
-                                                          const int32_t* __restrict__ ins_idx, int64_t nops,
-                                                          int64_t* __restrict__ ins_key, double* __restrict__ ins_val,
-                                                          int64_t* __restrict__ ins_pos, const int64_t* __restrict__ n_dev) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (n_dev ? *n_dev : nops)) return;
-    if (op_flag[i] != FL_INSERT) return;
-    const int32_t j = ins_idx[i];
-    ins_key[j] = op_key[i];
-    ins_val[j] = op_val[i];
-    ins_pos[j] = op_pos[i];
 }
 // per-leaf bookkeeping of the compacted inserts: every new key belongs to the leaf of its predecessor cell; inserts are
 // sorted, so the inserts of one leaf are contiguous.  The thread of the FIRST insert of a leaf counts the run and records
@@ -250,16 +248,30 @@ __global__ void __launch_bounds__(256) k_insert_leaf_info(const int64_t* __restr
 
 
 // ---------------------------------------------------------------------------------------------
-// K3 density tree: post[0][l] = leafcnt[l] + inscnt[l]; 10 levels per block in shared memory, upper levels by one block
+// K3 density tree + window pick (_look_for_rebalance!, pma.jl:105-141, for every touched leaf at once).
+//   k_tree_low      post[0][l] = leafcnt[l] + inscnt[l]; 10 levels per CTA in shared memory; the LAST CTA to finish (ticket)
+//                   sums the upper levels.  In the same pass every touched leaf takes the walk's first step: accepted at its own
+//                   level (the common case: pma.jl:120-123 with h = 0) -> marked on the spot; otherwise queued.
+//   k_select_pending  the queued leaves continue leaf -> root and mark the first window inside its density bounds.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_tree_low(const int32_t* __restrict__ leafcnt, const int32_t* __restrict__ inscnt,
-                                                    int32_t* __restrict__ post, Levels L) {
+                                                    int32_t* __restrict__ post, Levels L, const uint8_t* __restrict__ touched,
+                                                    uint8_t* __restrict__ mark, int64_t* __restrict__ status, int32_t* __restrict__ pending) {
     __shared__ int32_t s[1024];
+    __shared__ int is_last;
     const int64_t idx = (int64_t)blockIdx.x * 1024 + threadIdx.x;
     int32_t v = 0;
     if (idx < L.nsegs) {
         v = leafcnt[idx] + (inscnt ? inscnt[idx] : 0);
         post[L.off[0] + idx] = v;
+        if (touched[idx]) {
+            if (L.mn[0] <= v && v <= L.mx[0]) {
+                mark[L.off[0] + idx] = 1;
+            } else {
+                const unsigned long long slot = atomicAdd((unsigned long long*)&status[ST_NPEND], 1ull);
+                pending[slot] = (int32_t)idx;
+            }
+        }
     }
     s[threadIdx.x] = v;
     __syncthreads();
@@ -276,30 +288,33 @@ __global__ void __launch_bounds__(1024) k_tree_low(const int32_t* __restrict__ l
         }
         __syncthreads();
     }
-}
-__global__ void __launch_bounds__(1024) k_tree_high(int32_t* __restrict__ post, Levels L) {
+    if (L.H <= 10) return;
+    // upper levels: by the last CTA to get here (its predecessors' level-10 sums are visible: fence + ticket)
+    __threadfence();
+    if (threadIdx.x == 0) is_last = atomicAdd((unsigned long long*)&status[ST_TICKET], 1ull) == (unsigned long long)gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
     for (int k = 11; k <= L.H; ++k) {
         const int64_t nodes = L.nsegs >> k;
         for (int64_t i = threadIdx.x; i < nodes; i += 1024)
-            post[L.off[k] + i] = post[L.off[k - 1] + 2 * i] + post[L.off[k - 1] + 2 * i + 1];
+            post[L.off[k] + i] = __ldcg(&post[L.off[k - 1] + 2 * i]) + __ldcg(&post[L.off[k - 1] + 2 * i + 1]);
         __syncthreads();
     }
 }
 
-// every touched leaf walks leaf -> root and marks the first window inside its density bounds (pma.jl:113-129).
-// Windows above leaf level are also appended (once) to a work list.
-__global__ void __launch_bounds__(256) k_select_windows(const uint8_t* __restrict__ touched, const int32_t* __restrict__ post,
+// the queued leaves walk on, from level 1 (pma.jl:113-129).  Windows above leaf level are also appended (once) to a work list.
+__global__ void __launch_bounds__(256) k_select_pending(const int32_t* __restrict__ pending, const int32_t* __restrict__ post,
                                                          uint8_t* __restrict__ mark, Levels L, int64_t* __restrict__ status,
                                                          int32_t* __restrict__ hi_h, int64_t* __restrict__ hi_w) {
-    const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= L.nsegs || !touched[l]) return;
-    for (int h = 0; h <= L.H; ++h) {
-        const int64_t c = post[L.off[h] + (l >> h)];
-        if (L.mn[h] <= c && c <= L.mx[h]) {
-            const int64_t idx = L.off[h] + (l >> h);
-            if (h == 0) {
-                mark[idx] = 1;
-            } else {
+    const int64_t npend = status[ST_NPEND];
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < npend; q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t l = pending[q];
+        bool done = false;
+        for (int h = 1; h <= L.H && !done; ++h) {
+            const int64_t c = post[L.off[h] + (l >> h)];
+            if (L.mn[h] <= c && c <= L.mx[h]) {
+                const int64_t idx = L.off[h] + (l >> h);
                 unsigned* word = (unsigned*)(mark + (idx & ~(int64_t)3));
                 const unsigned bit = 1u << (8 * (unsigned)(idx & 3));
                 const unsigned old = atomicOr(word, bit);
@@ -310,13 +325,16 @@ __global__ void __launch_bounds__(256) k_select_windows(const uint8_t* __restric
                     status[ST_ANYHIGH] = 1;
                     if (h > L.hsmall) status[ST_ANYBIG] = 1;
                 }
+                done = true;
             }
-            return;
+        }
+        if (!done) {
+            const int64_t c = post[L.off[L.H]];
+            if (c > L.mx[L.H]) status[ST_OVER] = 1;   // density > t  -> _extend!  (pma.jl:132-134)
+            else status[ST_UNDER] = 1;                // density < p  -> _shrink!  (pma.jl:135-139)
         }
     }
-    const int64_t c = post[L.off[L.H]];
-    if (c > L.mx[L.H]) status[ST_OVER] = 1;   // density > t  -> _extend!  (pma.jl:132-134)
-    else status[ST_UNDER] = 1;                // density < p  -> _shrink!  (pma.jl:135-139)
+    if (blockIdx.x == 0 && threadIdx.x == 0) status[ST_ROOT] = post[L.off[L.H]];   // element count after the batch
 }
 
 // one CTA per listed window: outermost (no marked ancestor)?  then its leaves are covered by it
@@ -748,7 +766,7 @@ struct BatchWorkspace {   // per-handle scratch reused by every batch
     DBuf<int32_t> ins_idx, flag32;
     DBuf<int64_t> ins_key, ins_pos;
     DBuf<double> ins_val;
-    DBuf<int32_t> ins_first, post;
+    DBuf<int32_t> ins_first, post, pending;
     DBuf<uint8_t> hi_max;
     // everything that must start a batch as zero lives in ONE block cleared by one memset:
     DBuf<uint8_t> zero_blk;
@@ -854,11 +872,9 @@ struct PmaCore {
         int32_t* hi_h = ws.hi_h.ensure((size_t)nsegs + 1);
         int64_t* hi_w = ws.hi_w.ensure((size_t)nsegs + 1);
         ws.hi_max.ensure((size_t)nsegs + 1);
-        DSA_LAUNCH("tree_low", k_tree_low, grid_for(nsegs, 1024), 1024, 0, st, leafcnt.p, ws.inscnt, post, L);
-        if (L.H > 10) DSA_LAUNCH("tree_high", k_tree_high, 1, 1024, 0, st, post, L);
-        DSA_LAUNCH("select_windows", k_select_windows, grid_for(nsegs, 256), 256, 0, st, ws.touched, post, mark, L, status, hi_h, hi_w);
-        // status[ST_ROOT] <- root count
-        DSA_CUDA(cudaMemcpyAsync(status + ST_ROOT, post + L.off[L.H], sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        int32_t* pending = ws.pending.ensure((size_t)nsegs + 1);
+        DSA_LAUNCH("tree_low", k_tree_low, grid_for(nsegs, 1024), 1024, 0, st, leafcnt.p, ws.inscnt, post, L, ws.touched, mark, status, pending);
+        DSA_LAUNCH("select_pending", k_select_pending, 148, 256, 0, st, pending, post, mark, L, status, hi_h, hi_w);
         int64_t* hs = ws.h_status.ensure(ST_WORDS);
         DSA_CUDA(cudaMemcpyAsync(hs, status, ST_WORDS * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     }
@@ -959,26 +975,32 @@ struct PmaCore {
                           int64_t* d_sem, const int32_t* d_next_slot, cudaStream_t st, bool scratch_ready = false,
                           const int64_t* n_dev = nullptr, bool launch_only = false, const uint8_t* op_dead = nullptr) {
         if (!scratch_ready) prepare_batch_scratch(ws, nops, st);
-        const int lgS = ilog2_i64(g.segment_capacity);
         if (nops > 0) {
             const unsigned gr = grid_for(nops, 256);
-            DSA_LAUNCH("locate", k_locate, gr, 256, 0, st, keys.p, g.capacity, op_pid, op_key, op_val, nops, d_sem, d_next_slot,
-                       ws.op_pos.p, ws.op_flag.p, n_dev, op_dead);
-            // hits are applied; ins_idx = exclusive scan of the insert flags written by the same kernel
             int32_t* f32 = ws.flag32.ensure((size_t)nops);
-            DSA_LAUNCH("apply_hits", k_apply_hits, gr, 256, 0, st, keys.p, vals.p, ws.op_pos.p, ws.op_flag.p, op_val, nops,
-                       leafcnt.p, ws.touched, lgS, n_dev, f32);
-            exclusive_scan_i32<int32_t>(ws.scan, f32, ws.ins_idx.p, nops, ws.status + ST_NINS, st);
-            DSA_LAUNCH("compact_inserts", k_compact_inserts, gr, 256, 0, st, op_key, op_val, ws.op_pos.p, ws.op_flag.p, ws.ins_idx.p,
-                       nops, ws.ins_key.p, ws.ins_val.p, ws.ins_pos.p, n_dev);
-            ActiveLeaf* act = ws.act.ensure((size_t)std::min<int64_t>(nops, g.nb_segments) + 1);
-            DSA_LAUNCH("insert_leaf_info", k_insert_leaf_info, gr, 256, 0, st, ws.ins_pos.p, ws.status + ST_NINS, ws.inscnt,
-                       ws.ins_first.p, ws.touched, lgS, act, ws.status + ST_NACT);
+            DSA_LAUNCH("locate", k_locate, gr, 256, 0, st, keys.p, g.capacity, op_pid, op_key, op_val, nops, d_sem, d_next_slot,
+                       ws.op_pos.p, ws.op_flag.p, n_dev, op_dead, f32);
+            apply_located_ops<true>(ws, op_key, op_val, nops, st);
         }
         rebalance_launch(ws, st);
         if (!launch_only) {
             DSA_CUDA(cudaStreamSynchronize(st));
             rebalance_finish(ws, d_sem, st);
+        }
+    }
+
+    // located ops (ws.op_pos / op_flag / flag32 = insert flags) -> hits applied, inserts compacted, per-leaf insert runs
+    template <bool OVERWRITES>
+    void apply_located_ops(BatchWorkspace& ws, const int64_t* op_key, const double* op_val, int64_t nops, cudaStream_t st) {
+        const int lgS = ilog2_i64(g.segment_capacity);
+        const unsigned gr = grid_for(nops, 256);
+        {
+            exclusive_scan_i32<int32_t>(ws.scan, ws.flag32.p, ws.ins_idx.p, nops, ws.status + ST_NINS, st);
+            DSA_LAUNCH("apply_compact", k_apply_compact<OVERWRITES>, gr, 256, 0, st, keys.p, vals.p, op_key, op_val, ws.op_pos.p, ws.op_flag.p,
+                       ws.ins_idx.p, nops, leafcnt.p, ws.touched, lgS, ws.ins_key.p, ws.ins_val.p, ws.ins_pos.p);
+            ActiveLeaf* act = ws.act.ensure((size_t)std::min<int64_t>(nops, g.nb_segments) + 1);
+            DSA_LAUNCH("insert_leaf_info", k_insert_leaf_info, gr, 256, 0, st, ws.ins_pos.p, ws.status + ST_NINS, ws.inscnt,
+                       ws.ins_first.p, ws.touched, lgS, act, ws.status + ST_NACT);
         }
     }
 };

@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
+#include "../dynamicsparsearrays.jl_b200/csrc/pcsr.cuh"   // the product kernels, timed on the same synthetic arrays
+namespace dsa { Prof& prof() { static Prof p; return p; } DevicePool& device_pool() { static DevicePool* p = new DevicePool(); return *p; } }
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
 
@@ -144,6 +146,36 @@ int main() {
     {   // persistent grids without smem, for comparison with the smem variants
         run<int32_t, G_LDG, 4>("i32 keys, ldg gather, persistent 2x1024/SM", dk32, dv, cap, dx, tx, nx, 0, dout, nsmc * 2, 0, b12, 1024);
         run<int32_t, G_TEX, 4>("i32 keys, tex gather, persistent 2x1024/SM", dk32, dv, cap, dx, tx, nx, 0, dout, nsmc * 2, 0, b12, 1024);
+    }
+    {   // the product SpMV kernels on a row-major-like array: a semaphore cell (key 0, value = partition id) every ~166 cells
+        int64_t nparts = 0;
+        for (int64_t i = 0; i < cap; i += 166) { hk[i] = 0; hv[i] = (double)(++nparts); }
+        CK(cudaMemcpy(dk, hk.data(), cap * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dv, hv.data(), cap * 8, cudaMemcpyHostToDevice));
+        double *yslot, *carry; int32_t *ycnt, *ccnt, *clast;
+        CK(cudaMalloc(&yslot, (nparts + 1) * 8)); CK(cudaMalloc(&ycnt, (nparts + 1) * 4));
+        CK(cudaMalloc(&carry, (cap / 64) * 8)); CK(cudaMalloc(&ccnt, (cap / 64) * 4)); CK(cudaMalloc(&clast, (cap / 64) * 4));
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        auto timeit = [&](const char* name, auto launch) {
+            for (int i = 0; i < 3; ++i) launch();
+            CK(cudaDeviceSynchronize());
+            CK(cudaEventRecord(e0));
+            for (int i = 0; i < 20; ++i) launch();
+            CK(cudaEventRecord(e1));
+            CK(cudaDeviceSynchronize());
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            printf("%-60s : %8.2f us\n", name, 1e3 * ms / 20);
+        };
+        const int64_t nch4 = cap / 128, nch8 = cap / 256;
+        timeit("product k_spmv_blocked<false,4>", [&] {
+            dsa::k_spmv_blocked<false, 4><<<(unsigned)(nch4 * 32 / 256), 256>>>(dk, dv, cap, dx, nullptr, nx, yslot, ycnt, carry, ccnt, clast, nch4); });
+        timeit("product k_spmv_blocked<false,8>", [&] {
+            dsa::k_spmv_blocked<false, 8><<<(unsigned)(nch8 * 32 / 256), 256>>>(dk, dv, cap, dx, nullptr, nx, yslot, ycnt, carry, ccnt, clast, nch8); });
+        timeit("product k_spmv_blocked<false,4> + fixup", [&] {
+            dsa::k_spmv_blocked<false, 4><<<(unsigned)(nch4 * 32 / 256), 256>>>(dk, dv, cap, dx, nullptr, nx, yslot, ycnt, carry, ccnt, clast, nch4);
+            dsa::k_spmv_fixup<false><<<(unsigned)((nch4 + 255) / 256), 256>>>(yslot, ycnt, carry, ccnt, clast, nch4); });
     }
     return 0;
 }
