@@ -131,14 +131,17 @@ __global__ void __launch_bounds__(RT_THREADS) k_route_count(const int64_t* __res
     }
 }
 
-// one CTA, one warp per (orientation, owner) bin: exclusive scan over the tiles; totals -> this rank's row of the count matrix
+// one CTA per (orientation, owner) bin: exclusive scan of the bin's tile counts (stable partition offsets); the total is this
+// rank's send count for that bin
 __global__ void __launch_bounds__(1024) k_route_scan(const int32_t* __restrict__ tile_cnt, int64_t ntiles, int world,
                                                       int32_t* __restrict__ tile_off, int64_t* __restrict__ send_counts) {
-    const int bin = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (bin >= 2 * world) return;
-    int carry = 0;
-    for (int64_t t0 = 0; t0 < ntiles; t0 += 32) {
-        const int64_t t = t0 + lane;
+    __shared__ int warp_tot[32];
+    __shared__ int carry_s;
+    const int bin = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t t0 = 0; t0 < ntiles; t0 += 1024) {
+        const int64_t t = t0 + threadIdx.x;
         const int v = t < ntiles ? tile_cnt[t * 2 * world + bin] : 0;
         int s = v;
 #pragma unroll
@@ -146,10 +149,25 @@ __global__ void __launch_bounds__(1024) k_route_scan(const int32_t* __restrict__
             const int u = __shfl_up_sync(0xffffffffu, s, o);
             if (lane >= o) s += u;
         }
-        if (t < ntiles) tile_off[t * 2 * world + bin] = carry + s - v;
-        carry += __shfl_sync(0xffffffffu, s, 31);
+        if (lane == 31) warp_tot[wid] = s;
+        __syncthreads();
+        if (wid == 0) {
+            int wv = warp_tot[lane], ws = wv;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, ws, o);
+                if (lane >= o) ws += u;
+            }
+            warp_tot[lane] = ws - wv;   // exclusive over the warps
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        if (t < ntiles) tile_off[t * 2 * world + bin] = carry + warp_tot[wid] + s - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + warp_tot[wid] + s;
+        __syncthreads();
     }
-    if (lane == 0) send_counts[bin] = carry;   // bin = o * world + dst
+    if (threadIdx.x == 0) send_counts[bin] = carry_s;   // bin = o * world + dst
 }
 
 struct PushTargets {
@@ -161,12 +179,20 @@ __host__ __device__ __forceinline__ int64_t region_word(int o, int src, int a, i
     return (((int64_t)o * world + src) * 3 + a) * region_cap;
 }
 
+// The tile's ops are first laid out in shared memory in (owner, arrival) order, then copied out: consecutive threads store
+// consecutive words of one owner's run, so the peer stores leave the SM as full 128-byte lines (about RT_TILE / world ops = 1 KB
+// per owner, array and tile).  Storing straight from registers split every warp store into `world` 32-byte pieces: 196 us per
+// launch at 8 GPUs against 70 us at 2 (NVLink packets of 32 bytes), the limiter of the 8-GPU step.
 __global__ void __launch_bounds__(RT_THREADS) k_route_push(const int64_t* __restrict__ rows, const int64_t* __restrict__ cols,
                                                             const double* __restrict__ vals, int64_t n, RouteTables T,
                                                             const int32_t* __restrict__ tile_off, PushTargets P, int64_t region_cap) {
-    // counts of every (slab j, warp w) per bin, then their exclusive prefix in (j, w) order = index order inside the tile
-    __shared__ int wcnt[RT_ITEMS * (RT_THREADS / 32)][2][DIST_MAX_RANKS];
     constexpr int NSEG = RT_ITEMS * (RT_THREADS / 32);
+    // counts of every (slab j, warp w) per bin, then their exclusive prefix in (j, w) order = index order inside the tile
+    __shared__ int wcnt[NSEG][2][DIST_MAX_RANKS];
+    __shared__ int binstart[2][DIST_MAX_RANKS + 1];   // first staged index of every owner's run
+    __shared__ int toff[2][DIST_MAX_RANKS];           // offset of the tile's run inside the owner's region
+    __shared__ int64_t s_r[RT_TILE], s_c[RT_TILE];
+    __shared__ double s_v[RT_TILE];
     for (int t = threadIdx.x; t < NSEG * 2 * DIST_MAX_RANKS; t += RT_THREADS) (&wcnt[0][0][0])[t] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -200,33 +226,53 @@ __global__ void __launch_bounds__(RT_THREADS) k_route_push(const int64_t* __rest
     __syncthreads();
     if (threadIdx.x < 2 * T.world) {   // serial exclusive prefix over the 32 (slab, warp) segments of one bin
         const int o = threadIdx.x / T.world, d = threadIdx.x % T.world;
-        int run = tile_off[((int64_t)blockIdx.x * 2 + o) * T.world + d];
+        int run = 0;
         for (int sgm = 0; sgm < NSEG; ++sgm) {
             const int c = wcnt[sgm][o][d];
             wcnt[sgm][o][d] = run;
             run += c;
         }
+        binstart[o][d + 1] = run;   // count, turned into a start below
+        toff[o][d] = tile_off[((int64_t)blockIdx.x * 2 + o) * T.world + d];
     }
     __syncthreads();
-#pragma unroll
-    for (int j = 0; j < RT_ITEMS; ++j) {
-        const int64_t i = base + j * RT_THREADS + threadIdx.x;
-        if (i >= n) continue;
-#pragma unroll
-        for (int o = 0; o < 2; ++o) {
-            if (!(T.omask & (1 << o))) continue;
-            const int d = own[j][o];
-            const int64_t pos = wcnt[j * (RT_THREADS / 32) + w][o][d] + rk[j][o];
-            int64_t* dst = P.base[d] + region_word(o, P.region[d], 0, T.world, region_cap) + pos;   // NVLink peer store (or local when d == me)
-            dst[0] = r_[j];
-            dst[region_cap] = c_[j];
-            dst[2 * region_cap] = __double_as_longlong(v_[j]);
+    if (threadIdx.x < 2) {
+        const int o = threadIdx.x;
+        int run = 0;
+        binstart[o][0] = 0;
+        for (int d = 0; d < T.world; ++d) {
+            const int c = binstart[o][d + 1];
+            binstart[o][d + 1] = run + c;
+            run += c;
         }
     }
-    // One system-scope fence per CTA (cumulative over the CTA's stores through the barrier), not one per thread: a fence waits
-    // for the NVLink acknowledgements of the thread's outstanding peer stores, and 256 of them per CTA kept the CTAs resident
-    // for the round trip (75 us per launch at 2 GPUs).  Kernel completion + the count all-gather order the rest.
     __syncthreads();
+    for (int o = 0; o < 2; ++o) {
+        if (!(T.omask & (1 << o))) continue;
+#pragma unroll
+        for (int j = 0; j < RT_ITEMS; ++j) {
+            const int d = own[j][o];
+            if (d < 0) continue;
+            const int li = binstart[o][d] + wcnt[j * (RT_THREADS / 32) + w][o][d] + rk[j][o];
+            s_r[li] = r_[j];
+            s_c[li] = c_[j];
+            s_v[li] = v_[j];
+        }
+        __syncthreads();
+        const int cnt = binstart[o][T.world];
+        for (int t = threadIdx.x; t < cnt; t += RT_THREADS) {
+            int d = 0;
+            while (t >= binstart[o][d + 1]) ++d;
+            const int64_t pos = toff[o][d] + (t - binstart[o][d]);
+            int64_t* dst = P.base[d] + region_word(o, P.region[d], 0, T.world, region_cap) + pos;   // NVLink peer store (local when d == me)
+            dst[0] = s_r[t];
+            dst[region_cap] = s_c[t];
+            dst[2 * region_cap] = __double_as_longlong(s_v[t]);
+        }
+        __syncthreads();
+    }
+    // One system-scope fence per CTA (cumulative over the CTA's stores through the barrier); kernel completion + the count
+    // all-gather order the rest.
     if (threadIdx.x == 0) __threadfence_system();
 }
 

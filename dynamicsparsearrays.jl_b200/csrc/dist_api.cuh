@@ -174,7 +174,7 @@ static bool dist_exchange(dsa_dmatrix* D, const int64_t* d_rows, const int64_t* 
         int32_t* tc = D->tile_cnt.ensure((size_t)ntiles * 2 * W);
         int32_t* to = D->tile_off.ensure((size_t)ntiles * 2 * W);
         DSA_LAUNCH("route_count", k_route_count, (unsigned)ntiles, RT_THREADS, 0, st, d_rows, d_cols, n, T, tc, row + 2 * W);
-        DSA_LAUNCH("route_scan", k_route_scan, 1, 1024, 0, st, (const int32_t*)tc, ntiles, W, to, row);
+        DSA_LAUNCH("route_scan", k_route_scan, (unsigned)(2 * W), 1024, 0, st, (const int32_t*)tc, ntiles, W, to, row);
         DSA_LAUNCH("route_push", k_route_push, (unsigned)ntiles, RT_THREADS, 0, st, d_rows, d_cols, d_vals, n, T, (const int32_t*)to, P,
                    D->region_cap);
     }

@@ -568,7 +568,6 @@ struct PcsrWorkspace {
     SortWorkspace sort;
     DBuf<int32_t> op_slot, flag32, idx32, u_pid, new_slots, old2new, rank32, del_slots, cnt32, bcnt, boff, lidx, bslot;
     DBuf<BucketRec> brec;
-    DBuf<uint8_t> u_dead;
     DBuf<int64_t> miss_keys, cs, u_key, live_pos, nuniq, tmp_k, tmp_owner, del_keys;
     DBuf<double> u_val, tmp_v, yslot, carry, xdense;
     DBuf<uint64_t> sk;
