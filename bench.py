@@ -246,7 +246,7 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
-    if world > 1:
+    if world > 1 or os.environ.get("DSA_BENCH_FORCE_DIST") == "1":   # the latter: the sharded code path on one rank (no NVLink traffic)
         from bench_dist import main_dist   # sharded path (dsa_dist_*: peer-memory routing + NCCL all-gather)
         main_dist(args, rank, world, local_rank)
         return

@@ -73,7 +73,8 @@ inline void level_bounds(int64_t S, int64_t H, double t_d, double p_d, int64_t* 
 
 // Capacity after a batch whose root window failed (batch policy): repeat _extend! while the root
 // density exceeds t_h, or _shrink! while it is below p_h and height > 1 (pma.jl:132-139).
-inline Geometry geometry_after_root_failure(const Geometry& g, int64_t N) {
+// single_step: the batch was ONE op -> exactly one _extend! / _shrink! like the reference's setindex! (pma.jl:132-139).
+inline Geometry geometry_after_root_failure(const Geometry& g, int64_t N, bool single_step = false) {
     int64_t mn[40], mx[40];
     int64_t cap = g.capacity, h = g.height;
     level_bounds(g.segment_capacity, h, g.t_d, g.p_d, mn, mx);
@@ -82,13 +83,14 @@ inline Geometry geometry_after_root_failure(const Geometry& g, int64_t N) {
             cap *= 2;
             h += 1;
             level_bounds(g.segment_capacity, h, (T_H - T_0) / (double)h, (P_H - P_0) / (double)h, mn, mx);
-        } while (N > mx[h]);
+        } while (N > mx[h] && !single_step);
     } else {
         while (h > 1) {
             level_bounds(g.segment_capacity, h, (T_H - T_0) / (double)h, (P_H - P_0) / (double)h, mn, mx);
             if (N >= mn[h]) break;
             cap /= 2;
             h -= 1;
+            if (single_step) break;
         }
     }
     return geometry_resized(g, cap, h);

@@ -153,7 +153,7 @@ static void phase2_launch(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t 
         int32_t* f32 = ws.batch.flag32.ensure((size_t)n);
         DSA_LAUNCH("bucket_rank_locate", k_bucket_rank_locate, grt, 256, 0, st, rec, boff, bcnt, n, c.vals, P.pma.keys.p, P.pma.vals.p,
                    P.pma.g.capacity, P.d_sem.p, P.d_next_slot.p, u_key, u_val, ws.batch.op_pos.p, ws.batch.op_flag.p, f32);
-        P.pma.apply_located_ops<false>(ws.batch, u_key, u_val, n, st);
+        P.pma.apply_located_ops<false>(ws.batch, u_key, u_val, n, P.d_sem.p, st);
         P.pma.rebalance_launch(ws.batch, st);
         return;
     }

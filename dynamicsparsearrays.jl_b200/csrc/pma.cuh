@@ -211,6 +211,94 @@ __global__ void __launch_bounds__(256) k_apply_compact(int64_t* __restrict__ key
         vals[p] = op_val[i];
     }
 }
+// A batch of ONE op that turns out to be an insert is applied exactly like the reference's _insert! (writes.jl:26-43), so that
+// single writes leave the reference's own layout: the cells between the predecessor and the next gap to its right — wherever
+// that gap is, even in another leaf or partition — shift right by one (moves.jl:7-42, semaphore positions follow); if there is
+// no gap up to the array end, the cells back to the previous gap shift left (moves.jl:50-85).  The leaf of the new element is
+// then walked by the usual density tree (_look_for_rebalance!, pma.jl:105-141): accepted leaf => nothing else moves
+// (pma.jl:96-99).  One warp; the op leaves this kernel as "applied" (no pending insert).
+__global__ void __launch_bounds__(32) k_single_insert(int64_t* __restrict__ keys, double* __restrict__ vals, int64_t cap,
+                                                      const int64_t* __restrict__ op_key, const double* __restrict__ op_val,
+                                                      const int64_t* __restrict__ op_pos, uint8_t* __restrict__ op_flag,
+                                                      int32_t* __restrict__ ins_flag, int32_t* __restrict__ leafcnt,
+                                                      uint8_t* __restrict__ touched, int lgS, int64_t* __restrict__ sem) {
+    if (op_flag[0] != FL_INSERT) return;
+    const int lane = threadIdx.x;
+    const int64_t pp = op_pos[0];   // predecessor cell, -1 = none
+    int64_t g = -1;
+    for (int64_t b0 = pp + 1; b0 < cap; b0 += 32) {   // _nextemptypos (utils.jl:3-10): scans to the array end
+        const int64_t p = b0 + lane;
+        const unsigned b = __ballot_sync(0xffffffffu, p < cap && keys[p] == GAP_KEY);
+        if (b) {
+            g = b0 + __ffs(b) - 1;
+            break;
+        }
+    }
+    int64_t newpos;
+    if (g >= 0) {   // _movecellstoright!(array, pos + 1, next_empty_pos)
+        int64_t hi = g - 1;
+        while (hi >= pp + 1) {
+            const int64_t lo = hi - 31 > pp + 1 ? hi - 31 : pp + 1;
+            const int64_t p = lo + lane;
+            const bool valid = p <= hi;
+            int64_t k = 0;
+            double v = 0.0;
+            if (valid) {
+                k = keys[p];
+                v = vals[p];
+            }
+            __syncwarp();
+            if (valid) {
+                keys[p + 1] = k;
+                vals[p + 1] = v;
+                if (sem && k == 0) sem[(int64_t)v - 1] = p + 1;   // moves.jl:33-37
+            }
+            __syncwarp();
+            hi = lo - 1;
+        }
+        newpos = pp + 1;
+    } else {        // _previousemptypos + _movecellstoleft!(array, pos, previous_empty_pos)
+        for (int64_t t0 = pp - 1; t0 >= 0; t0 -= 32) {
+            const int64_t p = t0 - lane;
+            const unsigned b = __ballot_sync(0xffffffffu, p >= 0 && keys[p] == GAP_KEY);
+            if (b) {
+                g = t0 - (__ffs(b) - 1);
+                break;
+            }
+        }
+        if (g < 0) return;   // "No empty cell to insert a new element": cannot occur below density 1 (writes.jl:39)
+        int64_t lo = g + 1;
+        while (lo <= pp) {
+            const int64_t hi = lo + 31 < pp ? lo + 31 : pp;
+            const int64_t p = lo + lane;
+            const bool valid = p <= hi;
+            int64_t k = 0;
+            double v = 0.0;
+            if (valid) {
+                k = keys[p];
+                v = vals[p];
+            }
+            __syncwarp();
+            if (valid) {
+                keys[p - 1] = k;
+                vals[p - 1] = v;
+                if (sem && k == 0) sem[(int64_t)v - 1] = p - 1;   // moves.jl:76-80
+            }
+            __syncwarp();
+            lo = hi + 1;
+        }
+        newpos = pp;
+    }
+    if (lane == 0) {
+        keys[newpos] = op_key[0];
+        vals[newpos] = op_val[0];
+        leafcnt[g >> lgS] += 1;          // the cell that was the gap is now occupied; every leaf in between keeps its count
+        touched[newpos >> lgS] = 1;      // _look_for_rebalance!(pma, insertion_pos)
+        op_flag[0] = 0;
+        ins_flag[0] = 0;
+    }
+}
+
 // per-leaf bookkeeping of the compacted inserts: every new key belongs to the leaf of its predecessor cell; inserts are
 // sorted, so the inserts of one leaf are contiguous.  The thread of the FIRST insert of a leaf counts the run and records
 // (leaf, first index, count) in the list of leaves that receive inserts (unordered: each entry is independent work).
@@ -782,6 +870,7 @@ struct BatchWorkspace {   // per-handle scratch reused by every batch
     DBuf<double> shadow_v;
     HPinned<int64_t> h_status;
     ScanWorkspace scan;
+    bool single_op = false;      // the running batch is one op: reference-exact single write (k_single_insert, one resize step)
 };
 
 struct PmaCore {
@@ -905,7 +994,7 @@ struct PmaCore {
         const unsigned warp_grid = grid_for(nsegs * 32, 256);
         if (hs[ST_OVER] || hs[ST_UNDER]) {
             // root failed: _extend!/_shrink! (pma.jl:132-139) until the root accepts, then one full spread into the new array
-            Geometry ng = geometry_after_root_failure(g, N);
+            Geometry ng = geometry_after_root_failure(g, N, ws.single_op);
             DBuf<int64_t> nk;
             DBuf<double> nv;
             nk.ensure((size_t)ng.capacity);
@@ -951,6 +1040,7 @@ struct PmaCore {
 
     void prepare_batch_scratch(BatchWorkspace& ws, int64_t nops, cudaStream_t st) {
         const int64_t nsegs = g.nb_segments;
+        ws.single_op = false;
         ws.op_pos.ensure((size_t)nops + 1);
         ws.op_flag.ensure((size_t)nops + 1);
         ws.ins_idx.ensure((size_t)nops + 1);
@@ -980,7 +1070,7 @@ struct PmaCore {
             int32_t* f32 = ws.flag32.ensure((size_t)nops);
             DSA_LAUNCH("locate", k_locate, gr, 256, 0, st, keys.p, g.capacity, op_pid, op_key, op_val, nops, d_sem, d_next_slot,
                        ws.op_pos.p, ws.op_flag.p, n_dev, op_dead, f32);
-            apply_located_ops<true>(ws, op_key, op_val, nops, st);
+            apply_located_ops<true>(ws, op_key, op_val, nops, d_sem, st);
         }
         rebalance_launch(ws, st);
         if (!launch_only) {
@@ -991,9 +1081,13 @@ struct PmaCore {
 
     // located ops (ws.op_pos / op_flag / flag32 = insert flags) -> hits applied, inserts compacted, per-leaf insert runs
     template <bool OVERWRITES>
-    void apply_located_ops(BatchWorkspace& ws, const int64_t* op_key, const double* op_val, int64_t nops, cudaStream_t st) {
+    void apply_located_ops(BatchWorkspace& ws, const int64_t* op_key, const double* op_val, int64_t nops, int64_t* d_sem, cudaStream_t st) {
         const int lgS = ilog2_i64(g.segment_capacity);
         const unsigned gr = grid_for(nops, 256);
+        ws.single_op = nops == 1;
+        if (nops == 1)   // a single write keeps the reference's own layout (writes.jl:26-43)
+            DSA_LAUNCH("single_insert", k_single_insert, 1, 32, 0, st, keys.p, vals.p, g.capacity, op_key, op_val, (const int64_t*)ws.op_pos.p,
+                       ws.op_flag.p, ws.flag32.p, leafcnt.p, ws.touched, lgS, d_sem);
         {
             exclusive_scan_i32<int32_t>(ws.scan, ws.flag32.p, ws.ins_idx.p, nops, ws.status + ST_NINS, st);
             DSA_LAUNCH("apply_compact", k_apply_compact<OVERWRITES>, gr, 256, 0, st, keys.p, vals.p, op_key, op_val, ws.op_pos.p, ws.op_flag.p,

@@ -173,6 +173,10 @@ void apply_located(Pma& p, Semaphores* sem, std::vector<Op>& ops,
 
 // ---- plain PMA -------------------------------------------------------------------------
 void pma_set_batch(Pma& p, const int64_t* keys, const double* vals, int64_t n) {
+    if (n == 1) {   // a batch of ONE op is the reference's own setindex! (pma.jl:196-213): shift to the next gap (writes.jl:26-43),
+        pma_set(p, vals[0], keys[0]);   // one leaf -> root walk, at most one _extend! / _shrink!
+        return;
+    }
     std::vector<int64_t> idx((size_t)n);
     std::iota(idx.begin(), idx.end(), int64_t(0));
     std::stable_sort(idx.begin(), idx.end(), [&](int64_t a, int64_t b) { return keys[a] < keys[b]; });
@@ -199,6 +203,14 @@ static int64_t next_live_sem_pos(const Semaphores& s, int64_t pid, int64_t array
 void mpcsc_set_batch(Mpcsc& M, const int64_t* inkeys, const int64_t* partkeys, const double* vals, int64_t n) {
     for (int64_t i = 0; i < n; ++i)
         if (inkeys[i] < 1) throw Error{ERR_ARGUMENT, "in-array keys must be >= 1 (key 0 is the semaphore key, pcsr.jl:23)"};
+    if (n == 1) {   // a batch of ONE op on an existing partition is the reference's own setindex! (pcsr.jl:341-347 -> 294-339)
+        bool exact;
+        colkeys_find(M.col_keys, partkeys[0], &exact);
+        if (exact) {
+            mpcsc_set(M, vals[0], inkeys[0], partkeys[0]);
+            return;
+        }   // a single op that creates its partition follows the batch policy below (semaphore + element laid by one spread!)
+    }
     // 1. column map: replay addcolumn!'s slot logic (pcsr.jl:148-169) in arrival order, without touching the array
     ColKeys ck = M.col_keys;
     std::vector<int64_t> old_id((size_t)ck.length());

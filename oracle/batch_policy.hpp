@@ -15,6 +15,10 @@
 //     outermost one; each marked window is re-laid with pack!+spread!;
 //   * a failing root doubles / halves the capacity (pma.jl:143-161) until the
 //     root density is inside its thresholds, then the whole array is re-spread.
+//   * a batch of exactly ONE op (on an existing partition, or on a vector) is not
+//     re-laid at all: it IS the reference's setindex! — shift to the next gap
+//     (writes.jl:26-43, moves.jl:7-85), one leaf->root walk, at most one
+//     _extend!/_shrink! — so single writes are layout-bit-exact with the reference.
 // Logical contents after a batch are identical to applying the ops one by one
 // with the reference (tests check this against the sequential oracle).
 #pragma once

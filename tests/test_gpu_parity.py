@@ -607,3 +607,57 @@ def test_full_size_config2_properties():
     assert abs(ones.sum() - vals.sum()) <= 1e-9 * vals.sum()          # checksum of checksums
     t = gm.mul_dense(np.ones(m), trans=True)
     assert abs(t.sum() - vals.sum()) <= 1e-9 * vals.sum()
+
+
+def test_single_writes_keep_the_reference_layout():
+    """A batch of ONE op is the reference's own setindex!: shift to the next gap (writes.jl:26-43, moves.jl:7-85) — across leaf
+    and partition boundaries, to the left when the tail is full — one leaf->root walk, at most one _extend!/_shrink!.  The
+    layout after every single write is compared BIT FOR BIT with the sequential oracle (= the reference), not with the batch
+    policy: vectors, and matrix writes on existing rows / columns."""
+    rng = np.random.default_rng(2024)
+    # vector: random mix of new keys, overwrites and deletes
+    keys = np.unique(rng.integers(1, 20_000, 3000))
+    vals = rng.random(len(keys)) + 0.5
+    gv, seq = D.dynamicsparsevec(keys, vals), O.Vec(keys, vals)
+    live = keys.tolist()
+    for t in range(600):
+        r = rng.random()
+        if r < 0.6:
+            k, v = int(rng.integers(1, 20_000)), float(rng.random() + 0.5)
+        elif r < 0.8:
+            k, v = int(live[rng.integers(0, len(live))]), float(rng.random() + 0.5)   # overwrite (or re-insert)
+        else:
+            k, v = int(live[rng.integers(0, len(live))]), 0.0                          # delete (maybe already gone)
+        gv.set_batch([k], [v])
+        seq[k] = v
+        live.append(k)
+        if t % 25 == 24:
+            assert_vec_equal(gv, seq)
+    assert_vec_equal(gv, seq)
+    # a tiny vector filled from the right end: no gap to the right -> shifts to the LEFT, and _extend! one step at a time
+    gv, seq = D.dynamicsparsevec([5, 9], [1.0, 2.0]), O.Vec([5, 9], [1.0, 2.0])
+    for t in range(120):
+        k, v = 10 + 3 * t, float(t + 1)
+        gv.set_batch([k], [v])
+        seq[k] = v
+        assert_vec_equal(gv, seq)
+    for t in range(119, -1, -1):      # and emptied again: _shrink! one step per delete
+        gv.set_batch([10 + 3 * t], [0.0])
+        seq[10 + 3 * t] = 0.0
+        assert_vec_equal(gv, seq)
+    # matrix: single writes on existing rows and columns (both orientations shift independently, semaphores follow)
+    m, n = 60, 50
+    I, J = rng.integers(1, m + 1, 900), rng.integers(1, n + 1, 900)
+    V = rng.random(900) + 0.5
+    gm, sq = D.dynamicsparse(I, J, V, m=m, n=n), O.Matrix(I, J, V, m=m, n=n)
+    rows, cols = np.unique(I), np.unique(J)
+    for t in range(500):
+        i, j = int(rows[rng.integers(0, len(rows))]), int(cols[rng.integers(0, len(cols))])
+        v = 0.0 if rng.random() < 0.3 else float(rng.random() + 0.5)
+        gm.set_batch([i], [j], [v])
+        sq[i, j] = v
+        if t % 20 == 19:
+            assert_matrix_equal(gm, sq)      # layout, semaphores, column map: bit-exact with the reference
+    assert_matrix_equal(gm, sq)
+    x = rng.random(n)
+    assert _rel_close(gm.mul_dense(x), sq.mul_dense(x, m))
