@@ -98,12 +98,14 @@ struct AllocTimer {
 
 // ---- caching device allocator ---------------------------------------------------------------------
 // cudaMalloc / cudaFree of the 100 MB-class buffers of a growing structure cost milliseconds each (measured: 230 ms per batch
-// while a matrix doubles, profiles/prof_c5.py).  Blocks are therefore recycled: sizes are rounded to 4 classes per octave,
-// a released block goes back to a free list after a device synchronisation (the same guarantee cudaFree gives: nobody is
-// still using it), and is handed out again to the next request of a compatible size.  dsa_trim_memory() returns the cached
-// blocks to the driver.
+// while a matrix doubles, profiles/prof_c5.py).  Blocks are therefore recycled: sizes are rounded to 4 classes per octave and a
+// released block is handed out again to the next request of a compatible size.  One pool PER DEVICE (a process may drive
+// several GPUs through dsa_set_device).  Releasing does not synchronise: a released block waits in `pending` and becomes
+// reusable at the first device synchronisation that an allocation actually needs (or that dsa_trim_memory performs) — the
+// guarantee cudaFree gives (nobody is still using the block), paid only when a block is really recycled.
+// dsa_trim_memory() returns the cached blocks to the driver.
 struct DevicePool {
-    std::multimap<size_t, void*> free_blocks;
+    std::multimap<size_t, void*> free_blocks, pending;
     size_t cached_bytes = 0;
     std::mutex mu;   // handles of different host threads share the pool
     static size_t size_class(size_t bytes) {
@@ -112,15 +114,30 @@ struct DevicePool {
         const size_t step = size_t(1) << (lg - 2);
         return (bytes + step - 1) / step * step;
     }
-    void* get(size_t bytes) {
-        std::lock_guard<std::mutex> lock(mu);
-        const size_t want = size_class(bytes);
+    void* take_locked(size_t want) {
         auto it = free_blocks.lower_bound(want);
         if (it != free_blocks.end() && it->first <= want + want / 2) {
             void* p = it->second;
             cached_bytes -= it->first;
             free_blocks.erase(it);
             return p;
+        }
+        return nullptr;
+    }
+    void settle_locked() {   // everything released so far is idle after this
+        if (pending.empty()) return;
+        cudaDeviceSynchronize();
+        for (auto& kv : pending) free_blocks.emplace(kv.first, kv.second);
+        pending.clear();
+    }
+    void* get(size_t bytes) {
+        std::lock_guard<std::mutex> lock(mu);
+        const size_t want = size_class(bytes);
+        if (void* p = take_locked(want)) return p;
+        auto it = pending.lower_bound(want);
+        if (it != pending.end() && it->first <= want + want / 2) {   // a released block fits: wait for its last users once
+            settle_locked();
+            if (void* p = take_locked(want)) return p;
         }
         void* p = nullptr;
         AllocTimer t("(cudaMalloc)");
@@ -137,13 +154,13 @@ struct DevicePool {
         return p;
     }
     void put(void* p, size_t bytes) {
-        cudaDeviceSynchronize();   // what cudaFree would have guaranteed: no queued work still touches the block
         std::lock_guard<std::mutex> lock(mu);
         const size_t c = size_class(bytes);
-        free_blocks.emplace(c, p);
+        pending.emplace(c, p);
         cached_bytes += c;
     }
     void trim_locked() {
+        settle_locked();
         AllocTimer t("(cudaFree)");
         for (auto& kv : free_blocks) cudaFree(kv.second);
         free_blocks.clear();
@@ -154,19 +171,25 @@ struct DevicePool {
         trim_locked();
     }
 };
-DevicePool& device_pool();
+DevicePool& device_pool(int device);   // the pool of a device
+inline int current_device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d;
+}
 
 // ---- device buffer that only grows ------------------------------------------------------------
 template <typename T>
 struct DBuf {
     T* p = nullptr;
     size_t cap = 0;   // elements
+    int device = 0;   // where the block lives: it goes back to that device's pool
     DBuf() {}
     DBuf(const DBuf&) = delete;
     DBuf& operator=(const DBuf&) = delete;
     ~DBuf() { release(); }
     void release() {
-        if (p) device_pool().put(p, cap * sizeof(T));
+        if (p) device_pool(device).put(p, cap * sizeof(T));
         p = nullptr;
         cap = 0;
     }
@@ -175,7 +198,8 @@ struct DBuf {
         if (n > cap) {
             release();
             const size_t bytes = DevicePool::size_class((n + 64) * sizeof(T));
-            p = (T*)device_pool().get(bytes);
+            device = current_device();
+            p = (T*)device_pool(device).get(bytes);
             cap = bytes / sizeof(T);
         }
         return p;
@@ -183,6 +207,7 @@ struct DBuf {
     void swap(DBuf& o) {
         std::swap(p, o.p);
         std::swap(cap, o.cap);
+        std::swap(device, o.device);
     }
 };
 

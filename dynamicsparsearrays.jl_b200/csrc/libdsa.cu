@@ -11,8 +11,13 @@ Prof& prof() {
     static Prof p;
     return p;
 }
-DevicePool& device_pool() {
-    static DevicePool* p = new DevicePool();   // never destroyed: handles may be released during interpreter shutdown
+DevicePool& device_pool(int device) {
+    // never destroyed: handles may be released during interpreter shutdown
+    static std::mutex mu;
+    static std::map<int, DevicePool*>* pools = new std::map<int, DevicePool*>();
+    std::lock_guard<std::mutex> lock(mu);
+    DevicePool*& p = (*pools)[device];
+    if (!p) p = new DevicePool();
     return *p;
 }
 
@@ -65,6 +70,20 @@ static void phase1_read(PcsrWorkspace& ws, BatchCtx& c) {
         c.n = hcs[CS_N];
         c.n_dev = nullptr;
     }
+}
+
+// Everything a batch can be refused for, checked on the statistics of phase 1 BEFORE phase1_finish creates columns: a failed
+// call leaves the structure unchanged (include/dsa.h).  The bounds are conservative: `missing` counts ops, not distinct keys.
+static void phase1_validate(const Pcsr& P, const BatchCtx& c, const char* what) {
+    if (c.n <= 0) return;
+    if (c.bs.minkey < 1)
+        throw DsaError{DSA_ERR_ARGUMENT, std::string(what) + " must be >= 1 (each is an in-array key of one orientation; key 0 is the semaphore key, pcsr.jl:23)"};
+    const int64_t slots_after = P.nslots() + std::max<int64_t>(c.bs.missing, 0);
+    if (slots_after >= (int64_t(1) << 31)) throw DsaError{DSA_ERR_ARGUMENT, "too many partitions"};
+    const int kb = std::max(1, bits_for((uint64_t)std::max<int64_t>(c.bs.maxkey, P.max_inkey)));
+    const int pb = std::max(1, bits_for((uint64_t)std::max<int64_t>(slots_after - 1, 1)));
+    if ((c.bs.missing > 0 || c.bs.maxbucket > BUCKET_MAX) && kb + pb > 64)   // the radix path packs (slot, key) into one 64-bit sort key
+        throw DsaError{DSA_ERR_ARGUMENT, "key range too wide: bits(max in-array key) + bits(#partitions) must be <= 64"};
 }
 
 static void phase1_finish(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t st) {
@@ -185,7 +204,7 @@ void Pcsr::set_batch_d(PcsrWorkspace& ws, const int64_t* d_inkeys, const int64_t
     phase1_launch(*this, ws, c, st);
     DSA_CUDA(cudaStreamSynchronize(st));
     phase1_read(ws, c);
-    if (c.bs.minkey < 1) throw DsaError{DSA_ERR_ARGUMENT, "in-array keys must be >= 1 (key 0 is the semaphore key, pcsr.jl:23)"};
+    phase1_validate(*this, c, "in-array keys");
     if (max_part_nz) *max_part_nz = c.bs.maxpart_nz;
     if (max_key_nz) *max_key_nz = c.bs.maxkey_nz;
     phase1_finish(*this, ws, c, st);
@@ -421,8 +440,9 @@ static void matrix_set_batch_two(dsa_matrix* A, const int64_t* rows_c, const int
         if (nr > 0) { phase1_read(A->ws2, cr); nr = cr.n; }
         if (pre_mutate) (*pre_mutate)();   // caller-side validation that needs the first host synchronisation (may throw: nothing is mutated yet)
         // validate before mutate: rows are the in-array keys of the col-major structure, columns those of the row-major one
-        if ((nc > 0 && cc.bs.minkey < 1) || (nr > 0 && cr.bs.minkey < 1))
-            throw DsaError{DSA_ERR_ARGUMENT, "row and column keys must be >= 1 (each is an in-array key of one orientation; key 0 is the semaphore key, pcsr.jl:23)"};
+        // (both orientations are checked before either one creates a column)
+        if (nc > 0) phase1_validate(A->colmajor, cc, "row and column keys");
+        if (nr > 0) phase1_validate(A->rowmajor, cr, "row and column keys");
         if (nc > 0) phase1_finish(A->colmajor, A->ws, cc, st);
         if (nr > 0) phase1_finish(A->rowmajor, A->ws2, cr, st2);
         if (nc > 0) phase2_launch(A->colmajor, A->ws, cc, st);
@@ -1026,11 +1046,11 @@ int dsa_matrix_spmv_dense_range_d(dsa_matrix_t* A, int trans, const double* d_x,
 int dsa_trim_memory(void) {
     DSA_TRY
     cudaDeviceSynchronize();
-    device_pool().trim();
+    device_pool(current_device()).trim();
     return DSA_OK;
     DSA_CATCH
 }
-int64_t dsa_cached_bytes(void) { return (int64_t)device_pool().cached_bytes; }
+int64_t dsa_cached_bytes(void) { return (int64_t)device_pool(current_device()).cached_bytes; }
 int64_t dsa_launch_count(void) { return prof().launches; }
 int dsa_prof_enable(int on) {
     prof().enabled = on != 0;

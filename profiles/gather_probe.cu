@@ -7,7 +7,7 @@
 #include <cstdlib>
 #include <vector>
 #include "../dynamicsparsearrays.jl_b200/csrc/pcsr.cuh"   // the product kernels, timed on the same synthetic arrays
-namespace dsa { Prof& prof() { static Prof p; return p; } DevicePool& device_pool() { static DevicePool* p = new DevicePool(); return *p; } }
+namespace dsa { Prof& prof() { static Prof p; return p; } DevicePool& device_pool(int) { static DevicePool* p = new DevicePool(); return *p; } }
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
 
