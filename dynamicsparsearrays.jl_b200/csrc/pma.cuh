@@ -28,7 +28,7 @@ constexpr int SMALL_CELLS = 2048;
 
 enum : uint8_t { FL_OVERWRITE = 1, FL_DELETE = 2, FL_INSERT = 4 };
 enum { ST_OVER = 0, ST_UNDER = 1, ST_NINS = 2, ST_ROOT = 3, ST_NHIGH = 4, ST_ANYBIG = 5, ST_NACT = 6, ST_ANYHIGH = 7, ST_TICKET = 8, ST_NPEND = 9,
-       ST_WORDS = 16 };
+       ST_NBIG = 10, ST_MAXBIGH = 11, ST_WORDS = 16 };
 
 __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;
@@ -394,7 +394,8 @@ __global__ void __launch_bounds__(1024) k_tree_low(const int32_t* __restrict__ l
 // the queued leaves walk on, from level 1 (pma.jl:113-129).  Windows above leaf level are also appended (once) to a work list.
 __global__ void __launch_bounds__(256) k_select_pending(const int32_t* __restrict__ pending, const int32_t* __restrict__ post,
                                                          uint8_t* __restrict__ mark, Levels L, int64_t* __restrict__ status,
-                                                         int32_t* __restrict__ hi_h, int64_t* __restrict__ hi_w) {
+                                                         int32_t* __restrict__ hi_h, int64_t* __restrict__ hi_w,
+                                                         int32_t* __restrict__ big_h, int64_t* __restrict__ big_w) {
     const int64_t npend = status[ST_NPEND];
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < npend; q += (int64_t)gridDim.x * blockDim.x) {
         const int64_t l = pending[q];
@@ -411,7 +412,13 @@ __global__ void __launch_bounds__(256) k_select_pending(const int32_t* __restric
                     hi_h[slot] = h;
                     hi_w[slot] = l >> h;
                     status[ST_ANYHIGH] = 1;
-                    if (h > L.hsmall) status[ST_ANYBIG] = 1;
+                    if (h > L.hsmall) {   // too large for one CTA's shared memory: its own work list
+                        status[ST_ANYBIG] = 1;
+                        const unsigned long long bs = atomicAdd((unsigned long long*)&status[ST_NBIG], 1ull);
+                        big_h[bs] = h;
+                        big_w[bs] = l >> h;
+                        atomicMax((long long*)&status[ST_MAXBIGH], (long long)h);
+                    }
                 }
                 done = true;
             }
@@ -493,6 +500,8 @@ struct MergeArgs {
     const int32_t* hi_h;       // work list of windows above leaf level
     const int64_t* hi_w;
     const uint8_t* hi_max;
+    const int32_t* big_h;      // work list of the windows above SMALL_CELLS (list-driven big path)
+    const int64_t* big_w;
 };
 
 __device__ __forceinline__ int window_height(const uint8_t* __restrict__ mark, const Levels& L, int64_t l, int lane) {
@@ -502,16 +511,8 @@ __device__ __forceinline__ int window_height(const uint8_t* __restrict__ mark, c
     return b ? 31 - __clz(b) : -1;
 }
 
-__global__ void __launch_bounds__(256) k_merge_scatter(MergeArgs A, Levels L) {
-    const int64_t l = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (l >= L.nsegs) return;
-    int h;
-    if (A.root_mode) h = L.H;
-    else {
-        h = window_height(A.mark, L, l, lane);
-        if (h < A.min_h) return;
-    }
+// one leaf of a window of height h (lane = cell): survivors ranked and scattered to their spread! positions
+__device__ __forceinline__ void merge_scatter_leaf(const MergeArgs& A, const Levels& L, int64_t l, int h, int lane) {
     const int nins = A.inscnt[l];
     if (!A.root_mode && h == 0 && nins == 0) return;   // leaf accepted, nothing inserted: nothing moves (pma.jl:96-99)
     const int S = 1 << L.lgS;
@@ -568,6 +569,43 @@ __global__ void __launch_bounds__(256) k_merge_scatter(MergeArgs A, Levels L) {
     }
     // the leaf's inserts are placed by k_scatter_inserts (one thread per insert: a hot leaf may receive millions)
     if (!A.root_mode && h == 0 && lane == 0) A.leafcnt[l] = (int32_t)m;
+}
+
+// dense: one warp per leaf of the whole array (resize: every leaf belongs to the root window)
+__global__ void __launch_bounds__(256) k_merge_scatter(MergeArgs A, Levels L) {
+    const int64_t l = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (l >= L.nsegs) return;
+    int h;
+    if (A.root_mode) h = L.H;
+    else {
+        h = window_height(A.mark, L, l, lane);
+        if (h < A.min_h) return;
+    }
+    merge_scatter_leaf(A, L, l, h, lane);
+}
+
+// outermost = no marked ancestor (a window nested in a larger marked one is re-laid by that one)
+__device__ __forceinline__ bool window_is_outermost(const uint8_t* __restrict__ mark, const Levels& L, int h, int64_t w) {
+    for (int g = h + 1; g <= L.H; ++g)
+        if (mark[L.off[g] + (w >> (g - h))]) return false;
+    return true;
+}
+
+// list-driven: grid = (chunks, big windows).  Only the leaves of the listed windows are visited — a skewed batch marks a few
+// hundred windows of a few thousand cells in an array of tens of millions (the dense sweep cost 2 ms per batch at 2^25 cells).
+__global__ void __launch_bounds__(256) k_merge_scatter_big(MergeArgs A, Levels L) {
+    __shared__ int ok;
+    const int64_t i = blockIdx.y;
+    const int h = A.big_h[i];
+    const int64_t w = A.big_w[i];
+    if (threadIdx.x == 0) ok = window_is_outermost(A.mark, L, h, w);
+    __syncthreads();
+    if (!ok) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t nleaves = (int64_t)1 << h, first = w << h;
+    for (int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < nleaves; j += (int64_t)gridDim.x * (blockDim.x >> 5))
+        merge_scatter_leaf(A, L, first + j, h, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -774,15 +812,9 @@ __global__ void __launch_bounds__(256) k_scatter_inserts(MergeArgs A, Levels L, 
 }
 
 // windows of height >= 1: copy the shadow back, writing the analytic gaps and the new leaf counts
-__global__ void __launch_bounds__(256) k_copyback(int64_t* __restrict__ keys, double* __restrict__ vals,
-                                                   const int64_t* __restrict__ scr_k, const double* __restrict__ scr_v,
-                                                   const int32_t* __restrict__ post, const uint8_t* __restrict__ mark,
-                                                   int32_t* __restrict__ leafcnt, Levels L, int min_h) {
-    const int64_t l = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (l >= L.nsegs) return;
-    const int h = window_height(mark, L, l, lane);
-    if (h < 1 || h < min_h) return;
+__device__ __forceinline__ void copyback_leaf(int64_t* __restrict__ keys, double* __restrict__ vals, const int64_t* __restrict__ scr_k,
+                                              const double* __restrict__ scr_v, const int32_t* __restrict__ post,
+                                              int32_t* __restrict__ leafcnt, const Levels& L, int64_t l, int h, int lane) {
     const int S = 1 << L.lgS;
     const int64_t first_leaf = (l >> h) << h;
     const Spread sp = spread_make((int64_t)S << h, (int64_t)post[L.off[h] + (l >> h)]);
@@ -795,6 +827,34 @@ __global__ void __launch_bounds__(256) k_copyback(int64_t* __restrict__ keys, do
     }
     const unsigned b = __ballot_sync(0xffffffffu, live);
     if (lane == 0) leafcnt[l] = __popc(b);
+}
+__global__ void __launch_bounds__(256) k_copyback(int64_t* __restrict__ keys, double* __restrict__ vals,
+                                                   const int64_t* __restrict__ scr_k, const double* __restrict__ scr_v,
+                                                   const int32_t* __restrict__ post, const uint8_t* __restrict__ mark,
+                                                   int32_t* __restrict__ leafcnt, Levels L, int min_h) {
+    const int64_t l = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (l >= L.nsegs) return;
+    const int h = window_height(mark, L, l, lane);
+    if (h < 1 || h < min_h) return;
+    copyback_leaf(keys, vals, scr_k, scr_v, post, leafcnt, L, l, h, lane);
+}
+__global__ void __launch_bounds__(256) k_copyback_big(int64_t* __restrict__ keys, double* __restrict__ vals,
+                                                       const int64_t* __restrict__ scr_k, const double* __restrict__ scr_v,
+                                                       const int32_t* __restrict__ post, const uint8_t* __restrict__ mark,
+                                                       int32_t* __restrict__ leafcnt, Levels L, const int32_t* __restrict__ big_h,
+                                                       const int64_t* __restrict__ big_w) {
+    __shared__ int ok;
+    const int64_t i = blockIdx.y;
+    const int h = big_h[i];
+    const int64_t w = big_w[i];
+    if (threadIdx.x == 0) ok = window_is_outermost(mark, L, h, w);
+    __syncthreads();
+    if (!ok) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t nleaves = (int64_t)1 << h, first = w << h;
+    for (int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < nleaves; j += (int64_t)gridDim.x * (blockDim.x >> 5))
+        copyback_leaf(keys, vals, scr_k, scr_v, post, leafcnt, L, first + j, h, lane);
 }
 
 // recount (used after clone/import and by tests)
@@ -863,8 +923,8 @@ struct BatchWorkspace {   // per-handle scratch reused by every batch
     uint8_t* mark = nullptr;     // implicit tree
     uint8_t* touched = nullptr;  // per leaf
     uint8_t* cover = nullptr;    // per leaf
-    DBuf<int32_t> hi_h;
-    DBuf<int64_t> hi_w;
+    DBuf<int32_t> hi_h, big_h;
+    DBuf<int64_t> hi_w, big_w;
     DBuf<ActiveLeaf> act;
     DBuf<int64_t> shadow_k;
     DBuf<double> shadow_v;
@@ -963,7 +1023,9 @@ struct PmaCore {
         ws.hi_max.ensure((size_t)nsegs + 1);
         int32_t* pending = ws.pending.ensure((size_t)nsegs + 1);
         DSA_LAUNCH("tree_low", k_tree_low, grid_for(nsegs, 1024), 1024, 0, st, leafcnt.p, ws.inscnt, post, L, ws.touched, mark, status, pending);
-        DSA_LAUNCH("select_pending", k_select_pending, 148, 256, 0, st, pending, post, mark, L, status, hi_h, hi_w);
+        int32_t* big_h = ws.big_h.ensure((size_t)(nsegs >> (L.hsmall + 1)) + 2);
+        int64_t* big_w = ws.big_w.ensure((size_t)(nsegs >> (L.hsmall + 1)) + 2);
+        DSA_LAUNCH("select_pending", k_select_pending, 148, 256, 0, st, pending, post, mark, L, status, hi_h, hi_w, big_h, big_w);
         int64_t* hs = ws.h_status.ensure(ST_WORDS);
         DSA_CUDA(cudaMemcpyAsync(hs, status, ST_WORDS * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     }
@@ -1028,11 +1090,22 @@ struct PmaCore {
                 A.dst_k = ws.shadow_k.ensure((size_t)g.capacity);
                 A.dst_v = ws.shadow_v.ensure((size_t)g.capacity);
                 A.min_h = L.hsmall + 1;
-                DSA_LAUNCH("merge_scatter_big", k_merge_scatter, warp_grid, 256, 0, st, A, L);
+                A.big_h = ws.big_h.p;
+                A.big_w = ws.big_w.p;
+                const int64_t nbig = hs[ST_NBIG];
+                const bool listed = nbig > 0 && nbig <= 65535;   // grid.y limit; beyond it (never seen) the dense sweep still works
+                // chunks per window: ~2 leaves per warp for the largest window of the batch
+                const unsigned ychunks = (unsigned)std::min<int64_t>(2048, std::max<int64_t>(1, (int64_t(1) << hs[ST_MAXBIGH]) / 16));
+                if (listed) DSA_LAUNCH("merge_scatter_big", k_merge_scatter_big, dim3(ychunks, (unsigned)nbig), 256, 0, st, A, L);
+                else DSA_LAUNCH("merge_scatter_big", k_merge_scatter, warp_grid, 256, 0, st, A, L);
                 if (hs[ST_NINS] > 0)
                     DSA_LAUNCH("scatter_inserts_big", k_scatter_inserts, grid_for(hs[ST_NINS], 256), 256, 0, st, A, L, ws.status + ST_NINS);
-                DSA_LAUNCH("copyback_big", k_copyback, warp_grid, 256, 0, st, keys.p, vals.p, A.dst_k, A.dst_v, post, mark, leafcnt.p, L,
-                           L.hsmall + 1);
+                if (listed)
+                    DSA_LAUNCH("copyback_big", k_copyback_big, dim3(ychunks, (unsigned)nbig), 256, 0, st, keys.p, vals.p, A.dst_k, A.dst_v, post, mark,
+                               leafcnt.p, L, (const int32_t*)ws.big_h.p, (const int64_t*)ws.big_w.p);
+                else
+                    DSA_LAUNCH("copyback_big", k_copyback, warp_grid, 256, 0, st, keys.p, vals.p, A.dst_k, A.dst_v, post, mark, leafcnt.p, L,
+                               L.hsmall + 1);
             }
         }
         nnz = N;
