@@ -318,9 +318,17 @@ __global__ void __launch_bounds__(256) k_insert_leaf_info(const int64_t* __restr
         const int64_t pq = ins_pos[j - 1];
         if (((pq < 0 ? 0 : pq) >> lgS) == leaf) return;
     }
-    // the run of this leaf ends at the first insert whose predecessor lies in a later leaf (positions are sorted)
-    int64_t lo = j + 1, hi = n;
+    // the run of this leaf ends at the first insert whose predecessor lies in a later leaf (positions are sorted).  Runs are
+    // short (about one insert per touched leaf on uniform batches): look at the next few entries — the same cache line — before
+    // falling back to a binary search over the rest (skewed batches: thousands of inserts on one leaf)
     const int64_t leaf_end = (leaf + 1) << lgS;
+    int64_t lo = j + 1, hi = n;
+    int near = 0;
+    while (lo < n && near < 8 && ins_pos[lo] < leaf_end) {
+        ++lo;
+        ++near;
+    }
+    if (near < 8 || lo >= n) hi = lo;
     while (lo < hi) {
         const int64_t mid = (lo + hi) >> 1;
         if (ins_pos[mid] < leaf_end) lo = mid + 1;
