@@ -95,8 +95,10 @@ __device__ __forceinline__ int route_owner(const int64_t* __restrict__ sp, int n
 
 __global__ void __launch_bounds__(RT_THREADS) k_route_count(const int64_t* __restrict__ rows, const int64_t* __restrict__ cols, int64_t n,
                                                              RouteTables T, int32_t* __restrict__ tile_cnt, int64_t* __restrict__ bad_flag) {
+    // bad_flag[0]: a key < 1 (refused); bad_flag[1]: a key >= 2^32 (this rank's share travels as 24-byte triples instead of
+    // 16-byte {row << 32 | col, value} pairs)
     __shared__ int hist[2][DIST_MAX_RANKS];
-    int bad = 0;
+    int bad = 0, wide = 0;
     if (threadIdx.x < 2 * DIST_MAX_RANKS) (&hist[0][0])[threadIdx.x] = 0;
     __syncthreads();
     const int64_t base = (int64_t)blockIdx.x * RT_TILE;
@@ -107,6 +109,7 @@ __global__ void __launch_bounds__(RT_THREADS) k_route_count(const int64_t* __res
         if (i < n) {
             const int64_t c = cols[i], r = rows[i];
             if (c < 1 || r < 1) bad = 1;   // device contract: keys >= 1 (key 0 is the semaphore key, pcsr.jl:23)
+            if (((unsigned long long)c | (unsigned long long)r) >> 32) wide = 1;
             oc = route_owner(T.split[0], T.nsplit, c);
             orr = route_owner(T.split[1], T.nsplit, r);
         }
@@ -123,7 +126,8 @@ __global__ void __launch_bounds__(RT_THREADS) k_route_count(const int64_t* __res
             }
         }
     }
-    if (bad) *bad_flag = 1;
+    if (bad) bad_flag[0] = 1;
+    if (wide) bad_flag[1] = 1;
     __syncthreads();
     if (threadIdx.x < 2 * T.world) {
         const int o = threadIdx.x / T.world, d = threadIdx.x % T.world;
@@ -185,7 +189,12 @@ __host__ __device__ __forceinline__ int64_t region_word(int o, int src, int a, i
 // launch at 8 GPUs against 70 us at 2 (NVLink packets of 32 bytes), the limiter of the 8-GPU step.
 __global__ void __launch_bounds__(RT_THREADS) k_route_push(const int64_t* __restrict__ rows, const int64_t* __restrict__ cols,
                                                             const double* __restrict__ vals, int64_t n, RouteTables T,
-                                                            const int32_t* __restrict__ tile_off, PushTargets P, int64_t region_cap) {
+                                                            const int32_t* __restrict__ tile_off, PushTargets P, int64_t region_cap,
+                                                            int64_t* __restrict__ wide_flag) {
+    // every key of this rank's share fits 32 bits (the common case): {row << 32 | col, value} = 16 bytes per op and owner instead of 24.
+    // wide_flag[0] (from k_route_count) decides; wide_flag[1] <- what was used (the receivers' unpack reads it after the all-gather)
+    const bool packed = wide_flag && wide_flag[0] == 0;
+    if (wide_flag && blockIdx.x == 0 && threadIdx.x == 0) wide_flag[1] = packed ? 1 : 0;
     constexpr int NSEG = RT_ITEMS * (RT_THREADS / 32);
     // counts of every (slab j, warp w) per bin, then their exclusive prefix in (j, w) order = index order inside the tile
     __shared__ int wcnt[NSEG][2][DIST_MAX_RANKS];
@@ -254,8 +263,8 @@ __global__ void __launch_bounds__(RT_THREADS) k_route_push(const int64_t* __rest
             const int d = own[j][o];
             if (d < 0) continue;
             const int li = binstart[o][d] + wcnt[j * (RT_THREADS / 32) + w][o][d] + rk[j][o];
-            s_r[li] = r_[j];
-            s_c[li] = c_[j];
+            s_r[li] = packed ? (int64_t)(((unsigned long long)r_[j] << 32) | (unsigned long long)c_[j]) : r_[j];
+            if (!packed) s_c[li] = c_[j];
             s_v[li] = v_[j];
         }
         __syncthreads();
@@ -266,7 +275,7 @@ __global__ void __launch_bounds__(RT_THREADS) k_route_push(const int64_t* __rest
             const int64_t pos = toff[o][d] + (t - binstart[o][d]);
             int64_t* dst = P.base[d] + region_word(o, P.region[d], 0, T.world, region_cap) + pos;   // NVLink peer store (local when d == me)
             dst[0] = s_r[t];
-            dst[region_cap] = s_c[t];
+            if (!packed) dst[region_cap] = s_c[t];
             dst[2 * region_cap] = __double_as_longlong(s_v[t]);
         }
         __syncthreads();
@@ -284,12 +293,14 @@ __global__ void __launch_bounds__(256) k_dist_unpack(const int64_t* __restrict__
                                                       int64_t* __restrict__ out_cols1, double* __restrict__ out_vals1,
                                                       int64_t* __restrict__ n_out) {
     __shared__ int64_t off[DIST_MAX_RANKS + 1];
+    __shared__ int pk[DIST_MAX_RANKS];   // source s sent {row << 32 | col, value} pairs
     const int o = blockIdx.y;
     if (threadIdx.x == 0) {
         int64_t run = 0;
         for (int s = 0; s < world; ++s) {
             off[s] = run;
             run += counts[(int64_t)s * row_stride + o * world + me];
+            pk[s] = counts[(int64_t)s * row_stride + 2 * world + 2] != 0;
         }
         off[world] = run;
         if (blockIdx.x == 0) n_out[o] = run;
@@ -303,8 +314,9 @@ __global__ void __launch_bounds__(256) k_dist_unpack(const int64_t* __restrict__
         int s = 0;
         while (i >= off[s + 1]) ++s;
         const int64_t* src = rbuf + region_word(o, s, 0, world, region_cap) + (i - off[s]);
-        orows[i] = src[0];
-        ocols[i] = src[region_cap];
+        const int64_t a = src[0];
+        orows[i] = pk[s] ? (int64_t)((unsigned long long)a >> 32) : a;
+        ocols[i] = pk[s] ? (int64_t)((unsigned long long)a & 0xffffffffull) : src[region_cap];
         ovals[i] = __longlong_as_double(src[2 * region_cap]);
     }
 }

@@ -81,7 +81,7 @@ static void dist_setup_exchange(dsa_dmatrix* D, int64_t max_share, cudaStream_t 
     const int W = d->world;
     D->region_cap = std::max<int64_t>(max_share, 1);
     D->words_per_parity = (int64_t)2 * W * 3 * D->region_cap;
-    D->row_stride = 2 * W + 2;
+    D->row_stride = 2 * W + 4;   // 2 W send counts, bad-key flag, wide-key flag, packed flag (what the sender actually used), pad
     DSA_CUDA(cudaMalloc(&D->xbuf, (size_t)D->words_per_parity * 2 * 8));
     D->peer[d->rank] = D->xbuf;
     D->counts.ensure((size_t)W * D->row_stride);
@@ -175,8 +175,10 @@ static bool dist_exchange(dsa_dmatrix* D, const int64_t* d_rows, const int64_t* 
         int32_t* to = D->tile_off.ensure((size_t)ntiles * 2 * W);
         DSA_LAUNCH("route_count", k_route_count, (unsigned)ntiles, RT_THREADS, 0, st, d_rows, d_cols, n, T, tc, row + 2 * W);
         DSA_LAUNCH("route_scan", k_route_scan, (unsigned)(2 * W), 1024, 0, st, (const int32_t*)tc, ntiles, W, to, row);
+        // peer-memory transport: 16-byte ops when every key of the share fits 32 bits (decided on the device by k_route_count)
+        int64_t* wide = d->transport == 0 ? row + 2 * W + 1 : nullptr;
         DSA_LAUNCH("route_push", k_route_push, (unsigned)ntiles, RT_THREADS, 0, st, d_rows, d_cols, d_vals, n, T, (const int32_t*)to, P,
-                   D->region_cap);
+                   D->region_cap, wide);
     }
     // the one collective of the exchange: everybody's send counts (and the barrier behind which all peer stores are complete)
     dist_all_gather(d, row, D->counts.p, (size_t)D->row_stride, ncclInt64, st);

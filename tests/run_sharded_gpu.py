@@ -80,6 +80,8 @@ def run(m, n, nnz0, nb, nrounds, max_share, uneven, seed):
         hot = rng.random(nb) < 0.3
         I2[hot], J2[hot] = rng.integers(1, 12, hot.sum()), rng.integers(1, 9, hot.sum())
         V2 = np.where(rng.random(nb) < 0.3, 0.0, rng.integers(1, 9, nb).astype(float))
+        if rnd == 2:   # keys beyond 32 bits: the shares that hold them travel as 24-byte triples, the others stay packed (16 bytes)
+            J2[5], I2[nb // 2 + 9], V2[5], V2[nb // 2 + 9] = (1 << 40) + 7, (1 << 35) + 3, 2.0, 3.0
         lo, hi = rank * nb // world, (rank + 1) * nb // world
         if rnd % 2 == 0:   # device-resident share
             A.set_batch(torch.from_numpy(I2[lo:hi].copy()).to(dev), torch.from_numpy(J2[lo:hi].copy()).to(dev),
