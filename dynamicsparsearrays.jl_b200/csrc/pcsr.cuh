@@ -37,7 +37,7 @@ __device__ __forceinline__ int32_t live_lookup(const int64_t* __restrict__ live_
 
 // Grid-stride: the launch is sized from an upper bound when the op count only exists on the device (n_dev, distributed batches:
 // the receive counts of the exchange are never read by the host before this kernel runs); cs[CS_N] reports the count used.
-__global__ void __launch_bounds__(256) k_col_lookup(const int64_t* __restrict__ partkeys, const int64_t* __restrict__ inkeys,
+__global__ void __launch_bounds__(256, 6) k_col_lookup(const int64_t* __restrict__ partkeys, const int64_t* __restrict__ inkeys,
                                                      const double* __restrict__ vals, int64_t n_host, const int64_t* __restrict__ n_dev,
                                                      const int64_t* __restrict__ live_keys, const int32_t* __restrict__ live_slot,
                                                      int64_t nlive, const int32_t* __restrict__ keymap, int64_t keymap_min,

@@ -350,37 +350,53 @@ __global__ void __launch_bounds__(256) k_insert_leaf_info(const int64_t* __restr
 //                   level (the common case: pma.jl:120-123 with h = 0) -> marked on the spot; otherwise queued.
 //   k_select_pending  the queued leaves continue leaf -> root and mark the first window inside its density bounds.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_tree_low(const int32_t* __restrict__ leafcnt, const int32_t* __restrict__ inscnt,
-                                                    int32_t* __restrict__ post, Levels L, const uint8_t* __restrict__ touched,
-                                                    uint8_t* __restrict__ mark, int64_t* __restrict__ status, int32_t* __restrict__ pending) {
-    __shared__ int32_t s[1024];
+constexpr int TREE_LEAVES_PER_THREAD = 4, TREE_THREADS = 256, TREE_TILE = TREE_LEAVES_PER_THREAD * TREE_THREADS;   // 1024 leaves per CTA
+__global__ void __launch_bounds__(TREE_THREADS) k_tree_low(const int32_t* __restrict__ leafcnt, const int32_t* __restrict__ inscnt,
+                                                            int32_t* __restrict__ post, Levels L, const uint8_t* __restrict__ touched,
+                                                            uint8_t* __restrict__ mark, int64_t* __restrict__ status,
+                                                            int32_t* __restrict__ pending) {
+    __shared__ int32_t s[TREE_THREADS];
     __shared__ int is_last;
-    const int64_t idx = (int64_t)blockIdx.x * 1024 + threadIdx.x;
-    int32_t v = 0;
-    if (idx < L.nsegs) {
-        v = leafcnt[idx] + (inscnt ? inscnt[idx] : 0);
-        post[L.off[0] + idx] = v;
-        if (touched[idx]) {
-            if (L.mn[0] <= v && v <= L.mx[0]) {
-                mark[L.off[0] + idx] = 1;
-            } else {
-                const unsigned long long slot = atomicAdd((unsigned long long*)&status[ST_NPEND], 1ull);
-                pending[slot] = (int32_t)idx;
+    // a thread owns 4 consecutive leaves: levels 0..2 in registers, levels 3..10 in shared memory
+    const int64_t idx0 = ((int64_t)blockIdx.x * TREE_THREADS + threadIdx.x) * TREE_LEAVES_PER_THREAD;
+    int32_t v[TREE_LEAVES_PER_THREAD];
+#pragma unroll
+    for (int e = 0; e < TREE_LEAVES_PER_THREAD; ++e) {
+        const int64_t idx = idx0 + e;
+        v[e] = 0;
+        if (idx < L.nsegs) {
+            v[e] = leafcnt[idx] + (inscnt ? inscnt[idx] : 0);
+            post[L.off[0] + idx] = v[e];
+            if (touched[idx]) {
+                if (L.mn[0] <= v[e] && v[e] <= L.mx[0]) {
+                    mark[L.off[0] + idx] = 1;
+                } else {
+                    const unsigned long long slot = atomicAdd((unsigned long long*)&status[ST_NPEND], 1ull);
+                    pending[slot] = (int32_t)idx;
+                }
             }
         }
     }
-    s[threadIdx.x] = v;
+    const int32_t a = v[0] + v[1], b2 = v[2] + v[3];
+    if (L.H >= 1) {
+        const int64_t n1 = idx0 >> 1;
+        if (n1 < (L.nsegs >> 1)) post[L.off[1] + n1] = a;
+        if (n1 + 1 < (L.nsegs >> 1)) post[L.off[1] + n1 + 1] = b2;
+    }
+    int32_t t = a + b2;
+    if (L.H >= 2 && (idx0 >> 2) < (L.nsegs >> 2)) post[L.off[2] + (idx0 >> 2)] = t;
+    s[threadIdx.x] = t;
     __syncthreads();
     const int top = L.H < 10 ? L.H : 10;
-    for (int k = 1; k <= top; ++k) {
-        const int nk = 1024 >> k;
-        int32_t t = 0;
-        if ((int)threadIdx.x < nk) t = s[2 * threadIdx.x] + s[2 * threadIdx.x + 1];
+    for (int k = 3; k <= top; ++k) {
+        const int nk = TREE_TILE >> k;
+        int32_t u = 0;
+        if ((int)threadIdx.x < nk) u = s[2 * threadIdx.x] + s[2 * threadIdx.x + 1];
         __syncthreads();
         if ((int)threadIdx.x < nk) {
-            s[threadIdx.x] = t;
-            const int64_t node = (((int64_t)blockIdx.x * 1024) >> k) + threadIdx.x;
-            if (node < (L.nsegs >> k)) post[L.off[k] + node] = t;
+            s[threadIdx.x] = u;
+            const int64_t node = (((int64_t)blockIdx.x * TREE_TILE) >> k) + threadIdx.x;
+            if (node < (L.nsegs >> k)) post[L.off[k] + node] = u;
         }
         __syncthreads();
     }
@@ -393,7 +409,7 @@ __global__ void __launch_bounds__(1024) k_tree_low(const int32_t* __restrict__ l
     __threadfence();
     for (int k = 11; k <= L.H; ++k) {
         const int64_t nodes = L.nsegs >> k;
-        for (int64_t i = threadIdx.x; i < nodes; i += 1024)
+        for (int64_t i = threadIdx.x; i < nodes; i += TREE_THREADS)
             post[L.off[k] + i] = __ldcg(&post[L.off[k - 1] + 2 * i]) + __ldcg(&post[L.off[k - 1] + 2 * i + 1]);
         __syncthreads();
     }
@@ -438,27 +454,6 @@ __global__ void __launch_bounds__(256) k_select_pending(const int32_t* __restric
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) status[ST_ROOT] = post[L.off[L.H]];   // element count after the batch
-}
-
-// one CTA per listed window: outermost (no marked ancestor)?  then its leaves are covered by it
-__global__ void __launch_bounds__(128) k_cover_windows(const int32_t* __restrict__ hi_h, const int64_t* __restrict__ hi_w,
-                                                        const uint8_t* __restrict__ mark, Levels L, uint8_t* __restrict__ hi_max,
-                                                        uint8_t* __restrict__ cover) {
-    __shared__ int is_max;
-    const int64_t i = blockIdx.x;
-    const int h = hi_h[i];
-    const int64_t w = hi_w[i];
-    if (threadIdx.x == 0) {
-        int mx = 1;
-        for (int g = h + 1; g <= L.H; ++g)
-            if (mark[L.off[g] + (w >> (g - h))]) { mx = 0; break; }
-        is_max = mx;
-        hi_max[i] = (uint8_t)mx;
-    }
-    __syncthreads();
-    if (!is_max) return;
-    const int64_t first = w << h, n = (int64_t)1 << h;
-    for (int64_t j = threadIdx.x; j < n; j += blockDim.x) cover[first + j] = (uint8_t)(h + 1);
 }
 
 __device__ __forceinline__ int nth_set_bit(unsigned m, int n) {   // position of the n-th (0-based) set bit of m
@@ -507,7 +502,6 @@ struct MergeArgs {
     const int64_t* nact_dev;
     const int32_t* hi_h;       // work list of windows above leaf level
     const int64_t* hi_w;
-    const uint8_t* hi_max;
     const int32_t* big_h;      // work list of the windows above SMALL_CELLS (list-driven big path)
     const int64_t* big_w;
 };
@@ -699,18 +693,31 @@ __global__ void __launch_bounds__(256) k_leaf_merge(MergeArgs A, Levels L) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// K4 small windows (height >= 1, <= SMALL_CELLS cells): one CTA per listed outermost window.  The merged, ranked items
-// are scattered to their spread! offsets in shared memory, then the window is written back coalesced (pack! + spread!,
-// moves.jl:94-172, in one pass), with leaf counts and semaphore positions.
+// K4 windows above leaf level: one CTA per listed window.  Outermost windows mark their leaves as covered; those of at most
+// SMALL_CELLS cells are re-laid here: the merged, ranked items are scattered to their spread! offsets in shared memory, then the
+// window is written back coalesced (pack! + spread!, moves.jl:94-172, in one pass), with leaf counts and semaphore positions.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_window_small(MergeArgs A, Levels L) {
+__global__ void __launch_bounds__(256) k_window_small(MergeArgs A, Levels L, uint8_t* __restrict__ cover) {
     __shared__ int64_t sk[SMALL_CELLS];
     __shared__ double sv[SMALL_CELLS];
+    __shared__ int is_max;
     const int64_t i = blockIdx.x;
-    if (!A.hi_max[i]) return;
     const int h = A.hi_h[i];
-    if (h > L.hsmall) return;
     const int64_t w = A.hi_w[i];
+    // outermost (no marked ancestor)?  then its leaves are covered by it: k_leaf_merge (launched after this kernel) skips them
+    if (threadIdx.x == 0) {
+        int mx = 1;
+        for (int g = h + 1; g <= L.H; ++g)
+            if (A.mark[L.off[g] + (w >> (g - h))]) { mx = 0; break; }
+        is_max = mx;
+    }
+    __syncthreads();
+    if (!is_max) return;
+    {
+        const int64_t first = w << h, n = (int64_t)1 << h;
+        for (int64_t j = threadIdx.x; j < n; j += blockDim.x) cover[first + j] = (uint8_t)(h + 1);
+    }
+    if (h > L.hsmall) return;   // re-laid by the list-driven big path
     const int lgS = L.lgS, S = 1 << lgS;
     const int c = S << h;
     const int64_t m = A.post[L.off[h] + w];
@@ -923,7 +930,6 @@ struct BatchWorkspace {   // per-handle scratch reused by every batch
     DBuf<int64_t> ins_key, ins_pos;
     DBuf<double> ins_val;
     DBuf<int32_t> ins_first, post, pending;
-    DBuf<uint8_t> hi_max;
     // everything that must start a batch as zero lives in ONE block cleared by one memset:
     DBuf<uint8_t> zero_blk;
     int64_t* status = nullptr;   // ST_WORDS
@@ -1028,9 +1034,8 @@ struct PmaCore {
         int64_t* status = ws.status;
         int32_t* hi_h = ws.hi_h.ensure((size_t)nsegs + 1);
         int64_t* hi_w = ws.hi_w.ensure((size_t)nsegs + 1);
-        ws.hi_max.ensure((size_t)nsegs + 1);
         int32_t* pending = ws.pending.ensure((size_t)nsegs + 1);
-        DSA_LAUNCH("tree_low", k_tree_low, grid_for(nsegs, 1024), 1024, 0, st, leafcnt.p, ws.inscnt, post, L, ws.touched, mark, status, pending);
+        DSA_LAUNCH("tree_low", k_tree_low, grid_for(nsegs, TREE_TILE), TREE_THREADS, 0, st, leafcnt.p, ws.inscnt, post, L, ws.touched, mark, status, pending);
         int32_t* big_h = ws.big_h.ensure((size_t)(nsegs >> (L.hsmall + 1)) + 2);
         int64_t* big_w = ws.big_w.ensure((size_t)(nsegs >> (L.hsmall + 1)) + 2);
         DSA_LAUNCH("select_pending", k_select_pending, 148, 256, 0, st, pending, post, mark, L, status, hi_h, hi_w, big_h, big_w);
@@ -1047,7 +1052,6 @@ struct PmaCore {
         uint8_t* cover = ws.cover;
         int32_t* hi_h = ws.hi_h.p;
         int64_t* hi_w = ws.hi_w.p;
-        uint8_t* hi_max = ws.hi_max.p;
         int64_t* hs = ws.h_status.p;
         const int64_t N = (int64_t)(int32_t)(hs[ST_ROOT] & 0xffffffff);
         MergeArgs A;
@@ -1056,7 +1060,7 @@ struct PmaCore {
         A.post = post; A.mark = mark; A.inscnt = ws.inscnt; A.ins_first = ws.ins_first.p;
         A.ins_key = ws.ins_key.p; A.ins_val = ws.ins_val.p; A.ins_pos = ws.ins_pos.p;
         A.leafcnt = leafcnt.p; A.sem = d_sem;
-        A.cover = cover; A.hi_h = hi_h; A.hi_w = hi_w; A.hi_max = hi_max;
+        A.cover = cover; A.hi_h = hi_h; A.hi_w = hi_w;
         ensure_destpos(st);
         A.destpos = destpos.p;
         A.act = ws.act.p;
@@ -1082,8 +1086,9 @@ struct PmaCore {
             vals.swap(nv);
         } else {
             const int64_t nhigh = hs[ST_NHIGH];
-            if (nhigh > 0)
-                DSA_LAUNCH("cover_windows", k_cover_windows, (unsigned)nhigh, 128, 0, st, hi_h, hi_w, mark, L, hi_max, cover);
+            // windows above leaf level: cover marks + the small ones re-laid through shared memory, one CTA each (before the leaf
+            // merge, which skips covered leaves)
+            if (nhigh > 0) DSA_LAUNCH("window_small", k_window_small, (unsigned)nhigh, 256, 0, st, A, L, cover);
             // leaves accepted at their own level (the common case), in place
             const int leaves_per_warp = 32 >> L.lgS;
             const int64_t nact = hs[ST_NACT];
@@ -1091,8 +1096,6 @@ struct PmaCore {
                 const int64_t lm_warps = (nact + leaves_per_warp - 1) / leaves_per_warp;
                 DSA_LAUNCH("leaf_merge", k_leaf_merge, grid_for(lm_warps * 32, 256), 256, 0, st, A, L);
             }
-            // outermost windows of <= SMALL_CELLS cells: one CTA each, through shared memory
-            if (nhigh > 0) DSA_LAUNCH("window_small", k_window_small, (unsigned)nhigh, 256, 0, st, A, L);
             // bigger windows (rare: cascades): dense warp-per-leaf scatter into the shadow array + copy back
             if (hs[ST_ANYBIG]) {
                 A.dst_k = ws.shadow_k.ensure((size_t)g.capacity);

@@ -7,10 +7,10 @@ namespace dsa {
 
 // ---------------------------------------------------------------------------------------------
 // Exclusive prefix sum of int32 (three-phase: tile reduce -> scan of tile sums -> tile scan).
-// Tile = 256 threads x 8 items, 128-bit loads where aligned.  out may alias in.
+// Tile = 256 threads x 16 items.  out may alias in.
 // ---------------------------------------------------------------------------------------------
 constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_ITEMS = 16;   // 4096 items per tile: the look-back chain of a 1M-item scan is 245 tiles long
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 template <typename InT>
