@@ -1,6 +1,7 @@
 // libdsa — shared definitions: error type, device buffers, launch accounting.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -31,6 +32,12 @@ struct DsaError {
             throw ::dsa::DsaError{_code, std::string(#expr) + ": " + cudaGetErrorString(_e)};                      \
         }                                                                                                         \
     } while (0)
+
+// ---- NVTX range per C-ABI call (header-only NVTX v3: a no-op unless a tool is attached) ---------------
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 // ---- launch accounting + optional per-kernel event timing ----------------------------------
 struct ProfEntry {

@@ -281,7 +281,7 @@ struct dsa_matrix {
     DBuf<int64_t> d_ids;
 };
 
-#define DSA_TRY try {
+#define DSA_TRY try { ::dsa::NvtxRange _nvtx_range(__func__);
 #define DSA_CATCH                                                              \
     }                                                                          \
     catch (const DsaError& e) {                                                \

@@ -307,4 +307,103 @@ Base.:(*)(t::Transposed, v::VecLike) = _mul(t.array, true, _xs(v)..., size(t.arr
 Base.:(*)(v::VecLike, t::Transposed) = _mul(t.array, false, _xs(v)..., size(t.array, 1))                  # operations.jl:38-48
 Base.:(*)(v::VecLike, A::DynamicSparseMatrix) = _mul(A, true, _xs(v)..., size(A, 2))                      # operations.jl:50-60
 
+
+# ------------------------------------------------------------------------------------------ multi-GPU (include/dsa.h "multi-GPU")
+# One Julia process per GPU (e.g. under MPI.jl or Distributed).  A ShardedDynamicSparseMatrix is the same DynamicSparseMatrix
+# (matrix.jl:1-8) sharded by key range over the group; every method below is a collective: all ranks call it in the same order.
+# The 128-byte group id is drawn on rank 0 with dist_unique_id() and handed to the other ranks by the host program
+# (MPI.Bcast!, a file, a socket ...).
+export DistContext, ShardedDynamicSparseMatrix, dist_unique_id
+
+function dist_unique_id()
+    id = Vector{UInt8}(undef, 128)
+    _check(ccall((:dsa_dist_unique_id, libdsa), Cint, (Ptr{Cvoid},), id))
+    return id
+end
+
+mutable struct DistContext
+    h::Ptr{Cvoid}
+    rank::Int
+    world::Int
+    function DistContext(id::Vector{UInt8}, rank::Integer, world::Integer; device::Integer = rank)
+        _check(ccall((:dsa_set_device, libdsa), Cint, (Cint,), device))
+        h = Ref{Ptr{Cvoid}}()
+        _check(ccall((:dsa_dist_init, libdsa), Cint, (Ptr{Cvoid}, Cint, Cint, Ref{Ptr{Cvoid}}), id, rank, world, h))
+        c = new(h[], rank, world)
+        finalizer(x -> ccall((:dsa_dist_destroy, libdsa), Cint, (Ptr{Cvoid},), x.h), c)
+        return c
+    end
+end
+
+mutable struct ShardedDynamicSparseMatrix
+    h::Ptr{Cvoid}
+    ctx::DistContext          # keeps the group alive as long as the matrix
+    m::Int64
+    n::Int64
+    function ShardedDynamicSparseMatrix(ctx::DistContext, m::Integer, n::Integer; max_share::Integer,
+                                        row_split::Union{Nothing,Vector{Int64}} = nothing, col_split::Union{Nothing,Vector{Int64}} = nothing)
+        h = Ref{Ptr{Cvoid}}()
+        _check(ccall((:dsa_dmatrix_create, libdsa), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Int64, Ref{Ptr{Cvoid}}),
+                     ctx.h, m, n, row_split === nothing ? C_NULL : row_split, col_split === nothing ? C_NULL : col_split, max_share, h))
+        A = new(h[], ctx, m, n)
+        finalizer(x -> ccall((:dsa_dmatrix_destroy, libdsa), Cint, (Ptr{Cvoid},), x.h), A)
+        return A
+    end
+end
+Base.size(A::ShardedDynamicSparseMatrix) = (A.m, A.n)
+
+# dynamicsparse(I, J, V, m, n) over the group (matrix.jl:15-19): every rank passes ITS share of the global COO
+function dynamicsparse(ctx::DistContext, I::Vector{Int64}, J::Vector{Int64}, V::Vector{Float64}, m::Integer, n::Integer; max_share::Integer)
+    length(I) == length(J) == length(V) || throw(ArgumentError("rows, columns, and nonzeros do not have same length."))
+    A = ShardedDynamicSparseMatrix(ctx, m, n; max_share = max_share)
+    _check(ccall((:dsa_dmatrix_build_coo, libdsa), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int64, Cint),
+                 A.h, I, J, V, length(V), 0))
+    return A
+end
+
+# batched setindex! (matrix.jl:43-62): this rank's share of ONE global batch (op order: rank-major, then arrival)
+function set_batch!(A::ShardedDynamicSparseMatrix, rows::Vector{Int64}, cols::Vector{Int64}, vals::Vector{Float64})
+    length(rows) == length(cols) == length(vals) || throw(ArgumentError("rows, columns, and nonzeros do not have same length."))
+    _check(ccall((:dsa_dmatrix_set_batch, libdsa), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int64),
+                 A.h, rows, cols, vals, length(vals)))
+    return A
+end
+Base.setindex!(A::ShardedDynamicSparseMatrix, val, row::Integer, col::Integer) =
+    set_batch!(A, Int64[row], Int64[col], Float64[val])      # a collective of one op: the other ranks pass empty shares
+
+function Base.getindex(A::ShardedDynamicSparseMatrix, row::Integer, col::Integer)                         # matrix.jl:64-68
+    out = Ref{Float64}(0.0)
+    _check(ccall((:dsa_dmatrix_get_batch, libdsa), Cint, (Ptr{Cvoid}, Cint, Ref{Int64}, Ref{Int64}, Int64, Ref{Float64}),
+                 A.h, 0, Ref(Int64(row)), Ref(Int64(col)), 1, out))
+    return out[]
+end
+
+function _dmul(A::ShardedDynamicSparseMatrix, trans::Bool, x::Vector{Float64})                            # operations.jl:14-36
+    y = Vector{Float64}(undef, trans ? A.n : A.m)
+    _check(ccall((:dsa_dmatrix_spmv_dense, libdsa), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64, Ptr{Float64}, Int64),
+                 A.h, trans ? 1 : 0, x, length(x), y, length(y)))
+    return y
+end
+struct TransposedSharded; array::ShardedDynamicSparseMatrix; end
+Base.transpose(A::ShardedDynamicSparseMatrix) = TransposedSharded(A)
+Base.:(*)(A::ShardedDynamicSparseMatrix, x::Vector{Float64}) = _dmul(A, false, x)
+Base.:(*)(t::TransposedSharded, x::Vector{Float64}) = _dmul(t.array, true, x)
+
+function deletecolumn!(A::ShardedDynamicSparseMatrix, cols::Vector{Int64})                                # matrix.jl:95-102, same list on every rank
+    _check(ccall((:dsa_dmatrix_delete_columns, libdsa), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int64), A.h, cols, length(cols)))
+    return true
+end
+deletecolumn!(A::ShardedDynamicSparseMatrix, col::Integer) = deletecolumn!(A, Int64[col])
+function deleterow!(A::ShardedDynamicSparseMatrix, rows::Vector{Int64})                                   # matrix.jl:104-111
+    _check(ccall((:dsa_dmatrix_delete_rows, libdsa), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int64), A.h, rows, length(rows)))
+    return true
+end
+deleterow!(A::ShardedDynamicSparseMatrix, row::Integer) = deleterow!(A, Int64[row])
+
+function SparseArrays.nnz(A::ShardedDynamicSparseMatrix)                                                  # matrix.jl:91, summed over the shards
+    out = Vector{Int64}(undef, 8)
+    _check(ccall((:dsa_dmatrix_info, libdsa), Cint, (Ptr{Cvoid}, Ptr{Int64}), A.h, out))
+    return out[3]
+end
+
 end # module

@@ -17,11 +17,12 @@ COMPAT = {
     "double*": {"Ptr{Float64}", "Ref{Float64}"},
     "uint8_t*": {"Ptr{UInt8}", "Ref{UInt8}"},
     "void*": {"Ptr{Cvoid}"},
+    "const void*": {"Ptr{Cvoid}"},
     "char*": {"Ptr{UInt8}", "Cstring"},
-    "handle": {"Ptr{Cvoid}"},                 # dsa_vec_t* / dsa_matrix_t* (const or not)
+    "handle": {"Ptr{Cvoid}"},                 # dsa_vec_t* / dsa_matrix_t* / dsa_dist_t* / dsa_dmatrix_t* (const or not)
     "handle*": {"Ref{Ptr{Cvoid}}", "Ptr{Ptr{Cvoid}}"},
 }
-RET = {"int": "Cint", "const char*": "Cstring", "int64_t": "Int64"}
+RET = {"int": "Cint", "const char*": "Cstring", "int64_t": "Int64", "dsa_matrix_t*": "Ptr{Cvoid}"}
 
 
 def _header_decls():
@@ -39,8 +40,10 @@ def _header_decls():
             ty = ty.replace(" *", "*")
             stars = ty.count("*")
             base = ty.replace("*", "").strip()
-            if re.search(r"dsa_(vec|matrix)_t", base):
+            if re.search(r"dsa_(vec|matrix|dist|dmatrix)_t", base):
                 norm.append("handle" + "*" * (stars - 1))
+            elif base == "const void":
+                norm.append("const void" + "*" * stars)
             else:
                 norm.append(base + "*" * stars)
         decls[name] = (re.sub(r"\s+", " ", ret).replace(" *", "*"), norm)
