@@ -23,17 +23,23 @@ struct dsa_dmatrix {
     int64_t per[2] = {0, 0};         // widest shard (slice length of the SpMV gather buffer)
     dsa::RouteTables T{};
     int64_t region_cap = 0;          // = max_share
-    int64_t words_per_parity = 0;
-    int64_t* xbuf = nullptr;         // receive regions, both parities (plain cudaMalloc: exported through CUDA IPC)
+    int64_t words_per_parity = 0;    // words of one slot of the receive regions
+    int64_t* xbuf = nullptr;         // receive regions, DIST_SLOTS slots (plain cudaMalloc: exported through CUDA IPC)
     int64_t* peer[dsa::DIST_MAX_RANKS] = {nullptr};   // every rank's xbuf as mapped here (own = xbuf)
-    int64_t seq = 0;
-    int row_stride = 0;              // words per rank in the count matrix: 2 * world counts + bad-key flag + pad
+    int64_t seq = 0;                 // batches routed so far: batch s uses slot s % DIST_SLOTS
+    int row_stride = 0;              // words per rank in the count matrix: 2 * world counts + flags
+    struct Routed { int slot; int64_t n; int omask; };
+    std::vector<Routed> staged;      // routed (pushed) but not applied yet, oldest first: at most 2
+    cudaStream_t xst = nullptr;      // routing + peer stores run here, so that they overlap the previous batch's pipeline
+    cudaEvent_t ev_main = nullptr, ev_routed[3] = {nullptr, nullptr, nullptr};
     dsa::DBuf<int32_t> tile_cnt, tile_off;
     dsa::DBuf<int64_t> counts, rx_n, misc;
     dsa::HPinned<int64_t> h_counts, h_misc;
     dsa::DBuf<int64_t> rx_rows[2], rx_cols[2];
     dsa::DBuf<double> rx_vals[2];
     dsa::DBuf<int64_t> sendbuf;      // nccl transport: local staging in the receive-region layout
+    dsa::DBuf<int64_t> stg_r[3], stg_c[3];   // device copies of staged HOST shares, one set per slot
+    dsa::DBuf<double> stg_v[3];
     dsa::DBuf<double> ybuf, dtmp;
     dsa::DBuf<int64_t> itmp, itmp2;
     dsa::DBuf<double> ztmp;
@@ -43,11 +49,21 @@ struct dsa_dmatrix {
             for (int r = 0; r < ctx->world; ++r)
                 if (r != ctx->rank && peer[r]) cudaIpcCloseMemHandle(peer[r]);
         if (xbuf) cudaFree(xbuf);
+        if (xst) cudaStreamDestroy(xst);
+        if (ev_main) cudaEventDestroy(ev_main);
+        for (auto& e : ev_routed)
+            if (e) cudaEventDestroy(e);
         delete A;
     }
 };
 
 namespace dsa {
+
+// Receive regions, count matrices and send staging exist in 3 slots (batch s uses slot s % 3).  A rank may route batch s+1
+// while batch s is still being applied anywhere: its stores go to slot (s+1) % 3, whose last reader on any peer was the unpack
+// of batch s-2, and that unpack precedes the peer's contribution to the count all-gather of batch s-1, which this rank has
+// seen complete (it has returned from applying batch s-1) before it can route batch s+1.
+constexpr int DIST_SLOTS = 3;
 
 static void dist_all_gather(dsa_dist* d, const void* send, void* recv, size_t count, ncclDataType_t t, cudaStream_t st) {
     if (d->world == 1) {
@@ -82,12 +98,15 @@ static void dist_setup_exchange(dsa_dmatrix* D, int64_t max_share, cudaStream_t 
     D->region_cap = std::max<int64_t>(max_share, 1);
     D->words_per_parity = (int64_t)2 * W * 3 * D->region_cap;
     D->row_stride = 2 * W + 4;   // 2 W send counts, bad-key flag, wide-key flag, packed flag (what the sender actually used), pad
-    DSA_CUDA(cudaMalloc(&D->xbuf, (size_t)D->words_per_parity * 2 * 8));
+    DSA_CUDA(cudaMalloc(&D->xbuf, (size_t)D->words_per_parity * DIST_SLOTS * 8));
     D->peer[d->rank] = D->xbuf;
-    D->counts.ensure((size_t)W * D->row_stride);
-    D->h_counts.ensure((size_t)W * D->row_stride);
+    D->counts.ensure((size_t)DIST_SLOTS * W * D->row_stride);
+    D->h_counts.ensure((size_t)DIST_SLOTS * W * D->row_stride);
     D->rx_n.ensure(4);
-    DSA_CUDA(cudaMemsetAsync(D->counts.p, 0, (size_t)W * D->row_stride * 8, st));
+    DSA_CUDA(cudaMemsetAsync(D->counts.p, 0, (size_t)DIST_SLOTS * W * D->row_stride * 8, st));
+    DSA_CUDA(cudaStreamCreateWithFlags(&D->xst, cudaStreamNonBlocking));
+    DSA_CUDA(cudaEventCreateWithFlags(&D->ev_main, cudaEventDisableTiming));
+    for (auto& e : D->ev_routed) DSA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     const char* tr = getenv("DSA_DIST_TRANSPORT");
     int want_p2p = !(tr && std::string(tr) == "nccl");
     if (W > 1) {
@@ -140,58 +159,77 @@ static void dist_setup_exchange(dsa_dmatrix* D, int64_t max_share, cudaStream_t 
         D->rx_cols[o].ensure((size_t)bound);
         D->rx_vals[o].ensure((size_t)bound);
     }
-    if (d->transport == 1) D->sendbuf.ensure((size_t)D->words_per_parity);
+    if (d->transport == 1) D->sendbuf.ensure((size_t)D->words_per_parity * DIST_SLOTS);
 }
 
-// One round of the exchange: route this rank's (rows, cols, vals)[n] to the owners (orientations in omask), leave what this rank
-// receives in rx_{rows,cols,vals}[o] (rank-major, arrival order) with the counts in rx_n[o] (device).  Peer-memory transport:
-// nothing here waits for the host.  Returns true when the host already knows the receive counts (nccl transport): *hn0/*hn1.
-static bool dist_exchange(dsa_dmatrix* D, const int64_t* d_rows, const int64_t* d_cols, const double* d_vals, int64_t n, int omask,
-                          cudaStream_t st, int64_t* hn0, int64_t* hn1) {
+// First half of the exchange, on the routing stream: count, scan, and push this rank's (rows, cols, vals)[n] into the owners'
+// receive regions (orientations in omask).  Nothing here waits for the host or for a collective.
+static void dist_route(dsa_dmatrix* D, const int64_t* d_rows, const int64_t* d_cols, const double* d_vals, int64_t n, int omask) {
     dsa_dist* d = D->ctx;
     const int W = d->world;
     if (n > D->region_cap)
         throw DsaError{DSA_ERR_ARGUMENT, "batch share of " + std::to_string(n) + " updates exceeds max_share = " + std::to_string(D->region_cap)};
-    const int parity = (int)(D->seq & 1);
+    if (D->staged.size() >= 2) throw DsaError{DSA_ERR_ERROR, "two batches are already staged: call dsa_dmatrix_apply_staged first"};
+    cudaStream_t st = D->A->sh.st, xs = D->xst;
+    const int slot = (int)(D->seq % DIST_SLOTS);
     D->seq += 1;
+    DSA_CUDA(cudaEventRecord(D->ev_main, st));   // the share is ready in the handle's stream order
+    DSA_CUDA(cudaStreamWaitEvent(xs, D->ev_main, 0));
     RouteTables T = D->T;
     T.omask = omask;
-    int64_t* row = D->counts.p + (size_t)d->rank * D->row_stride;
-    DSA_CUDA(cudaMemsetAsync(row, 0, (size_t)D->row_stride * 8, st));
+    int64_t* row = D->counts.p + ((size_t)slot * W + d->rank) * D->row_stride;
+    DSA_CUDA(cudaMemsetAsync(row, 0, (size_t)D->row_stride * 8, xs));
     const int64_t ntiles = (n + RT_TILE - 1) / RT_TILE;
     PushTargets P;
     memset(&P, 0, sizeof(P));
     for (int r = 0; r < W; ++r) {
         if (d->transport == 0) {
-            P.base[r] = D->peer[r] + (size_t)parity * D->words_per_parity;
+            P.base[r] = D->peer[r] + (size_t)slot * D->words_per_parity;
             P.region[r] = d->rank;
         } else {
-            P.base[r] = D->sendbuf.p;
+            P.base[r] = D->sendbuf.p + (size_t)slot * D->words_per_parity;
             P.region[r] = r;
         }
     }
     if (n > 0) {
         int32_t* tc = D->tile_cnt.ensure((size_t)ntiles * 2 * W);
         int32_t* to = D->tile_off.ensure((size_t)ntiles * 2 * W);
-        DSA_LAUNCH("route_count", k_route_count, (unsigned)ntiles, RT_THREADS, 0, st, d_rows, d_cols, n, T, tc, row + 2 * W);
-        DSA_LAUNCH("route_scan", k_route_scan, (unsigned)(2 * W), 1024, 0, st, (const int32_t*)tc, ntiles, W, to, row);
+        DSA_LAUNCH("route_count", k_route_count, (unsigned)ntiles, RT_THREADS, 0, xs, d_rows, d_cols, n, T, tc, row + 2 * W);
+        DSA_LAUNCH("route_scan", k_route_scan, (unsigned)(2 * W), 1024, 0, xs, (const int32_t*)tc, ntiles, W, to, row);
         // peer-memory transport: 16-byte ops when every key of the share fits 32 bits (decided on the device by k_route_count)
         int64_t* wide = d->transport == 0 ? row + 2 * W + 1 : nullptr;
-        DSA_LAUNCH("route_push", k_route_push, (unsigned)ntiles, RT_THREADS, 0, st, d_rows, d_cols, d_vals, n, T, (const int32_t*)to, P,
+        DSA_LAUNCH("route_push", k_route_push, (unsigned)ntiles, RT_THREADS, 0, xs, d_rows, d_cols, d_vals, n, T, (const int32_t*)to, P,
                    D->region_cap, wide);
     }
-    // the one collective of the exchange: everybody's send counts (and the barrier behind which all peer stores are complete)
-    dist_all_gather(d, row, D->counts.p, (size_t)D->row_stride, ncclInt64, st);
-    int64_t* hc = D->h_counts.p;
-    DSA_CUDA(cudaMemcpyAsync(hc, D->counts.p, (size_t)W * D->row_stride * 8, cudaMemcpyDeviceToHost, st));   // read at the next host sync
+    DSA_CUDA(cudaEventRecord(D->ev_routed[slot], xs));
+    D->staged.push_back(dsa_dmatrix::Routed{slot, n, omask});
+}
+
+static int64_t* dist_host_counts(dsa_dmatrix* D, int slot) { return D->h_counts.p + (size_t)slot * D->ctx->world * D->row_stride; }
+
+// Second half, on the handle's stream: the count all-gather (the only collective of the exchange, and the barrier behind which
+// every peer's stores are complete) and the unpack of what this rank received into rx_{rows,cols,vals}[o] (rank-major, arrival
+// order) with the counts in rx_n[o] (device).  Returns true when the host already knows the receive counts (nccl transport).
+static bool dist_complete(dsa_dmatrix* D, const dsa_dmatrix::Routed& R, int64_t* hn0, int64_t* hn1) {
+    dsa_dist* d = D->ctx;
+    const int W = d->world;
+    cudaStream_t st = D->A->sh.st;
+    const int slot = R.slot;
+    DSA_CUDA(cudaStreamWaitEvent(st, D->ev_routed[slot], 0));
+    int64_t* cmat = D->counts.p + (size_t)slot * W * D->row_stride;
+    int64_t* row = cmat + (size_t)d->rank * D->row_stride;
+    dist_all_gather(d, row, cmat, (size_t)D->row_stride, ncclInt64, st);
+    int64_t* hc = dist_host_counts(D, slot);
+    DSA_CUDA(cudaMemcpyAsync(hc, cmat, (size_t)W * D->row_stride * 8, cudaMemcpyDeviceToHost, st));   // read at the next host sync
     if (d->transport == 0) {
-        DSA_LAUNCH("dist_unpack", k_dist_unpack, dim3(148 * 2, 2), 256, 0, st, (const int64_t*)D->counts.p, D->row_stride, W, d->rank,
-                   (const int64_t*)(D->xbuf + (size_t)parity * D->words_per_parity), D->region_cap, D->rx_rows[0].p, D->rx_cols[0].p,
+        DSA_LAUNCH("dist_unpack", k_dist_unpack, dim3(148 * 2, 2), 256, 0, st, (const int64_t*)cmat, D->row_stride, W, d->rank,
+                   (const int64_t*)(D->xbuf + (size_t)slot * D->words_per_parity), D->region_cap, D->rx_rows[0].p, D->rx_cols[0].p,
                    D->rx_vals[0].p, D->rx_rows[1].p, D->rx_cols[1].p, D->rx_vals[1].p, D->rx_n.p);
         return false;
     }
     // nccl transport: exact sizes need the counts on the host
     DSA_CUDA(cudaStreamSynchronize(st));
+    const int64_t* sendbuf = D->sendbuf.p + (size_t)slot * D->words_per_parity;
     int64_t tot[2] = {0, 0};
     if (W > 1) DSA_NCCL(nccl().GroupStart());
     for (int o = 0; o < 2; ++o) {
@@ -201,7 +239,7 @@ static bool dist_exchange(dsa_dmatrix* D, const int64_t* d_rows, const int64_t* 
             const int64_t sc = hc[(size_t)d->rank * D->row_stride + o * W + s];   // what I send s
             for (int a = 0; a < 3; ++a) {
                 int64_t* dst = (a == 0 ? D->rx_rows[o].p : a == 1 ? D->rx_cols[o].p : (int64_t*)D->rx_vals[o].p) + off;
-                const int64_t* src = D->sendbuf.p + region_word(o, s, a, W, D->region_cap);
+                const int64_t* src = sendbuf + region_word(o, s, a, W, D->region_cap);
                 if (s == d->rank) {
                     if (rc > 0) DSA_CUDA(cudaMemcpyAsync(dst, src, (size_t)rc * 8, cudaMemcpyDeviceToDevice, st));
                 } else {
@@ -219,22 +257,26 @@ static bool dist_exchange(dsa_dmatrix* D, const int64_t* d_rows, const int64_t* 
     return true;
 }
 
-static bool dist_any_bad_key(dsa_dmatrix* D) {
+static bool dist_any_bad_key(dsa_dmatrix* D, int slot) {
     const int W = D->ctx->world;
+    const int64_t* hc = dist_host_counts(D, slot);
     for (int s = 0; s < W; ++s)
-        if (D->h_counts.p[(size_t)s * D->row_stride + 2 * W]) return true;
+        if (hc[(size_t)s * D->row_stride + 2 * W]) return true;
     return false;
 }
 
-// routed batch: exchange + the per-GPU pipeline on what arrived
-static void dist_set_batch(dsa_dmatrix* D, const int64_t* d_rows, const int64_t* d_cols, const double* d_vals, int64_t n, int omask) {
+// the oldest routed batch: exchange completed + the per-GPU pipeline on what arrived
+static void dist_apply_staged(dsa_dmatrix* D) {
+    if (D->staged.empty()) throw DsaError{DSA_ERR_ERROR, "no staged batch"};
+    const dsa_dmatrix::Routed R = D->staged.front();
+    D->staged.erase(D->staged.begin());
     dsa_matrix* A = D->A;
-    cudaStream_t st = A->sh.st;
+    const int omask = R.omask;
     int64_t hn0 = 0, hn1 = 0;
-    const bool host_counts = dist_exchange(D, d_rows, d_cols, d_vals, n, omask, st, &hn0, &hn1);
+    const bool host_counts = dist_complete(D, R, &hn0, &hn1);
     const char* bad_msg = "row and column keys must be >= 1 (each is an in-array key of one orientation; key 0 is the semaphore key, pcsr.jl:23)";
     if (host_counts) {
-        if (dist_any_bad_key(D)) throw DsaError{DSA_ERR_ARGUMENT, bad_msg};   // every rank sees every flag: all of them throw
+        if (dist_any_bad_key(D, R.slot)) throw DsaError{DSA_ERR_ARGUMENT, bad_msg};   // every rank sees every flag: all of them throw
         if (hn0 > 0 || hn1 > 0)
             matrix_set_batch_two(A, D->rx_rows[0].p, D->rx_cols[0].p, D->rx_vals[0].p, (omask & 1) ? hn0 : 0, D->rx_rows[1].p, D->rx_cols[1].p,
                                  D->rx_vals[1].p, (omask & 2) ? hn1 : 0);
@@ -242,11 +284,19 @@ static void dist_set_batch(dsa_dmatrix* D, const int64_t* d_rows, const int64_t*
     }
     // counts live on the device: the pipeline runs on upper bounds until its own first host synchronisation
     const int64_t bound = (int64_t)D->ctx->world * D->region_cap;
+    const int slot = R.slot;
     std::function<void()> pre_mutate = [&] {
-        if (dist_any_bad_key(D)) throw DsaError{DSA_ERR_ARGUMENT, bad_msg};
+        if (dist_any_bad_key(D, slot)) throw DsaError{DSA_ERR_ARGUMENT, bad_msg};
     };
     matrix_set_batch_two(A, D->rx_rows[0].p, D->rx_cols[0].p, D->rx_vals[0].p, (omask & 1) ? bound : 0, D->rx_rows[1].p, D->rx_cols[1].p,
                          D->rx_vals[1].p, (omask & 2) ? bound : 0, D->rx_n.p, D->rx_n.p + 1, &pre_mutate);
+}
+
+// routed batch in one call
+static void dist_set_batch(dsa_dmatrix* D, const int64_t* d_rows, const int64_t* d_cols, const double* d_vals, int64_t n, int omask) {
+    if (!D->staged.empty()) throw DsaError{DSA_ERR_ERROR, "a staged batch is pending: call dsa_dmatrix_apply_staged first"};
+    dist_route(D, d_rows, d_cols, d_vals, n, omask);
+    dist_apply_staged(D);
 }
 
 static void dist_spmv(dsa_dmatrix* D, int trans, const double* d_x, int64_t nx, double* d_y, int64_t ny) {
@@ -513,7 +563,10 @@ int dsa_dmatrix_build_coo(dsa_dmatrix_t* D, const int64_t* rows, const int64_t* 
         int64_t* dc = h2d(A->stg.b, cols + a, b - a, st);
         double* dv = h2d(A->stg.v, vals + a, b - a, st);
         int64_t hn[2] = {0, 0};
-        const bool known = dist_exchange(D, dr, dc, dv, b - a, 3, st, &hn[0], &hn[1]);
+        dist_route(D, dr, dc, dv, b - a, 3);
+        const dsa_dmatrix::Routed R = D->staged.front();
+        D->staged.erase(D->staged.begin());
+        const bool known = dist_complete(D, R, &hn[0], &hn[1]);
         if (!known) {
             int64_t* h = D->h_misc.ensure(8);
             DSA_CUDA(cudaMemcpyAsync(h, D->rx_n.p, 16, cudaMemcpyDeviceToHost, st));
@@ -523,7 +576,7 @@ int dsa_dmatrix_build_coo(dsa_dmatrix_t* D, const int64_t* rows, const int64_t* 
         } else {
             DSA_CUDA(cudaStreamSynchronize(st));
         }
-        bad = bad || dist_any_bad_key(D);
+        bad = bad || dist_any_bad_key(D, R.slot);
         for (int o = 0; o < 2; ++o) {
             if (have[o] + hn[o] > room[o]) {   // grow geometrically, keeping what was received so far
                 const int64_t nr = std::max<int64_t>({2 * room[o], have[o] + hn[o], 1024});
@@ -556,6 +609,39 @@ int dsa_dmatrix_build_coo(dsa_dmatrix_t* D, const int64_t* rows, const int64_t* 
     DSA_CATCH
 }
 
+int dsa_dmatrix_stage_batch_d(dsa_dmatrix_t* D, const int64_t* d_rows, const int64_t* d_cols, const double* d_vals, int64_t n) {
+    DSA_TRY
+    dist_route(D, d_rows, d_cols, d_vals, std::max<int64_t>(n, 0), 3);
+    return DSA_OK;
+    DSA_CATCH
+}
+int dsa_dmatrix_stage_batch(dsa_dmatrix_t* D, const int64_t* rows, const int64_t* cols, const double* vals, int64_t n) {
+    DSA_TRY
+    n = std::max<int64_t>(n, 0);
+    if (n > D->region_cap)
+        throw DsaError{DSA_ERR_ARGUMENT, "batch share of " + std::to_string(n) + " updates exceeds max_share = " + std::to_string(D->region_cap)};
+    if (D->staged.size() >= 2) throw DsaError{DSA_ERR_ERROR, "two batches are already staged: call dsa_dmatrix_apply_staged first"};
+    const int slot = (int)(D->seq % DIST_SLOTS);
+    // the copies run on the routing stream: the previous user of this slot's staging buffers was the routing of batch seq - 3,
+    // on the same stream
+    int64_t* dr = D->stg_r[slot].ensure((size_t)std::max<int64_t>(n, 1));
+    int64_t* dc = D->stg_c[slot].ensure((size_t)std::max<int64_t>(n, 1));
+    double* dv = D->stg_v[slot].ensure((size_t)std::max<int64_t>(n, 1));
+    if (n > 0) {
+        DSA_CUDA(cudaMemcpyAsync(dr, rows, (size_t)n * 8, cudaMemcpyHostToDevice, D->xst));
+        DSA_CUDA(cudaMemcpyAsync(dc, cols, (size_t)n * 8, cudaMemcpyHostToDevice, D->xst));
+        DSA_CUDA(cudaMemcpyAsync(dv, vals, (size_t)n * 8, cudaMemcpyHostToDevice, D->xst));
+    }
+    dist_route(D, dr, dc, dv, n, 3);
+    return DSA_OK;
+    DSA_CATCH
+}
+int dsa_dmatrix_apply_staged(dsa_dmatrix_t* D) {
+    DSA_TRY
+    dist_apply_staged(D);
+    return DSA_OK;
+    DSA_CATCH
+}
 int dsa_dmatrix_set_batch_d(dsa_dmatrix_t* D, const int64_t* d_rows, const int64_t* d_cols, const double* d_vals, int64_t n) {
     DSA_TRY
     dist_set_batch(D, d_rows, d_cols, d_vals, std::max<int64_t>(n, 0), 3);

@@ -1053,14 +1053,17 @@ int dsa_trim_memory(void) {
 int64_t dsa_cached_bytes(void) { return (int64_t)device_pool(current_device()).cached_bytes; }
 int64_t dsa_launch_count(void) { return prof().launches; }
 int dsa_prof_enable(int on) {
+    if (!on) prof().resolve();
     prof().enabled = on != 0;
     return DSA_OK;
 }
 int dsa_prof_reset(void) {
+    prof().resolve();
     prof().entries.clear();
     return DSA_OK;
 }
 int64_t dsa_prof_dump(char* buf, int64_t cap) {
+    prof().resolve();
     std::string s;
     for (auto& kv : prof().entries) {
         char line[256];

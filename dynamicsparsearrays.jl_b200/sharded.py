@@ -164,6 +164,25 @@ class DistMatrix:
         rows, cols, vals = _i64(rows), _i64(cols), _f64(vals)
         check(lib().dsa_dmatrix_set_batch(self._h, _hp(rows), _hp(cols), _hp(vals), C.c_int64(len(vals))))
 
+    def stage_batch(self, rows, cols, vals):
+        """Route this rank's share of the NEXT global batch and push it into the owners' receive regions on a side stream;
+        returns at once.  apply_staged() applies the oldest staged batch: staging batch k+1 before applying batch k overlaps the
+        exchange with the kernels of batch k.  The arrays must stay alive until the matching apply_staged() has returned."""
+        self._staged = getattr(self, "_staged", [])
+        if isinstance(rows, torch.Tensor) and rows.is_cuda:
+            check(lib().dsa_dmatrix_stage_batch_d(self._h, _dp(rows), _dp(cols), _dp(vals), C.c_int64(rows.numel())))
+        elif isinstance(rows, torch.Tensor):    # pinned host tensors
+            check(lib().dsa_dmatrix_stage_batch(self._h, _dp(rows), _dp(cols), _dp(vals), C.c_int64(rows.numel())))
+        else:
+            rows, cols, vals = _i64(rows), _i64(cols), _f64(vals)
+            check(lib().dsa_dmatrix_stage_batch(self._h, _hp(rows), _hp(cols), _hp(vals), C.c_int64(len(vals))))
+        self._staged.append((rows, cols, vals))
+
+    def apply_staged(self):
+        check(lib().dsa_dmatrix_apply_staged(self._h))
+        if getattr(self, "_staged", None):
+            self._staged.pop(0)
+
     def spmv(self, x, trans=False, out=None):
         """y = A * x (x of length n) or transpose(A) * x; x replicated on every rank, y returned on every rank."""
         ny = self.n if trans else self.m

@@ -201,6 +201,14 @@ int dsa_dmatrix_build_local_d(dsa_dmatrix_t* D, int which, const int64_t* d_inke
  * batch whose op order is rank-major, then arrival within a rank: last writer wins in that order, 0.0 deletes. */
 int dsa_dmatrix_set_batch(dsa_dmatrix_t* D, const int64_t* rows, const int64_t* cols, const double* vals, int64_t n);
 int dsa_dmatrix_set_batch_d(dsa_dmatrix_t* D, const int64_t* d_rows, const int64_t* d_cols, const double* d_vals, int64_t n);
+/* The same batch in two halves, so that the exchange of batch k+1 overlaps the kernels of batch k (both collective):
+ * dsa_dmatrix_stage_batch[_d] routes the share and pushes it into the owners' receive regions on a side stream and returns at
+ * once (host buffers must stay valid, and should be pinned, until the matching apply returns; device buffers until it has been
+ * applied); dsa_dmatrix_apply_staged applies the oldest staged batch.  At most 2 batches staged; reads and products between
+ * the two calls see the matrix without the staged batch. */
+int dsa_dmatrix_stage_batch(dsa_dmatrix_t* D, const int64_t* rows, const int64_t* cols, const double* vals, int64_t n);
+int dsa_dmatrix_stage_batch_d(dsa_dmatrix_t* D, const int64_t* d_rows, const int64_t* d_cols, const double* d_vals, int64_t n);
+int dsa_dmatrix_apply_staged(dsa_dmatrix_t* D);
 /* mat * x (trans = 0) / transpose(mat) * x (trans = 1), x replicated on every rank, y (ny entries) returned on every rank:
  * each rank computes its slice from its row-major (col-major) shard into the gather buffer, one ncclAllGather (operations.jl:14-36) */
 int dsa_dmatrix_spmv_dense(dsa_dmatrix_t* D, int trans, const double* x, int64_t nx, double* y, int64_t ny);

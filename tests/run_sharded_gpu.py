@@ -83,11 +83,20 @@ def run(m, n, nnz0, nb, nrounds, max_share, uneven, seed):
         if rnd == 2:   # keys beyond 32 bits: the shares that hold them travel as 24-byte triples, the others stay packed (16 bytes)
             J2[5], I2[nb // 2 + 9], V2[5], V2[nb // 2 + 9] = (1 << 40) + 7, (1 << 35) + 3, 2.0, 3.0
         lo, hi = rank * nb // world, (rank + 1) * nb // world
-        if rnd % 2 == 0:   # device-resident share
+        if rnd % 3 == 0:   # device-resident share
             A.set_batch(torch.from_numpy(I2[lo:hi].copy()).to(dev), torch.from_numpy(J2[lo:hi].copy()).to(dev),
                         torch.from_numpy(V2[lo:hi].copy()).to(dev))
-        else:              # host share
+        elif rnd % 3 == 1:  # host share
             A.set_batch(I2[lo:hi], J2[lo:hi], V2[lo:hi])
+        else:              # the same batch in two halves: routed + pushed on the side stream, applied later
+            nnz_before = A.info()["nnz"]
+            if rnd % 2 == 0:
+                A.stage_batch(torch.from_numpy(I2[lo:hi].copy()).to(dev), torch.from_numpy(J2[lo:hi].copy()).to(dev),
+                              torch.from_numpy(V2[lo:hi].copy()).to(dev))
+            else:
+                A.stage_batch(I2[lo:hi].copy(), J2[lo:hi].copy(), V2[lo:hi].copy())
+            assert A.info()["nnz"] == nnz_before          # a staged batch is not visible yet
+            A.apply_staged()
         G.set_batch_policy(I2, J2, V2)
         mc, mr = owner_of(J2, cs) == rank, owner_of(I2, rs) == rank
         Gc.set_batch_policy(I2[mc], J2[mc], V2[mc])
@@ -159,8 +168,8 @@ def run(m, n, nnz0, nb, nrounds, max_share, uneven, seed):
     A.close()
 
 
-run(m=3000, n=2600, nnz0=120_000, nb=40_000, nrounds=4, max_share=60_000, uneven=False, seed=5)
-run(m=700, n=900, nnz0=30_000, nb=9_000, nrounds=3, max_share=max(4_000, -(-9_000 // world)), uneven=True, seed=6)   # several build rounds (few ranks), unequal shards
+run(m=3000, n=2600, nnz0=120_000, nb=40_000, nrounds=6, max_share=60_000, uneven=False, seed=5)
+run(m=700, n=900, nnz0=30_000, nb=9_000, nrounds=4, max_share=max(4_000, -(-9_000 // world)), uneven=True, seed=6)   # several build rounds (few ranks), unequal shards
 if rank == 0:
     print(f"sharded parity ok on {world} GPU(s), transport {ctx.info()['transport']}, nccl {ctx.info()['nccl_version']}")
 ctx.close()
