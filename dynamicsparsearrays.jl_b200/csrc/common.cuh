@@ -44,68 +44,39 @@ struct ProfEntry {
     int64_t count = 0;
     double ms = 0.0;
 };
-// Per-kernel timing (dsa_prof_enable): every launch is bracketed by two CUDA events on ITS stream; the events are only read
-// when the profile is dumped, so the kernels of a step still run back to back (a synchronisation after every launch made each
-// kernel start on an idle GPU and read ~15 us longer).  Kernels that overlap on two streams each see the shared GPU.
-struct ProfPending {
-    const char* name;
-    cudaEvent_t e0, e1;
-};
+// Per-kernel timing (dsa_prof_enable): every launch is bracketed by two CUDA events on its stream and waited for, so the
+// kernels of a step run ONE AT A TIME (no overlap of the two orientations' streams): the durations are those of each kernel
+// alone, comparable with an ncu launch list; their sum is larger than the step.
 struct Prof {
     bool enabled = false;
     int64_t launches = 0;
     std::map<std::string, ProfEntry> entries;
-    std::vector<ProfPending> pending;
-    std::vector<cudaEvent_t> free_events;
-    cudaEvent_t take() {
-        if (!free_events.empty()) {
-            cudaEvent_t e = free_events.back();
-            free_events.pop_back();
-            return e;
-        }
-        cudaEvent_t e = nullptr;
-        cudaEventCreate(&e);
-        return e;
-    }
-    void resolve() {   // after the device is idle: fold the pending brackets into the per-name totals
-        if (pending.empty()) return;
-        cudaDeviceSynchronize();
-        for (ProfPending& p : pending) {
-            float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) {
-                ProfEntry& e = entries[p.name];
-                e.count += 1;
-                e.ms += ms;
-            } else {
-                cudaGetLastError();
-            }
-            free_events.push_back(p.e0);
-            free_events.push_back(p.e1);
-        }
-        pending.clear();
-    }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    void resolve() {}
 };
 Prof& prof();
 
 struct LaunchScope {   // brackets ONE kernel launch
     const char* name;
     cudaStream_t st;
-    cudaEvent_t e0 = nullptr;
     LaunchScope(const char* n, cudaStream_t s) : name(n), st(s) {
         Prof& p = prof();
         p.launches += 1;
         if (p.enabled) {
-            e0 = p.take();
-            cudaEventRecord(e0, st);
+            if (!p.e0) { cudaEventCreate(&p.e0); cudaEventCreate(&p.e1); }
+            cudaEventRecord(p.e0, st);
         }
     }
     ~LaunchScope() {
-        if (e0) {
-            Prof& p = prof();
-            cudaEvent_t e1 = p.take();
-            cudaEventRecord(e1, st);
-            p.pending.push_back(ProfPending{name, e0, e1});
-            if (p.pending.size() >= 4096) p.resolve();   // bound the number of live events
+        Prof& p = prof();
+        if (p.enabled) {
+            cudaEventRecord(p.e1, st);
+            cudaEventSynchronize(p.e1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, p.e0, p.e1);
+            ProfEntry& e = p.entries[name];
+            e.count += 1;
+            e.ms += ms;
         }
     }
 };
