@@ -901,16 +901,28 @@ int dsa_matrix_spmv(dsa_matrix_t* A, int trans, const int64_t* x_keys, const dou
     Pcsr& P = trans ? A->colmajor : A->rowmajor;
     *count_out = 0;
     const int64_t dim = std::max<int64_t>(P.max_inkey, 1);
-    double* xd = A->ws.xdense.ensure((size_t)dim);
-    uint8_t* xm = A->ws.xmask.ensure((size_t)dim);
-    DSA_CUDA(cudaMemsetAsync(xd, 0, (size_t)dim * 8, st));
-    DSA_CUDA(cudaMemsetAsync(xm, 0, (size_t)dim, st));
-    if (nx > 0) {
+    // x as a dense buffer indexed by key (one load per cell) as long as the key space is not far larger than the data; beyond
+    // that (ids around 1e10 through a key codec: a dense x would not fit, the reference's Dict does) x stays a sorted list
+    // and every cell looks its key up by binary search
+    const bool lookup = dim > (int64_t(1) << 26) && dim > 16 * (nx + P.pma.nnz + 1);
+    if (lookup) {
+        for (int64_t i = 1; i < nx; ++i)
+            if (x_keys[i] <= x_keys[i - 1]) throw DsaError{DSA_ERR_ARGUMENT, "x keys must be strictly ascending"};
         int64_t* dk = h2d(A->stg.a, x_keys, nx, st);
         double* dv = h2d(A->stg.v, x_vals, nx, st);
-        DSA_LAUNCH("scatter_x", k_scatter_x, grid_for(nx, 256), 256, 0, st, dk, dv, nx, xd, xm, dim);
+        P.spmv_slots(A->ws, dv, nullptr, nx, st, dk);
+    } else {
+        double* xd = A->ws.xdense.ensure((size_t)dim);
+        uint8_t* xm = A->ws.xmask.ensure((size_t)dim);
+        DSA_CUDA(cudaMemsetAsync(xd, 0, (size_t)dim * 8, st));
+        DSA_CUDA(cudaMemsetAsync(xm, 0, (size_t)dim, st));
+        if (nx > 0) {
+            int64_t* dk = h2d(A->stg.a, x_keys, nx, st);
+            double* dv = h2d(A->stg.v, x_vals, nx, st);
+            DSA_LAUNCH("scatter_x", k_scatter_x, grid_for(nx, 256), 256, 0, st, dk, dv, nx, xd, xm, dim);
+        }
+        matrix_spmv_slots(A, trans, xd, xm, dim);
     }
-    matrix_spmv_slots(A, trans, xd, xm, dim);
     const int64_t ns = P.nslots();
     if (ns == 0) return DSA_OK;
     int32_t* flag = A->ws.flag32.ensure((size_t)ns);

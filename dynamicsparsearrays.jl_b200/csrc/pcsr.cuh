@@ -375,9 +375,13 @@ __device__ __forceinline__ void ldg_stream4(const double* p, double& a, double& 
     asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
 
-template <bool SPARSE_X, int C>
+// XMODE: 0 = dense x (x[key - 1], every entry stored); 1 = dense x + presence mask (a sparse x scattered into a dense buffer);
+// 2 = sparse x looked up by binary search in its ascending key list (xkeys[nx], x = the matching values): for key spaces far
+// larger than the number of entries (ids around 1e10 through a key codec), where a dense buffer would not fit.
+template <int XMODE, int C>
 __global__ void __launch_bounds__(256) k_spmv_blocked(const int64_t* __restrict__ keys, const double* __restrict__ vals, int64_t cap,
-                                                       const double* __restrict__ x, const uint8_t* __restrict__ xmask, int64_t nx,
+                                                       const double* __restrict__ x, const uint8_t* __restrict__ xmask,
+                                                       const int64_t* __restrict__ xkeys, int64_t nx,
                                                        double* __restrict__ yslot, int32_t* __restrict__ ycnt,
                                                        double* __restrict__ carry, int32_t* __restrict__ carry_cnt,
                                                        int32_t* __restrict__ chunk_last_slot, int64_t nchunks) {
@@ -413,19 +417,39 @@ __global__ void __launch_bounds__(256) k_spmv_blocked(const int64_t* __restrict_
         xv[c] = 0.0;
         xm[c] = 1;
     }
-    if (nx > 0) {   // warp-uniform
+    constexpr bool SPARSE_X = XMODE != 0;
+    if (nx > 0 && XMODE != 2) {   // warp-uniform
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const int64_t kk = k[c];
             const int64_t idx = (kk > 0 && kk <= nx) ? kk - 1 : 0;
             xv[c] = __ldg(x + idx);
-            if (SPARSE_X) xm[c] = __ldg(xmask + idx);
+            if (XMODE == 1) xm[c] = __ldg(xmask + idx);
+        }
+    }
+    if (XMODE == 2) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int64_t kk = k[c];
+            xm[c] = 0;
+            if (kk > 0) {
+                int64_t lo = 0, hi = nx;
+                while (lo < hi) {
+                    const int64_t mid = (lo + hi) >> 1;
+                    if (__ldg(xkeys + mid) < kk) lo = mid + 1;
+                    else hi = mid;
+                }
+                if (lo < nx && __ldg(xkeys + lo) == kk) {
+                    xm[c] = 1;
+                    xv[c] = __ldg(x + lo);
+                }
+            }
         }
     }
 #pragma unroll
     for (int c = 0; c < C; ++c) {
         const int64_t kk = k[c];
-        const bool present = kk > 0 && kk <= nx && xm[c] != 0;
+        const bool present = kk > 0 && (XMODE == 2 || kk <= nx) && xm[c] != 0;
         tcn[c] = present ? 1 : 0;
         if (kk > 0) t[c] = present ? __dmul_rn(xv[c], t[c]) : 0.0;
     }
@@ -716,8 +740,10 @@ struct Pcsr {
     }
 
     // Dense x: the product counts (only the sparse output needs them) are not computed.
+    // d_xkeys != nullptr: x = (d_xkeys, d_x)[nx] ascending, looked up by binary search (no dense buffer).
     template <int C>
-    void spmv_launch_blocked(PcsrWorkspace& ws, const double* d_x, const uint8_t* d_xmask, int64_t nx, cudaStream_t st) {
+    void spmv_launch_blocked(PcsrWorkspace& ws, const double* d_x, const uint8_t* d_xmask, int64_t nx, cudaStream_t st,
+                             const int64_t* d_xkeys = nullptr) {
         const int64_t cap = pma.g.capacity;
         const int64_t nchunks = (cap + 32 * C - 1) / (32 * C);
         const int64_t ns = nslots();
@@ -727,19 +753,24 @@ struct Pcsr {
         int32_t* ccnt = ws.carry_cnt.ensure((size_t)nchunks);
         int32_t* clast = ws.chunk_last.ensure((size_t)nchunks);
         const unsigned gr = grid_for(nchunks * 32, 256);
-        if (d_xmask) {
-            DSA_LAUNCH("spmv_blocked", (k_spmv_blocked<true, C>), gr, 256, 0, st, pma.keys.p, pma.vals.p, cap, d_x, d_xmask, nx, yslot, ycnt,
+        if (d_xkeys) {
+            DSA_LAUNCH("spmv_blocked", (k_spmv_blocked<2, C>), gr, 256, 0, st, pma.keys.p, pma.vals.p, cap, d_x, d_xmask, d_xkeys, nx, yslot, ycnt,
+                       carry, ccnt, clast, nchunks);
+            DSA_LAUNCH("spmv_fixup", k_spmv_fixup<true>, grid_for(nchunks, 256), 256, 0, st, yslot, ycnt, carry, ccnt, clast, nchunks);
+        } else if (d_xmask) {
+            DSA_LAUNCH("spmv_blocked", (k_spmv_blocked<1, C>), gr, 256, 0, st, pma.keys.p, pma.vals.p, cap, d_x, d_xmask, d_xkeys, nx, yslot, ycnt,
                        carry, ccnt, clast, nchunks);
             DSA_LAUNCH("spmv_fixup", k_spmv_fixup<true>, grid_for(nchunks, 256), 256, 0, st, yslot, ycnt, carry, ccnt, clast, nchunks);
         } else {
-            DSA_LAUNCH("spmv_blocked", (k_spmv_blocked<false, C>), gr, 256, 0, st, pma.keys.p, pma.vals.p, cap, d_x, d_xmask, nx, yslot, ycnt,
+            DSA_LAUNCH("spmv_blocked", (k_spmv_blocked<0, C>), gr, 256, 0, st, pma.keys.p, pma.vals.p, cap, d_x, d_xmask, d_xkeys, nx, yslot, ycnt,
                        carry, ccnt, clast, nchunks);
             DSA_LAUNCH("spmv_fixup", k_spmv_fixup<false>, grid_for(nchunks, 256), 256, 0, st, yslot, ycnt, carry, ccnt, clast, nchunks);
         }
     }
     // SpMV; results by slot in ws.yslot / ws.ycnt
-    void spmv_slots(PcsrWorkspace& ws, const double* d_x, const uint8_t* d_xmask, int64_t nx, cudaStream_t st) {
-        spmv_launch_blocked<4>(ws, d_x, d_xmask, nx, st);
+    void spmv_slots(PcsrWorkspace& ws, const double* d_x, const uint8_t* d_xmask, int64_t nx, cudaStream_t st,
+                    const int64_t* d_xkeys = nullptr) {
+        spmv_launch_blocked<4>(ws, d_x, d_xmask, nx, st, d_xkeys);
     }
 
     void clone_from(const Pcsr& o, cudaStream_t st) {

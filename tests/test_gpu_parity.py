@@ -661,3 +661,28 @@ def test_single_writes_keep_the_reference_layout():
     assert_matrix_equal(gm, sq)
     x = rng.random(n)
     assert _rel_close(gm.mul_dense(x), sq.mul_dense(x, m))
+
+
+def test_spmv_sparse_x_over_a_huge_key_space():
+    """ids around 1e10 (what a key codec for dates / UInt32 hashes produces): a dense x indexed by key would need tens of GB, the
+    reference's Dict accumulator does not care.  The library switches to a sorted-x lookup (binary search per cell); same result."""
+    rng = np.random.default_rng(77)
+    nnz = 6000
+    I, J = rng.integers(1, 30_000_000_000, nnz), rng.integers(1, 50_000_000_000, nnz)
+    J[: nnz // 2] = rng.choice(J[nnz // 2:], nnz // 2)        # columns with several entries
+    I[: nnz // 3] = rng.choice(I[nnz // 3:], nnz // 3)        # rows with several entries
+    V = rng.integers(1, 9, nnz).astype(float) / 4.0
+    gm, om = D.dynamicsparse(I, J, V), O.Matrix(I, J, V)
+    for trans, keys in ((False, J), (True, I)):
+        xk = np.unique(np.concatenate([rng.choice(keys, 1500), rng.integers(1, 50_000_000_000, 300)]))   # present and absent keys
+        xv = rng.integers(1, 5, len(xk)).astype(float)
+        y = (gm.T if trans else gm) @ (xk, xv)
+        yk, yv = om.mul(xk, xv, trans=trans)
+        assert np.array_equal(y.nzind, yk) and np.array_equal(y.nzval, yv)     # integer-valued data: exact
+    gm.set_batch(I[:50], J[:50], np.zeros(50))                                  # and after a dynamic batch
+    om.set_many(I[:50], J[:50], np.zeros(50))
+    xk = np.unique(rng.choice(J, 2000))
+    xv = rng.random(len(xk))
+    y = gm @ (xk, xv)
+    yk, yv = om.mul(xk, xv)
+    assert np.array_equal(y.nzind, yk) and _rel_close(y.nzval, yv)
