@@ -167,9 +167,12 @@ static void dist_setup_exchange(dsa_dmatrix* D, int64_t max_share, cudaStream_t 
 static void dist_route(dsa_dmatrix* D, const int64_t* d_rows, const int64_t* d_cols, const double* d_vals, int64_t n, int omask) {
     dsa_dist* d = D->ctx;
     const int W = d->world;
-    if (n > D->region_cap)
-        throw DsaError{DSA_ERR_ARGUMENT, "batch share of " + std::to_string(n) + " updates exceeds max_share = " + std::to_string(D->region_cap)};
     if (D->staged.size() >= 2) throw DsaError{DSA_ERR_ERROR, "two batches are already staged: call dsa_dmatrix_apply_staged first"};
+    // A share larger than the receive regions cannot be pushed.  The refusal must be COLLECTIVE (a rank that threw here alone
+    // would leave its peers waiting in the count all-gather): the rank routes nothing and raises its flag in the count row;
+    // every rank sees it after the all-gather and refuses the batch.
+    const bool oversize = n > D->region_cap;
+    if (oversize) n = 0;
     cudaStream_t st = D->A->sh.st, xs = D->xst;
     const int slot = (int)(D->seq % DIST_SLOTS);
     D->seq += 1;
@@ -200,6 +203,10 @@ static void dist_route(dsa_dmatrix* D, const int64_t* d_rows, const int64_t* d_c
         int64_t* wide = d->transport == 0 ? row + 2 * W + 1 : nullptr;
         DSA_LAUNCH("route_push", k_route_push, (unsigned)ntiles, RT_THREADS, 0, xs, d_rows, d_cols, d_vals, n, T, (const int32_t*)to, P,
                    D->region_cap, wide);
+    }
+    if (oversize) {
+        static const int64_t two = 2;
+        DSA_CUDA(cudaMemcpyAsync(row + 2 * W, &two, 8, cudaMemcpyHostToDevice, xs));
     }
     DSA_CUDA(cudaEventRecord(D->ev_routed[slot], xs));
     D->staged.push_back(dsa_dmatrix::Routed{slot, n, omask});
@@ -257,12 +264,19 @@ static bool dist_complete(dsa_dmatrix* D, const dsa_dmatrix::Routed& R, int64_t*
     return true;
 }
 
-static bool dist_any_bad_key(dsa_dmatrix* D, int slot) {
+// 0 = fine, 1 = some rank passed a key < 1, 2 = some rank passed a share larger than max_share (identical on every rank)
+static int dist_refusal(dsa_dmatrix* D, int slot) {
     const int W = D->ctx->world;
     const int64_t* hc = dist_host_counts(D, slot);
-    for (int s = 0; s < W; ++s)
-        if (hc[(size_t)s * D->row_stride + 2 * W]) return true;
-    return false;
+    int worst = 0;
+    for (int s = 0; s < W; ++s) worst = std::max(worst, (int)hc[(size_t)s * D->row_stride + 2 * W]);
+    return worst;
+}
+static void dist_throw_if_refused(dsa_dmatrix* D, int slot) {
+    const int r = dist_refusal(D, slot);
+    if (r == 2) throw DsaError{DSA_ERR_ARGUMENT, "a rank's share of the batch exceeds max_share = " + std::to_string(D->region_cap)};
+    if (r == 1)
+        throw DsaError{DSA_ERR_ARGUMENT, "row and column keys must be >= 1 (each is an in-array key of one orientation; key 0 is the semaphore key, pcsr.jl:23)"};
 }
 
 // the oldest routed batch: exchange completed + the per-GPU pipeline on what arrived
@@ -274,9 +288,8 @@ static void dist_apply_staged(dsa_dmatrix* D) {
     const int omask = R.omask;
     int64_t hn0 = 0, hn1 = 0;
     const bool host_counts = dist_complete(D, R, &hn0, &hn1);
-    const char* bad_msg = "row and column keys must be >= 1 (each is an in-array key of one orientation; key 0 is the semaphore key, pcsr.jl:23)";
     if (host_counts) {
-        if (dist_any_bad_key(D, R.slot)) throw DsaError{DSA_ERR_ARGUMENT, bad_msg};   // every rank sees every flag: all of them throw
+        dist_throw_if_refused(D, R.slot);   // every rank sees every flag: all of them throw
         if (hn0 > 0 || hn1 > 0)
             matrix_set_batch_two(A, D->rx_rows[0].p, D->rx_cols[0].p, D->rx_vals[0].p, (omask & 1) ? hn0 : 0, D->rx_rows[1].p, D->rx_cols[1].p,
                                  D->rx_vals[1].p, (omask & 2) ? hn1 : 0);
@@ -285,9 +298,7 @@ static void dist_apply_staged(dsa_dmatrix* D) {
     // counts live on the device: the pipeline runs on upper bounds until its own first host synchronisation
     const int64_t bound = (int64_t)D->ctx->world * D->region_cap;
     const int slot = R.slot;
-    std::function<void()> pre_mutate = [&] {
-        if (dist_any_bad_key(D, slot)) throw DsaError{DSA_ERR_ARGUMENT, bad_msg};
-    };
+    std::function<void()> pre_mutate = [&] { dist_throw_if_refused(D, slot); };
     matrix_set_batch_two(A, D->rx_rows[0].p, D->rx_cols[0].p, D->rx_vals[0].p, (omask & 1) ? bound : 0, D->rx_rows[1].p, D->rx_cols[1].p,
                          D->rx_vals[1].p, (omask & 2) ? bound : 0, D->rx_n.p, D->rx_n.p + 1, &pre_mutate);
 }
@@ -576,7 +587,7 @@ int dsa_dmatrix_build_coo(dsa_dmatrix_t* D, const int64_t* rows, const int64_t* 
         } else {
             DSA_CUDA(cudaStreamSynchronize(st));
         }
-        bad = bad || dist_any_bad_key(D, R.slot);
+        bad = bad || dist_refusal(D, R.slot) != 0;
         for (int o = 0; o < 2; ++o) {
             if (have[o] + hn[o] > room[o]) {   // grow geometrically, keeping what was received so far
                 const int64_t nr = std::max<int64_t>({2 * room[o], have[o] + hn[o], 1024});
@@ -618,9 +629,11 @@ int dsa_dmatrix_stage_batch_d(dsa_dmatrix_t* D, const int64_t* d_rows, const int
 int dsa_dmatrix_stage_batch(dsa_dmatrix_t* D, const int64_t* rows, const int64_t* cols, const double* vals, int64_t n) {
     DSA_TRY
     n = std::max<int64_t>(n, 0);
-    if (n > D->region_cap)
-        throw DsaError{DSA_ERR_ARGUMENT, "batch share of " + std::to_string(n) + " updates exceeds max_share = " + std::to_string(D->region_cap)};
     if (D->staged.size() >= 2) throw DsaError{DSA_ERR_ERROR, "two batches are already staged: call dsa_dmatrix_apply_staged first"};
+    if (n > D->region_cap) {   // refused collectively by the routing (every rank learns it from the count all-gather)
+        dist_route(D, nullptr, nullptr, nullptr, n, 3);
+        return DSA_OK;
+    }
     const int slot = (int)(D->seq % DIST_SLOTS);
     // the copies run on the routing stream: the previous user of this slot's staging buffers was the routing of batch seq - 3,
     // on the same stream

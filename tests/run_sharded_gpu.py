@@ -164,7 +164,15 @@ def run(m, n, nnz0, nb, nrounds, max_share, uneven, seed):
         raise AssertionError("key 0 must be refused")
     except D.ArgumentError:
         pass
+    try:   # a share larger than max_share on ONE rank: refused on every rank (the flag travels with the send counts)
+        big = max_share + 1 if rank == world - 1 else 0
+        A.set_batch(np.ones(big, np.int64), np.ones(big, np.int64), np.ones(big))
+        raise AssertionError("an oversize share must be refused")
+    except D.ArgumentError:
+        pass
     assert A.info()["nnz"] == nnz_before
+    x = rng.integers(0, 4, n).astype(float)
+    assert np.array_equal(A.spmv(x), G.mul_dense(x, m))       # the group is still in step after three refused collectives
     A.close()
 
 
