@@ -323,7 +323,10 @@ class Matrix(_Handle):
         if not (len(I) == len(J) == len(V)):
             raise OracleError(ERR_ARGUMENT, "rows, columns, and nonzeros do not have same length.")
         err = C.c_int()
-        given = m is not None
+        given = m is not None or n is not None
+        if given:   # each missing dimension defaults on its own: m = _guess_length(I), n = _guess_length(J)  (matrix.jl:15)
+            m = int(m) if m is not None else (int(I.max()) if len(I) else 0)
+            n = int(n) if n is not None else (int(J.max()) if len(J) else 0)
         h = lib().orc_mat_build(_p(I), _p(J), _p(V), C.c_int64(len(I)), C.c_int64(m or 0), C.c_int64(n or 0),
                                 C.c_int(1 if given else 0), C.c_int(combine), C.byref(err))
         _check(err.value)
