@@ -1106,7 +1106,9 @@ struct PmaCore {
                 const int64_t nbig = hs[ST_NBIG];
                 const bool listed = nbig > 0 && nbig <= 65535;   // grid.y limit; beyond it (never seen) the dense sweep still works
                 // chunks per window: ~2 leaves per warp for the largest window of the batch
-                const unsigned ychunks = (unsigned)std::min<int64_t>(2048, std::max<int64_t>(1, (int64_t(1) << hs[ST_MAXBIGH]) / 16));
+                // (and at most ~128k CTAs in all: many listed windows share the chunks of the largest one)
+                const int64_t want_chunks = std::min<int64_t>(2048, std::max<int64_t>(1, (int64_t(1) << hs[ST_MAXBIGH]) / 16));
+                const unsigned ychunks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want_chunks, (int64_t(1) << 17) / std::max<int64_t>(nbig, 1)));
                 if (listed) DSA_LAUNCH("merge_scatter_big", k_merge_scatter_big, dim3(ychunks, (unsigned)nbig), 256, 0, st, A, L);
                 else DSA_LAUNCH("merge_scatter_big", k_merge_scatter, warp_grid, 256, 0, st, A, L);
                 if (hs[ST_NINS] > 0)

@@ -103,13 +103,19 @@ def c3():
             M.deletecolumn(int(c))
 
     D.dynamicsparse([1], [1], [1.0])   # context warm-up
+    # first pass: warms the library's block pool (a cold process pays ~65 cudaMalloc calls of ~1.4 ms each: 0.7 s for the 10
+    # rounds against 0.2 s warm); the reported pass is the second one
+    cold = run(lambda I, J, V: D.dynamicsparse(I, J, V, m=m), lambda M, I, J, V: M.set_batch(I, J, V),
+               lambda M, d: D.deletecolumn(M, d) if len(d) else None, g_mul)
+    t_cold = cold[1] + cold[2]
+    del cold
     gm, tg, tgm, yg = run(lambda I, J, V: D.dynamicsparse(I, J, V, m=m), lambda M, I, J, V: M.set_batch(I, J, V),
                           lambda M, d: D.deletecolumn(M, d) if len(d) else None, g_mul)
     om, to, tom, yo = run(lambda I, J, V: O.Matrix(I, J, V, m=m), lambda M, I, J, V: M.set_many(I, J, V), o_del, o_mul)
     for (a1, a2), (b1, b2) in zip(yg, yo):
         assert np.allclose(a1, b1, rtol=1e-12) and np.allclose(a2, b2, rtol=1e-12)
     return {"config": "C3 column generation: 10 rounds x (append 10k cols x 50 nnz, deletecolumn! 5%, A*x and A'*pi), host buffers",
-            "gpu_Mupdates_s": upd / tg / 1e6, "cpu_Mupdates_s": upd / to / 1e6, "gpu_total_s": tg + tgm, "cpu_total_s": to + tom,
+            "gpu_Mupdates_s": upd / tg / 1e6, "cpu_Mupdates_s": upd / to / 1e6, "gpu_total_s": tg + tgm, "gpu_total_s_cold_process": t_cold, "cpu_total_s": to + tom,
             "gpu_spmv_pair_ms": 1e3 * tgm / rounds, "cpu_spmv_pair_ms": 1e3 * tom / rounds, "live_columns": len(live), "nnz": D.nnz(gm)}
 
 
