@@ -154,7 +154,7 @@ def main_dist(args, rank, world, local_rank):
     launches0 = L.dsa_launch_count()
     ms_first = timed(W, K)
     launches_first = L.dsa_launch_count() - launches0
-    R = int(min(400, max(1, np.ceil(args.min_timed_s * 1e3 / max(ms_first, 1e-3)))))
+    R = int(min(400, max(1, np.ceil(1.1 * args.min_timed_s * 1e3 / max(ms_first, 1e-3)) + 1)))   # the first repeat is the slowest
     ms_rest = timed(W + K, (R - 1) * K) if R > 1 else 0.0
     s_next = W + K * R
     launches = L.dsa_launch_count() - launches0
