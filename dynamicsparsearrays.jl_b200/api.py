@@ -776,7 +776,11 @@ def save_checkpoint(x, path):
         x._not_fillmode("Cannot checkpoint a matrix in fill mode")
         I, J, V = to_coo(x)
         m, n = x._dims()
-        np.savez_compressed(path, kind="matrix", rows=I, cols=J, vals=V, m=m, n=n)
+        ec, er = x.export(_lib.COLMAJOR), x.export(_lib.ROWMAJOR)
+        # live partitions, empty ones included (a column created by a zero write, or emptied entry by entry, stays a live
+        # partition: nbpartitions and deletecolumn! see it, test/functional/sparsematrix.jl:266-268)
+        np.savez_compressed(path, kind="matrix", rows=I, cols=J, vals=V, m=m, n=n,
+                            live_cols=ec["col_keys"][ec["col_live"].astype(bool)], live_rows=er["col_keys"][er["col_live"].astype(bool)])
     else:
         raise TypeError(type(x))
 
@@ -792,7 +796,16 @@ def load_checkpoint(path, key_codec=None, row_codec=None, col_codec=None):
     I, J, V = _i64(z["rows"]), _i64(z["cols"]), _f64(z["vals"])
     check(lib().dsa_matrix_build_coo(_p(I), _p(J), _p(V), C.c_int64(len(I)), C.c_int64(int(z["m"])), C.c_int64(int(z["n"])),
                                      C.c_int(1), C.c_int(_lib.COMBINE["+"]), C.byref(h)))
-    return DynamicSparseMatrix(h, row_codec=row_codec, col_codec=col_codec)
+    A = DynamicSparseMatrix(h, row_codec=row_codec, col_codec=col_codec)
+    if "live_cols" in z.files:   # re-create the live partitions that hold no entry: a zero write creates its column / row
+        lc, lr = _i64(z["live_cols"]), _i64(z["live_rows"])   # (pcsr.jl:341-347 calls addcolumn! before looking at the value)
+        ec = np.setdiff1d(lc, np.unique(J))
+        er = np.setdiff1d(lr, np.unique(I))
+        if len(ec) and len(lr):
+            check(lib().dsa_matrix_set_batch(A._h, _p(np.full(len(ec), lr[0], np.int64)), _p(ec), _p(np.zeros(len(ec))), C.c_int64(len(ec))))
+        if len(er) and len(lc):
+            check(lib().dsa_matrix_set_batch(A._h, _p(er), _p(np.full(len(er), lc[0], np.int64)), _p(np.zeros(len(er))), C.c_int64(len(er))))
+    return A
 
 
 class PackedCSC:

@@ -217,9 +217,14 @@ def test_checkpoint_roundtrip(backend, tmp_path):
     same = np.diff(c) == 0
     assert np.all(np.diff(r)[same] > 0)                              # ... ascending rows inside a column
     assert np.array_equal(A.get_batch(r, c), v)
-    D.save_checkpoint(A, tmp_path / "a.npz")
-    B = D.load_checkpoint(tmp_path / "a.npz")
+    A[7, 44] = 0.0                                                   # a zero write creates column 44 and keeps it empty
+    A[49, 3] = 0.0                                                   # ... and row 49
+    D.save_checkpoint(A, tmp_path / "a")                             # np.savez appends ".npz"
+    B = D.load_checkpoint(tmp_path / "a")
     assert B.size == A.size == (50, 45) and D.nnz(B) == D.nnz(A)
+    for o in ("colmajor", "rowmajor"):                               # live partitions, empty ones included
+        assert D.nbpartitions(getattr(B, o)) == D.nbpartitions(getattr(A, o))
+    D.deletecolumn(B, 44)                                            # the empty column is there to be deleted
     rb, cb, vb = D.to_coo(B)
     assert np.array_equal(r, rb) and np.array_equal(c, cb) and np.array_equal(v.view(np.int64), vb.view(np.int64))
     x = rng.integers(0, 8, 45).astype(float)     # exact arithmetic: the two layouts may sum a row in different orders
