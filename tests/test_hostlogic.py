@@ -175,3 +175,39 @@ def test_python_buffer_matches_reference_semantics():   # buffer.jl:10-50
                                                                       (5, 9, 1.0)])
 
 
+
+
+def test_bench_workload_is_periodic_and_distinct():
+    """bench.py's workload: the batches form a cycle (batch k deletes what batch k-1 inserted, the initial matrix holds the last
+    batch's inserts), so nnz is stationary and after every full cycle the stored keys are those of the start — checked here on
+    the CPU oracle at a reduced size with the same generator."""
+    import bench as B
+    from oracle import oracle as O
+    old = B.N_OVER
+    B.N_OVER = 200
+    try:
+        x, coo, batches, ins_only = B.make_workload(4, m=3000, n=3000, nnz0=20_000, nb=4000, seed=11)
+    finally:
+        B.N_OVER = old
+    lin = lambda i, j: (np.asarray(i) - 1) * 3000 + (np.asarray(j) - 1)
+    init = lin(coo[0], coo[1])
+    assert len(np.unique(init)) == len(init) == 20_000 - 200                # distinct (i, j); nnz0 - N_OVER entries
+    assert len(x) == 3000 and all(len(b[0]) == 4000 for b in batches)
+    M = O.Matrix(coo[0], coo[1], coo[2], m=3000, n=3000)
+    nnz0 = M.nnz()
+
+    def stored():
+        e = M.export(1)
+        mk = e["tag"].astype(bool) & (e["key"] > 0)
+        return int(mk.sum())
+
+    for rep in range(2):
+        for b in batches:
+            M.set_many(*b)
+            assert M.nnz() == nnz0                                          # stationary, batch after batch
+    assert stored() == M.nnz()
+    # the insert-only batch holds new entries only
+    assert len(np.intersect1d(lin(ins_only[0], ins_only[1]), init)) == 0
+    before = M.nnz()
+    M.set_many(*ins_only)
+    assert M.nnz() == before + 4000
