@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(256) k_bucket_scatter(const int32_t* __restric
 // land at the sorted index.  An op followed by a later write to the same (partition, key) is dead (last writer wins).
 // Overwrites store their value at once (a search reads keys only); deletes are applied by k_apply_compact, after every op
 // of the batch has been located.
-__global__ void __launch_bounds__(256) k_bucket_rank_locate(const BucketRec* __restrict__ rec, const int32_t* __restrict__ boff,
+__global__ void __launch_bounds__(256, 8) k_bucket_rank_locate(const BucketRec* __restrict__ rec, const int32_t* __restrict__ boff,
                                                              const int32_t* __restrict__ bcnt, int64_t n, const double* __restrict__ vals,
                                                              const int64_t* __restrict__ keys, double* __restrict__ cell_vals, int64_t cap,
                                                              const int64_t* __restrict__ sem, const int32_t* __restrict__ next_slot,

@@ -84,6 +84,9 @@ __global__ void __launch_bounds__(256) k_layout(int64_t* __restrict__ keys, doub
 // ---------------------------------------------------------------------------------------------
 // K6 find: the reference's gapped binary search (finds.jl:29-57), 0-based, one thread per query.
 // Returns the position of the exact hit or of the predecessor (-1 = none); *hit tells which.
+// (An 8-ary variant — 7 independent probes per round, 3 dependent rounds instead of 8 on a partition span — returned the same
+// positions and was slower: 79 us against 55 us for the bucket kernel at config 2, 13 M against 142 M finds/s on the 2^21-cell
+// vector: three times the loads at half the occupancy cost more than the shorter dependency chain saves.)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int64_t gapped_find(const int64_t* __restrict__ keys, int64_t key, int64_t from, int64_t to, bool* hit) {
     int64_t lo = from, hi = to;
