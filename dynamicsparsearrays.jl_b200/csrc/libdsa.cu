@@ -4,6 +4,7 @@
 #include <memory>
 #include <mutex>
 #include "pcsr.cuh"
+#include "tile.cuh"
 
 namespace dsa {
 
@@ -45,11 +46,50 @@ struct BatchCtx {
     const int64_t* n_dev = nullptr;    // device-side op count (distributed batches: the exchange's receive counts never visit the host)
     BatchStats bs{};
     std::vector<int32_t> new_slots_h;
+    bool tile = false;                 // tile-streamed batch (tile.cuh)
+    bool no_tile = false;              // the tile-streamed attempt was refused: general path
 };
 
+// Tile-streamed batches (tile.cuh): 0 = never, 1 = when the batch is dense enough to touch most leaves (default),
+// 2 = whenever the structure allows it (tests).  DSA_TILE overrides the default; dsa_set_tile_mode() changes it at run time.
+static int g_tile_mode = [] {
+    const char* e = getenv("DSA_TILE");
+    return e ? atoi(e) : 1;
+}();
+
+static bool tile_eligible(Pcsr& P, const BatchCtx& c) {
+    if (g_tile_mode == 0 || c.no_tile || c.n < 2) return false;
+    const Geometry& g = P.pma.g;
+    if (g.capacity < TILE_CELLS || g.segment_capacity < 8 || g.segment_capacity > 32 || P.nslots() == 0) return false;
+    const int64_t ntiles = g.capacity >> TILE_LG;
+    if (g_tile_mode >= 2) return c.n <= ntiles * TILE_CAP;
+    if (P.tile_penalty > 0) {   // a recent batch overflowed a tile bucket or created columns: do not pay for the attempt again at once
+        P.tile_penalty -= 1;
+        return false;
+    }
+    // below ~capacity/64 ops the random-access pipeline moves fewer bytes than one pass over the array; above TILE_CAP/2 ops
+    // per tile on average a bucket is likely to overflow
+    return c.n >= g.capacity / 64 && c.n <= ntiles * (TILE_CAP / 2);
+}
+
 static void phase1_launch(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t st) {
-    int32_t* op_slot = ws.op_slot.ensure((size_t)c.n);
     int64_t* hcs = ws.h_cs.ensure(CS_WORDS);
+    c.tile = tile_eligible(P, c);
+    if (c.tile) {
+        // one block, one memset: [batch statistics][per-tile op counters]
+        const int64_t ntiles = P.pma.g.capacity >> TILE_LG;
+        int32_t* blk = ws.bcnt.ensure((size_t)ntiles + 1 + 2 * CS_WORDS);
+        int64_t* cs = (int64_t*)blk;
+        TileRec* rec = ws.trec.ensure((size_t)ntiles * TILE_CAP);
+        DSA_CUDA(cudaMemsetAsync(blk, 0, ((size_t)ntiles + 1 + 2 * CS_WORDS) * 4, st));
+        const int32_t* next_slot = P.nslots() == P.nlive() ? nullptr : P.d_next_slot.p;   // no tombstones: the next slot is s + 1
+        DSA_LAUNCH("tile_assign", k_tile_assign, lookup_grid(c.n), 256, 0, st, c.partkeys, c.inkeys, c.vals, c.n, c.n_dev, P.d_live_keys.p,
+                   P.d_live_slot.p, P.nlive(), P.keymap(), P.keymap_min, P.keymap_len, P.pma.keys.p, P.pma.g.capacity, P.d_sem.p, next_slot,
+                   P.nslots(), cs, blk + 2 * CS_WORDS, rec);
+        DSA_CUDA(cudaMemcpyAsync(hcs, cs, CS_WORDS * 8, cudaMemcpyDeviceToHost, st));
+        return;
+    }
+    int32_t* op_slot = ws.op_slot.ensure((size_t)c.n);
     const int64_t ns = P.nslots();
     // one block, one memset: [batch statistics (zero = neutral, pcsr.cuh cs_code)][per-partition bucket counters]
     int32_t* blk = ws.bcnt.ensure((size_t)ns + 1 + 2 * CS_WORDS);
@@ -72,6 +112,17 @@ static void phase1_read(PcsrWorkspace& ws, BatchCtx& c) {
     }
 }
 
+// A tile-streamed attempt is refused when the batch creates columns or overflows a tile's bucket: nothing has been modified
+// (k_tile_assign only reads the structure), the batch starts over on the general path.  Returns true if it must be relaunched.
+static bool tile_refused(Pcsr& P, BatchCtx& c) {
+    if (!c.tile) return false;
+    if (c.bs.missing == 0 && c.bs.maxbucket <= TILE_CAP) return false;
+    c.tile = false;
+    c.no_tile = true;
+    P.tile_penalty = 8;
+    return true;
+}
+
 // Everything a batch can be refused for, checked on the statistics of phase 1 BEFORE phase1_finish creates columns: a failed
 // call leaves the structure unchanged (include/dsa.h).  The bounds are conservative: `missing` counts ops, not distinct keys.
 static void phase1_validate(const Pcsr& P, const BatchCtx& c, const char* what) {
@@ -82,7 +133,7 @@ static void phase1_validate(const Pcsr& P, const BatchCtx& c, const char* what) 
     if (slots_after >= (int64_t(1) << 31)) throw DsaError{DSA_ERR_ARGUMENT, "too many partitions"};
     const int kb = std::max(1, bits_for((uint64_t)std::max<int64_t>(c.bs.maxkey, P.max_inkey)));
     const int pb = std::max(1, bits_for((uint64_t)std::max<int64_t>(slots_after - 1, 1)));
-    if ((c.bs.missing > 0 || c.bs.maxbucket > BUCKET_MAX) && kb + pb > 64)   // the radix path packs (slot, key) into one 64-bit sort key
+    if (!c.tile && (c.bs.missing > 0 || c.bs.maxbucket > BUCKET_MAX) && kb + pb > 64)   // the radix path packs (slot, key) into one 64-bit sort key
         throw DsaError{DSA_ERR_ARGUMENT, "key range too wide: bits(max in-array key) + bits(#partitions) must be <= 64"};
 }
 
@@ -154,6 +205,33 @@ static void phase2_launch(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t 
     if (nnew) DSA_CUDA(cudaMemcpyAsync(d_new, c.new_slots_h.data(), (size_t)nnew * 4, cudaMemcpyHostToDevice, st));
     const int kb = std::max(1, bits_for((uint64_t)c.bs.maxkey));
     const int pb = std::max(1, bits_for((uint64_t)std::max<int64_t>(P.nslots() - 1, 1)));
+    if (c.tile) {
+        // one CTA per tile: locate, apply, re-lay the accepted leaves; then the shared tail (density tree, window selection)
+        P.pma.prepare_batch_scratch(ws.batch, 0, st);
+        ws.batch.ins_key.ensure((size_t)n + 1);
+        ws.batch.ins_val.ensure((size_t)n + 1);
+        ws.batch.ins_pos.ensure((size_t)n + 1);
+        P.pma.ensure_destpos(st);
+        static std::mutex attr_mu;
+        static std::map<int, bool> attr_set;
+        {
+            std::lock_guard<std::mutex> lock(attr_mu);
+            bool& done = attr_set[current_device()];
+            if (!done) {
+                DSA_CUDA(cudaFuncSetAttribute(k_tile_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
+                done = true;
+            }
+        }
+        TileArgs T;
+        T.keys = P.pma.keys.p; T.vals = P.pma.vals.p; T.rec = ws.trec.p; T.tcnt = ws.bcnt.p + 2 * CS_WORDS; T.sem = P.d_sem.p;
+        T.destpos = P.pma.destpos.p; T.leafcnt = P.pma.leafcnt.p; T.touched = ws.batch.touched; T.inscnt = ws.batch.inscnt;
+        T.ins_first = ws.batch.ins_first.p; T.ins_key = ws.batch.ins_key.p; T.ins_val = ws.batch.ins_val.p; T.ins_pos = ws.batch.ins_pos.p;
+        T.status = ws.batch.status;
+        const int64_t ntiles = P.pma.g.capacity >> TILE_LG;
+        DSA_LAUNCH("tile_merge", k_tile_merge, (unsigned)ntiles, TILE_THREADS, sizeof(TileSmem), st, T, P.pma.levels());
+        P.pma.rebalance_launch(ws.batch, st);
+        return;
+    }
     if (kb + pb > 64) throw DsaError{DSA_ERR_ARGUMENT, "key range too wide: bits(max in-array key) + bits(#partitions) must be <= 64"};
     const unsigned grt = grid_for(ntot, 256);
     int32_t* u_pid = ws.u_pid.ensure((size_t)ntot);
@@ -204,6 +282,11 @@ void Pcsr::set_batch_d(PcsrWorkspace& ws, const int64_t* d_inkeys, const int64_t
     phase1_launch(*this, ws, c, st);
     DSA_CUDA(cudaStreamSynchronize(st));
     phase1_read(ws, c);
+    if (tile_refused(*this, c)) {
+        phase1_launch(*this, ws, c, st);
+        DSA_CUDA(cudaStreamSynchronize(st));
+        phase1_read(ws, c);
+    }
     phase1_validate(*this, c, "in-array keys");
     if (max_part_nz) *max_part_nz = c.bs.maxpart_nz;
     if (max_key_nz) *max_key_nz = c.bs.maxkey_nz;
@@ -438,6 +521,15 @@ static void matrix_set_batch_two(dsa_matrix* A, const int64_t* rows_c, const int
         if (st2 != st) DSA_CUDA(cudaStreamSynchronize(st2));
         if (nc > 0) { phase1_read(A->ws, cc); nc = cc.n; }
         if (nr > 0) { phase1_read(A->ws2, cr); nr = cr.n; }
+        {   // a refused tile-streamed attempt starts over on the general path (nothing was modified)
+            const bool rc = nc > 0 && tile_refused(A->colmajor, cc), rr = nr > 0 && tile_refused(A->rowmajor, cr);
+            if (rc) phase1_launch(A->colmajor, A->ws, cc, st);
+            if (rr) phase1_launch(A->rowmajor, A->ws2, cr, st2);
+            if (rc) DSA_CUDA(cudaStreamSynchronize(st));
+            if (rr) DSA_CUDA(cudaStreamSynchronize(st2));
+            if (rc) phase1_read(A->ws, cc);
+            if (rr) phase1_read(A->ws2, cr);
+        }
         if (pre_mutate) (*pre_mutate)();   // caller-side validation that needs the first host synchronisation (may throw: nothing is mutated yet)
         // validate before mutate: rows are the in-array keys of the col-major structure, columns those of the row-major one
         // (both orientations are checked before either one creates a column)
@@ -1064,6 +1156,11 @@ int dsa_trim_memory(void) {
 }
 int64_t dsa_cached_bytes(void) { return (int64_t)device_pool(current_device()).cached_bytes; }
 int64_t dsa_launch_count(void) { return prof().launches; }
+int dsa_set_tile_mode(int mode) {
+    const int prev = g_tile_mode;
+    g_tile_mode = mode;
+    return prev;
+}
 int dsa_prof_enable(int on) {
     if (!on) prof().resolve();
     prof().enabled = on != 0;

@@ -584,6 +584,21 @@ __global__ void __launch_bounds__(256) k_scatter_x(const int64_t* __restrict__ x
     }
 }
 
+// ---- tile-streamed batches (tile.cuh): geometry of a tile and the record an op is bucketed as ----
+constexpr int TILE_LG = 11, TILE_CELLS = 1 << TILE_LG;   // 2048 cells = 32 KB of keys + values
+constexpr int TILE_CAP = 512;                             // ops a tile's bucket holds
+constexpr int TILE_THREADS = 256;
+constexpr int TILE_MAX_LEAVES = TILE_CELLS / 8;           // segment capacity >= 8
+
+struct __align__(16) TileRec {   // 32 B: one sector per op
+    int64_t key;     // in-array key
+    double val;
+    uint32_t arr;    // arrival index in the batch (last writer wins)
+    int32_t slot;
+    uint16_t lo, hi; // tile-local search range (inclusive); lo > hi = empty span: the predecessor is the cell at hi
+    uint32_t pad;
+};
+
 // =============================================================================================
 // MappedPackedCSC on the device
 // =============================================================================================
@@ -592,6 +607,7 @@ struct PcsrWorkspace {
     SortWorkspace sort;
     DBuf<int32_t> op_slot, flag32, idx32, u_pid, new_slots, old2new, rank32, del_slots, cnt32, bcnt, boff, lidx, bslot;
     DBuf<BucketRec> brec;
+    DBuf<TileRec> trec;          // tile buckets of a tile-streamed batch: TILE_CAP records per tile
     DBuf<int64_t> miss_keys, cs, u_key, live_pos, nuniq, tmp_k, tmp_owner, del_keys;
     DBuf<double> u_val, tmp_v, yslot, carry, xdense;
     DBuf<uint64_t> sk;
@@ -620,6 +636,7 @@ struct Pcsr {
     int64_t keymap_min = 0, keymap_len = 0;
     std::vector<int32_t> next_slot_h;
     int64_t max_inkey = 0;      // upper bound of the in-array keys ever stored (sizes the dense x of SpMV)
+    int tile_penalty = 0;       // batches to wait before the next tile-streamed attempt (after a refused one)
 
     const int32_t* keymap() const { return keymap_len > 0 ? d_keymap.p : nullptr; }
     int64_t nslots() const { return (int64_t)slot_key.size(); }

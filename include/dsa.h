@@ -230,6 +230,14 @@ int dsa_dmatrix_info(dsa_dmatrix_t* D, int64_t* out8);
 int dsa_trim_memory(void);
 int64_t dsa_cached_bytes(void);
 
+/* ---------------------------------------------------------------- tuning --------------- */
+/* How a batched setindex! of a matrix orientation (pcsr.jl:341-347 per op) is applied.  0: always the random-access pipeline
+ * (per-partition buckets / radix sort, locate in HBM, leaf merge).  1 (default): batches of at least capacity/64 ops are
+ * tile-streamed (one pass over the array, every op located and every accepted leaf re-laid in shared memory); a batch that
+ * creates columns or overflows a tile's bucket starts over on the random-access pipeline.  2: tile-streamed whenever the
+ * structure allows it (tests).  Both pipelines leave the same layout, bit for bit.  Returns the previous mode. */
+int dsa_set_tile_mode(int mode);
+
 /* ---------------------------------------------------------------- measurement ---------- */
 /* kernel launches issued by this library since load (bench.py's gpu_launches) */
 int64_t dsa_launch_count(void);
