@@ -130,7 +130,6 @@ __global__ void __launch_bounds__(256, 6) k_tile_assign(const int64_t* __restric
 
 // the reference's gapped binary search (finds.jl:29-57) on the tile in shared memory: position of the hit or of the predecessor
 __device__ __forceinline__ int tile_find(const int64_t* sk, int64_t key, int lo, int hi, bool* hit) {
-    const int from = lo;
     while (lo <= hi) {
         const int mid = (lo + hi) >> 1;
         int i = mid;
@@ -150,7 +149,6 @@ __device__ __forceinline__ int tile_find(const int64_t* sk, int64_t key, int lo,
             return i;
         }
     }
-    (void)from;
     *hit = false;
     int i = hi;
     while (i > 0 && sk[i] == GAP_KEY) --i;   // finds.jl:49-56 (the predecessor lies in this tile by construction)
@@ -164,21 +162,19 @@ struct TileSmem {
     double sv[TILE_CELLS];
     int64_t rkey[TILE_CAP];
     double rval[TILE_CAP];
-    uint32_t claim[TILE_CELLS];   // per cell: 1 + arrival of the last op that hits it
     uint32_t rarr[TILE_CAP];
     int32_t rslot[TILE_CAP];
-    int lcnt[TILE_MAX_LEAVES];    // per leaf: ops that miss (insert candidates and deletes of absent keys)
-    int ndel[TILE_MAX_LEAVES];    // per leaf: cells blanked
-    uint16_t rpos[TILE_CAP];      // tile-local position of the hit / predecessor; bit 15 = hit
-    uint16_t rli[TILE_CAP];       // index inside the leaf's list, later the merged rank
-    uint16_t llist[TILE_CAP];     // misses grouped by leaf
-    uint16_t loff[TILE_MAX_LEAVES];
-    uint16_t alist[TILE_MAX_LEAVES];   // leaves with misses
-    uint8_t rstat[TILE_CAP];      // 1 = live insert
-    uint8_t dvf[TILE_MAX_LEAVES]; // leaf has an overwritten value
-    uint8_t mrg[TILE_MAX_LEAVES]; // leaf was re-laid
-    int wtot[8];
-    int nactive;
+    // per leaf
+    uint32_t live[TILE_MAX_LEAVES];   // cells stored before the batch
+    uint32_t del[TILE_MAX_LEAVES];    // cells blanked by the batch
+    uint32_t ovw[TILE_MAX_LEAVES];    // cells whose value is overwritten
+    uint32_t insm[TILE_MAX_LEAVES];   // merged ranks taken by the inserts (leaves re-laid here)
+    int nins[TILE_MAX_LEAVES];        // inserts of the leaf
+    int lhead[TILE_MAX_LEAVES];       // first op of the leaf's list (-1 = none)
+    // per op
+    uint16_t rpos[TILE_CAP];          // tile-local position of the hit / predecessor; bit 15 = hit
+    int16_t rnext[TILE_CAP];          // next op of the same leaf (-1 = end)
+    uint8_t rstat[TILE_CAP];          // 1 = live insert
 };
 
 struct TileArgs {
@@ -187,7 +183,7 @@ struct TileArgs {
     const TileRec* rec;
     const int32_t* tcnt;
     int64_t* sem;
-    const uint8_t* destpos;
+    const uint8_t* destpos;   // [33][32]: spread! offset of rank r when a leaf holds m elements
     int32_t* leafcnt;
     uint8_t* touched;
     int32_t* inscnt;
@@ -198,7 +194,23 @@ struct TileArgs {
     int64_t* status;
 };
 
-__global__ void __launch_bounds__(TILE_THREADS, 3) k_tile_merge(TileArgs A, Levels L) {
+// number of the leaf's live inserts ordered before (pp, key): inserts go by (predecessor cell, key)
+__device__ __forceinline__ int tile_insert_rank(const TileSmem& s, int head, int pp, int64_t key) {
+    int rk = 0;
+    for (int o = head; o >= 0; o = s.rnext[o]) {
+        if (s.rstat[o]) {
+            const int po = s.rpos[o] & 0x7fff;
+            rk += (po < pp) || (po == pp && s.rkey[o] < key);
+        }
+    }
+    return rk;
+}
+
+// Control flow is data-parallel throughout: cell phases run one lane per cell (rows of 32 cells = 32/S leaves), op phases one
+// thread per op; an op only ever walks the list of the ops of its own leaf (one or two entries on a uniform batch).
+// Cells are only READ from shared memory: everything a leaf changes goes straight to global memory, each cell written by
+// exactly one thread (a survivor, an insert, or the gap a re-laid leaf leaves there), so no phase needs an in-place hazard check.
+__global__ void __launch_bounds__(TILE_THREADS, TILE_CTAS_PER_SM) k_tile_merge(TileArgs A, Levels L) {
     extern __shared__ __align__(16) unsigned char tile_smem_raw[];
     TileSmem& s = *reinterpret_cast<TileSmem*>(tile_smem_raw);
     const int t = blockIdx.x;
@@ -208,247 +220,172 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) k_tile_merge(TileArgs A, Leve
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t tbase = (int64_t)t << TILE_LG;
     const int lgS = L.lgS, S = 1 << lgS, NL = TILE_CELLS >> lgS;
+    const int G = 32 >> lgS, grp = lane >> lgS, q = lane & (S - 1);
+    const unsigned gmask = S >= 32 ? 0xffffffffu : ((1u << S) - 1u);
+    const int mn0 = (int)L.mn[0], mx0 = (int)L.mx[0];
     constexpr unsigned FULL = 0xffffffffu;
+    constexpr int ROWS = TILE_CELLS / 32, WARPS = TILE_THREADS / 32, RPW = ROWS / WARPS;
 
-    // ---- A: the tile's cells, once ----------------------------------------------------------------------------------
+    // ---- A: the tile's cells, once; live mask per leaf ---------------------------------------------------------------
     {
-        const longlong2* gk = reinterpret_cast<const longlong2*>(A.keys + tbase);
-        const double2* gv = reinterpret_cast<const double2*>(A.vals + tbase);
-        longlong2* dk = reinterpret_cast<longlong2*>(s.sk);
-        double2* dv = reinterpret_cast<double2*>(s.sv);
+        int64_t k[RPW];
+        double v[RPW];
 #pragma unroll
-        for (int i = 0; i < TILE_CELLS / 2 / TILE_THREADS; ++i) {
-            dk[tid + i * TILE_THREADS] = gk[tid + i * TILE_THREADS];
-            dv[tid + i * TILE_THREADS] = gv[tid + i * TILE_THREADS];
+        for (int i = 0; i < RPW; ++i) {
+            const int c = ((i * WARPS + warp) << 5) + lane;
+            k[i] = A.keys[tbase + c];
+            v[i] = A.vals[tbase + c];
         }
-        for (int i = tid; i < TILE_CELLS; i += TILE_THREADS) s.claim[i] = 0;
-        for (int i = tid; i < NL; i += TILE_THREADS) {
-            s.lcnt[i] = 0;
-            s.ndel[i] = 0;
-            s.dvf[i] = 0;
-            s.mrg[i] = 0;
+#pragma unroll
+        for (int i = 0; i < RPW; ++i) {
+            const int row = i * WARPS + warp;
+            const int c = (row << 5) + lane;
+            s.sk[c] = k[i];
+            s.sv[c] = v[i];
+            const unsigned b = __ballot_sync(FULL, k[i] != GAP_KEY);
+            if (lane < G) {
+                const int l = row * G + lane;
+                s.live[l] = (b >> (lane << lgS)) & gmask;
+                s.del[l] = 0;
+                s.ovw[l] = 0;
+                s.insm[l] = 0;
+                s.nins[l] = 0;
+                s.lhead[l] = -1;
+            }
         }
     }
     __syncthreads();
 
-    // ---- B: locate every op in shared memory ------------------------------------------------------------------------
+    // ---- B: every op located in shared memory and pushed on the list of its leaf ---------------------------------------
     for (int j = tid; j < nrec; j += TILE_THREADS) {
         const int4* rp = reinterpret_cast<const int4*>(A.rec + (int64_t)t * TILE_CAP + j);
         const int4 a = rp[0], b = rp[1];
         const int64_t key = (int64_t)((uint64_t)(uint32_t)a.x | ((uint64_t)(uint32_t)a.y << 32));
-        const double val = __longlong_as_double((long long)((uint64_t)(uint32_t)a.z | ((uint64_t)(uint32_t)a.w << 32)));
-        const uint32_t arr = (uint32_t)b.x;
         const int lo = (int)((uint32_t)b.z & 0xffffu), hi = (int)((uint32_t)b.z >> 16);
         bool hit = false;
         const int pos = tile_find(s.sk, key, lo, hi, &hit);
         s.rkey[j] = key;
-        s.rval[j] = val;
-        s.rarr[j] = arr;
+        s.rval[j] = __longlong_as_double((long long)((uint64_t)(uint32_t)a.z | ((uint64_t)(uint32_t)a.w << 32)));
+        s.rarr[j] = (uint32_t)b.x;
         s.rslot[j] = b.y;
         s.rpos[j] = (uint16_t)(pos | (hit ? 0x8000 : 0));
-        if (hit) atomicMax(&s.claim[pos], arr + 1u);
-        else s.rli[j] = (uint16_t)atomicAdd(&s.lcnt[pos >> lgS], 1);
+        s.rnext[j] = (int16_t)atomicExch(&s.lhead[pos >> lgS], j);
     }
     __syncthreads();
 
-    // ---- C: hits (the last arrival wins, writes.jl:16-19 / 65-68) + offsets of the per-leaf miss lists --------------
+    // ---- C: last writer wins per key (arrival order); hits overwrite (writes.jl:16-19) or blank (writes.jl:65-68) -------
     for (int j = tid; j < nrec; j += TILE_THREADS) {
+        const int64_t key = s.rkey[j];
+        const int32_t slot = s.rslot[j];
+        const uint32_t arr = s.rarr[j];
         const int pp = s.rpos[j];
-        if (pp & 0x8000) {
-            const int pos = pp & 0x7fff;
-            if (s.claim[pos] == s.rarr[j] + 1u) {
-                const double v = s.rval[j];
+        const int pos = pp & 0x7fff, l = pos >> lgS;
+        bool dead = false;
+        for (int o = s.lhead[l]; o >= 0; o = s.rnext[o]) dead |= (s.rkey[o] == key && s.rslot[o] == slot && s.rarr[o] > arr);
+        const double v = s.rval[j];
+        uint8_t st = 0;
+        if (!dead) {
+            const unsigned bit = 1u << (pos & (S - 1));
+            if (pp & 0x8000) {
                 if (v != 0.0) {
                     s.sv[pos] = v;
-                    s.dvf[pos >> lgS] = 1;
+                    atomicOr(&s.ovw[l], bit);
                 } else {
-                    s.sk[pos] = GAP_KEY;
-                    atomicAdd(&s.ndel[pos >> lgS], 1);
+                    atomicOr(&s.del[l], bit);
                 }
+            } else if (v != 0.0) {
+                st = 1;
+                atomicAdd(&s.nins[l], 1);
             }
         }
-    }
-    {   // block scan of (misses, leaf has misses) packed in one int; NL <= TILE_THREADS
-        const int x = tid < NL ? s.lcnt[tid] : 0;
-        const int mine = x | ((x > 0 ? 1 : 0) << 16);
-        int inc = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int y = __shfl_up_sync(FULL, inc, o);
-            if (lane >= o) inc += y;
-        }
-        if (lane == 31) s.wtot[warp] = inc;
-        __syncthreads();
-        int before = 0;
-        for (int w = 0; w < warp; ++w) before += s.wtot[w];
-        const int excl = before + inc - mine;
-        if (tid < NL) {
-            s.loff[tid] = (uint16_t)(excl & 0xffff);
-            if (x > 0) s.alist[excl >> 16] = (uint16_t)tid;
-        }
-        if (tid == TILE_THREADS - 1) s.nactive = (before + inc) >> 16;
+        s.rstat[j] = st;
     }
     __syncthreads();
 
-    // ---- D: misses grouped by leaf -----------------------------------------------------------------------------------
+    // ---- D: inserts.  A leaf whose post-batch count stays inside its own bounds (pma.jl:119-123, h = 0) is re-laid here:
+    //         merged rank = survivors up to the predecessor cell + inserts ordered before; the insert goes to its spread!
+    //         position at once.  Otherwise the leaf's inserts are handed, in order, to the density tree / window kernels. --------
     for (int j = tid; j < nrec; j += TILE_THREADS) {
-        const int pp = s.rpos[j];
-        if (!(pp & 0x8000)) s.llist[s.loff[pp >> lgS] + s.rli[j]] = (uint16_t)j;
+        if (!s.rstat[j]) continue;
+        const int pp = s.rpos[j] & 0x7fff, l = pp >> lgS;
+        const unsigned surv = s.live[l] & ~s.del[l];
+        const int m = __popc(surv) + s.nins[l];
+        if (m < mn0 || m > mx0) continue;
+        const int64_t key = s.rkey[j];
+        const int R = __popc(surv & mask_le(pp & (S - 1))) + tile_insert_rank(s, s.lhead[l], pp, key);
+        atomicOr(&s.insm[l], 1u << R);
+        const int64_t d = tbase + (l << lgS) + __ldg(A.destpos + m * 32 + R);
+        A.keys[d] = key;
+        A.vals[d] = s.rval[j];
+    }
+    for (int l = tid; l < NL; l += TILE_THREADS) {
+        const int ni = s.nins[l];
+        if (ni == 0) continue;
+        const int m = __popc(s.live[l] & ~s.del[l]) + ni;
+        if (m >= mn0 && m <= mx0) continue;
+        const int head = s.lhead[l];
+        const int64_t gb = (int64_t)atomicAdd((unsigned long long*)&A.status[ST_NINS], (unsigned long long)ni);
+        for (int j = head; j >= 0; j = s.rnext[j]) {
+            if (!s.rstat[j]) continue;
+            const int pp = s.rpos[j] & 0x7fff;
+            const int rk = tile_insert_rank(s, head, pp, s.rkey[j]);
+            A.ins_key[gb + rk] = s.rkey[j];
+            A.ins_val[gb + rk] = s.rval[j];
+            A.ins_pos[gb + rk] = tbase + pp;
+        }
+        const int64_t lg = (int64_t)t * NL + l;
+        A.inscnt[lg] = ni;
+        A.ins_first[lg] = (int32_t)gb;
     }
     __syncthreads();
 
-    // ---- E: one S-lane group per leaf with misses (32/S leaves per warp; control flow is warp-uniform) ---------------
-    {
-        const int G = 32 >> lgS, grp = lane >> lgS, q = lane & (S - 1), gshift = grp << lgS;
-        const unsigned gmask = S >= 32 ? 0xffffffffu : ((1u << S) - 1u);
-        const int mn0 = (int)L.mn[0], mx0 = (int)L.mx[0];
-        const int nact = s.nactive;
-        for (int a0 = warp * G; a0 < nact; a0 += (TILE_THREADS / 32) * G) {
-            const int a = a0 + grp;
-            const bool have = a < nact;
-            const int l = have ? s.alist[a] : 0;
-            const int n_l = have ? s.lcnt[l] : 0;
-            const int base = s.loff[l];
-            const int cell = (l << lgS) + q;
-            const int64_t ck = s.sk[cell];   // after the deletes and overwrites of phase C
-            const double cv = s.sv[cell];
-            const unsigned lm = (__ballot_sync(FULL, have && ck != GAP_KEY) >> gshift) & gmask;
-            const int maxn = __reduce_max_sync(FULL, n_l);
-            // sweep 1: last writer wins among the misses of one key; the surviving non-zero writes are the inserts
-            int nins = 0;
-            for (int j0 = 0; j0 < maxn; j0 += S) {
-                const int j = j0 + q;
-                const bool v = j < n_l;
-                const int idx = v ? s.llist[base + j] : 0;
-                const int64_t key = s.rkey[idx];
-                const int32_t slot = s.rslot[idx];
-                const uint32_t arr = s.rarr[idx];
-                bool dead = false;
-                for (int o = 0; o < maxn; ++o) {
-                    if (o < n_l) {
-                        const int io = s.llist[base + o];
-                        dead |= (s.rkey[io] == key && s.rslot[io] == slot && s.rarr[io] > arr);
-                    }
-                }
-                const bool ins = v && !dead && s.rval[idx] != 0.0;
-                if (v) s.rstat[idx] = ins ? 1 : 0;
-                nins += __popc((__ballot_sync(FULL, ins) >> gshift) & gmask);
-            }
-            __syncwarp();
-            if (!__any_sync(FULL, nins > 0)) continue;
-            const int m = __popc(lm) + nins;
-            const bool acc = nins > 0 && m >= mn0 && m <= mx0;   // the leaf is its own window (pma.jl:119-123, h = 0)
-            const bool left = nins > 0 && !acc;                   // a larger window (or a resize) takes the leaf's inserts
-            unsigned long long gb = 0;
-            if (left && q == 0) gb = atomicAdd((unsigned long long*)&A.status[ST_NINS], (unsigned long long)nins);
-            gb = __shfl_sync(FULL, gb, gshift);
-            // sweep 2: order of the inserts (predecessor cell, key) -> merged rank / slot in the hand-over arrays
-            unsigned insmask = 0;
-            for (int j0 = 0; j0 < maxn; j0 += S) {
-                const int j = j0 + q;
-                const bool v = j < n_l;
-                const int idx = v ? s.llist[base + j] : 0;
-                const bool ins = v && s.rstat[idx];
-                const int pp = s.rpos[idx] & 0x7fff;
-                const int64_t key = s.rkey[idx];
-                int rk = 0;
-                for (int o = 0; o < maxn; ++o) {
-                    if (o < n_l) {
-                        const int io = s.llist[base + o];
-                        if (s.rstat[io]) {
-                            const int po = s.rpos[io] & 0x7fff;
-                            rk += (po < pp) || (po == pp && s.rkey[io] < key);
-                        }
-                    }
-                }
-                unsigned bit = 0;
-                if (ins && acc) {
-                    const int R = __popc(lm & mask_le(pp & (S - 1))) + rk;   // survivors up to the predecessor + earlier inserts
-                    s.rli[idx] = (uint16_t)R;
-                    bit = 1u << R;
-                }
-                if (ins && left) {
-                    const int64_t g = (int64_t)gb + rk;
-                    A.ins_key[g] = key;
-                    A.ins_val[g] = s.rval[idx];
-                    A.ins_pos[g] = tbase + pp;
-                }
-                insmask |= (__reduce_or_sync(FULL, bit << gshift) >> gshift) & gmask;
-            }
-            __syncwarp();
-            // merge: survivor with rank r among the survivors takes the r-th merged rank not taken by an insert
-            const int mm = acc ? m : 0;
-            const unsigned mask = L.leafmask[mm];
-            const uint8_t* __restrict__ dtab = A.destpos + mm * 32;
-            const bool isurv = acc && ck != GAP_KEY;
-            const int srank = __popc(lm & ((1u << q) - 1u));
-            int R = srank;
-            if (isurv) {
-                while (true) {
-                    const int Rn = srank + __popc(insmask & mask_le(R));
+    // ---- E: cells.  Re-laid leaves: every survivor moves to the spread! position of its merged rank (the r-th rank not taken
+    //         by an insert), cells outside the new occupancy mask become gaps (pack! + spread!, moves.jl:94-172).  Other leaves:
+    //         blanked cells and overwritten values only. ----------------------------------------------------------------------
+#pragma unroll 1
+    for (int i = 0; i < RPW; ++i) {
+        const int row = i * WARPS + warp;
+        const int c = (row << 5) + lane;
+        const int l = row * G + grp;
+        const unsigned dl = s.del[l], ov = s.ovw[l];
+        const int ni = s.nins[l];
+        if (!__any_sync(FULL, (dl | ov) != 0 || ni != 0)) continue;
+        const unsigned surv = s.live[l] & ~dl;
+        const int cnt = __popc(surv);
+        const int m = cnt + ni;
+        const bool relay = ni > 0 && m >= mn0 && m <= mx0;
+        const int64_t lbase = tbase + (l << lgS);
+        if (relay) {
+            const unsigned mask = L.leafmask[m];
+            if ((surv >> q) & 1u) {
+                const unsigned insm = s.insm[l];
+                const int srank = __popc(surv & ((1u << q) - 1u));
+                int R = srank;
+                while (true) {   // least fixed point of R = srank + #inserts at ranks <= R
+                    const int Rn = srank + __popc(insm & mask_le(R));
                     if (Rn == R) break;
                     R = Rn;
                 }
+                const int64_t d = lbase + __ldg(A.destpos + m * 32 + R);
+                const int64_t k = s.sk[c];
+                const double v = s.sv[c];
+                A.keys[d] = k;
+                A.vals[d] = v;
+                if (k == 0) A.sem[(int64_t)v - 1] = d;   // moves.jl:160-166
             }
-            __syncwarp();
-            if (acc && !((mask >> q) & 1u)) {
-                s.sk[cell] = GAP_KEY;
-                s.sv[cell] = 0.0;
+            if (!((mask >> q) & 1u)) {
+                A.keys[lbase + q] = GAP_KEY;
+                A.vals[lbase + q] = 0.0;
             }
-            if (isurv) {
-                const int d = (l << lgS) + dtab[R];
-                s.sk[d] = ck;
-                s.sv[d] = cv;
-            }
-            for (int j0 = 0; j0 < maxn; j0 += S) {
-                const int j = j0 + q;
-                const bool v = j < n_l;
-                const int idx = v ? s.llist[base + j] : 0;
-                if (v && acc && s.rstat[idx]) {
-                    const int d = (l << lgS) + dtab[s.rli[idx]];
-                    s.sk[d] = s.rkey[idx];
-                    s.sv[d] = s.rval[idx];
-                }
-            }
-            if (have && q == 0 && nins > 0) {
-                if (acc) {
-                    s.mrg[l] = 1;
-                } else {
-                    const int64_t lg = (int64_t)t * NL + l;
-                    A.inscnt[lg] = nins;
-                    A.ins_first[lg] = (int32_t)gb;
-                    A.touched[lg] = 1;
-                }
-            }
-            __syncwarp();
+        } else {
+            if ((dl >> q) & 1u) A.keys[lbase + q] = GAP_KEY;
+            else if ((ov >> q) & 1u) A.vals[lbase + q] = s.sv[c];
         }
-    }
-    __syncthreads();
-
-    // ---- F: modified leaves go back (keys if cells were blanked or re-laid, values if overwritten or re-laid) --------
-    {
-        const int G = 32 >> lgS, grp = lane >> lgS, q = lane & (S - 1), gshift = grp << lgS;
-        const unsigned gmask = S >= 32 ? 0xffffffffu : ((1u << S) - 1u);
-        for (int l0 = warp * G; l0 < NL; l0 += (TILE_THREADS / 32) * G) {
-            const int l = l0 + grp;
-            const bool merged = s.mrg[l] != 0;
-            const bool dK = merged || s.ndel[l] > 0;
-            const bool dV = merged || s.dvf[l] != 0;
-            const int cell = (l << lgS) + q;
-            const int64_t k = s.sk[cell];
-            const int64_t p = tbase + cell;
-            if (dK) A.keys[p] = k;
-            if (dV) {
-                const double v = s.sv[cell];
-                A.vals[p] = v;
-                if (merged && k == 0) A.sem[(int64_t)v - 1] = p;   // moves.jl:160-166
-            }
-            const unsigned b = (__ballot_sync(FULL, k != GAP_KEY) >> gshift) & gmask;
-            if (dK && q == 0) {
-                const int64_t lg = (int64_t)t * NL + l;
-                A.leafcnt[lg] = __popc(b);
-                A.touched[lg] = 1;
-            }
+        if (q == 0 && (dl != 0 || ni != 0)) {
+            const int64_t lg = (int64_t)t * NL + l;
+            A.touched[lg] = 1;
+            if (relay) A.leafcnt[lg] = m;
+            else if (dl) A.leafcnt[lg] = cnt;
         }
     }
 }
