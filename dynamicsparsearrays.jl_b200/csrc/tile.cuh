@@ -157,17 +157,17 @@ __device__ __forceinline__ int tile_find(const int64_t* sk, int64_t key, int lo,
 
 __device__ __forceinline__ unsigned mask_le(int x) { return x >= 31 ? 0xffffffffu : ((2u << x) - 1u); }
 
+static_assert(TILE_CAP <= 256 && TILE_CELLS <= 2048, "op indices are stored in 8 bits, tile-local positions in 15");
 struct TileSmem {
-    int64_t sk[TILE_CELLS];
-    double sv[TILE_CELLS];
+    int64_t sk[TILE_CELLS];           // the tile's keys (read-only after the load)
     int64_t rkey[TILE_CAP];
     double rval[TILE_CAP];
     uint32_t rarr[TILE_CAP];
     int32_t rslot[TILE_CAP];
+    uint32_t work[TILE_CELLS + TILE_MAX_LEAVES];   // phase E work list: (cell << 16) | what lands there; S + 1 entries per re-laid leaf
     // per leaf
     uint32_t live[TILE_MAX_LEAVES];   // cells stored before the batch
     uint32_t del[TILE_MAX_LEAVES];    // cells blanked by the batch
-    uint32_t ovw[TILE_MAX_LEAVES];    // cells whose value is overwritten
     uint32_t insm[TILE_MAX_LEAVES];   // merged ranks taken by the inserts (leaves re-laid here)
     int nins[TILE_MAX_LEAVES];        // inserts of the leaf
     int lhead[TILE_MAX_LEAVES];       // first op of the leaf's list (-1 = none)
@@ -175,6 +175,8 @@ struct TileSmem {
     uint16_t rpos[TILE_CAP];          // tile-local position of the hit / predecessor; bit 15 = hit
     int16_t rnext[TILE_CAP];          // next op of the same leaf (-1 = end)
     uint8_t rstat[TILE_CAP];          // 1 = live insert
+    uint8_t rop[TILE_CELLS];          // per re-laid leaf: rop[leaf cell 0 + R] = the op that takes merged rank R
+    int nwork;                        // re-laid leaves so far * S
 };
 
 struct TileArgs {
@@ -206,70 +208,82 @@ __device__ __forceinline__ int tile_insert_rank(const TileSmem& s, int head, int
     return rk;
 }
 
-// Control flow is data-parallel throughout: cell phases run one lane per cell (rows of 32 cells = 32/S leaves), op phases one
-// thread per op; an op only ever walks the list of the ops of its own leaf (one or two entries on a uniform batch).
-// Cells are only READ from shared memory: everything a leaf changes goes straight to global memory, each cell written by
-// exactly one thread (a survivor, an insert, or the gap a re-laid leaf leaves there), so no phase needs an in-place hazard check.
+// Control flow is data-parallel and kept short (the kernel is bound by instruction issue, not by HBM): op phases run one thread
+// per op and only ever walk the list of the ops of the op's own leaf (one or two entries on a uniform batch); one thread per
+// modified leaf writes down, cell by cell, what lands where (a work list); the cells of the work list are then fetched and stored
+// by one thread each.  Only the keys are staged (the searches read them); values are touched where something changes: an
+// overwrite stores its value in place, a re-laid leaf is written destination-driven (the r-th survivor, an insert, or a gap per
+// cell), so every cell has exactly one writer and a re-laid leaf goes back as full lines.
 __global__ void __launch_bounds__(TILE_THREADS, TILE_CTAS_PER_SM) k_tile_merge(TileArgs A, Levels L) {
     extern __shared__ __align__(16) unsigned char tile_smem_raw[];
     TileSmem& s = *reinterpret_cast<TileSmem*>(tile_smem_raw);
     const int t = blockIdx.x;
-    int nrec = A.tcnt[t];
-    if (nrec <= 0) return;
-    if (nrec > TILE_CAP) nrec = TILE_CAP;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t tbase = (int64_t)t << TILE_LG;
     const int lgS = L.lgS, S = 1 << lgS, NL = TILE_CELLS >> lgS;
-    const int G = 32 >> lgS, grp = lane >> lgS, q = lane & (S - 1);
-    const unsigned gmask = S >= 32 ? 0xffffffffu : ((1u << S) - 1u);
     const int mn0 = (int)L.mn[0], mx0 = (int)L.mx[0];
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr int ROWS = TILE_CELLS / 32, WARPS = TILE_THREADS / 32, RPW = ROWS / WARPS;
+    constexpr int ROWS = TILE_CELLS / 32, WARPS = TILE_THREADS / 32, RPW = ROWS / WARPS, OPT = TILE_CAP / TILE_THREADS;
+    constexpr int VPT = TILE_CELLS / 2 / TILE_THREADS;   // 16-byte key loads per thread
 
-    // ---- A: the tile's cells, once; live mask per leaf ---------------------------------------------------------------
+    // ---- A: the tile's keys and the tile's ops, all loads in flight together; live mask per leaf -----------------------
+    int nrec = A.tcnt[t];
+    int4 ra[OPT], rb[OPT];
     {
-        int64_t k[RPW];
-        double v[RPW];
+        longlong2 kk[VPT];
+        const longlong2* gk = reinterpret_cast<const longlong2*>(A.keys + tbase);
 #pragma unroll
-        for (int i = 0; i < RPW; ++i) {
-            const int c = ((i * WARPS + warp) << 5) + lane;
-            k[i] = A.keys[tbase + c];
-            v[i] = A.vals[tbase + c];
+        for (int i = 0; i < VPT; ++i) kk[i] = gk[tid + i * TILE_THREADS];
+        if (nrec > TILE_CAP) nrec = TILE_CAP;
+#pragma unroll
+        for (int i = 0; i < OPT; ++i) {
+            const int j = tid + i * TILE_THREADS;
+            if (j < nrec) {
+                const int4* rp = reinterpret_cast<const int4*>(A.rec + (int64_t)t * TILE_CAP + j);
+                ra[i] = rp[0];
+                rb[i] = rp[1];
+            }
         }
+        if (nrec <= 0) return;
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) reinterpret_cast<longlong2*>(s.sk)[tid + i * TILE_THREADS] = kk[i];
+        for (int l = tid; l < NL; l += TILE_THREADS) {
+            s.del[l] = 0;
+            s.insm[l] = 0;
+            s.nins[l] = 0;
+            s.lhead[l] = -1;
+        }
+        if (tid == 0) s.nwork = 0;
+    }
+    __syncthreads();
+    {   // live masks: a warp reads a row of 32 cells, the first 32/S lanes store the masks of its leaves
+        const int G = 32 >> lgS;
+        const unsigned gmask = S >= 32 ? 0xffffffffu : ((1u << S) - 1u);
 #pragma unroll
         for (int i = 0; i < RPW; ++i) {
             const int row = i * WARPS + warp;
-            const int c = (row << 5) + lane;
-            s.sk[c] = k[i];
-            s.sv[c] = v[i];
-            const unsigned b = __ballot_sync(FULL, k[i] != GAP_KEY);
-            if (lane < G) {
-                const int l = row * G + lane;
-                s.live[l] = (b >> (lane << lgS)) & gmask;
-                s.del[l] = 0;
-                s.ovw[l] = 0;
-                s.insm[l] = 0;
-                s.nins[l] = 0;
-                s.lhead[l] = -1;
-            }
+            const unsigned b = __ballot_sync(FULL, s.sk[(row << 5) + lane] != GAP_KEY);
+            if (lane < G) s.live[row * G + lane] = (b >> (lane << lgS)) & gmask;
         }
     }
-    __syncthreads();
 
     // ---- B: every op located in shared memory and pushed on the list of its leaf ---------------------------------------
-    for (int j = tid; j < nrec; j += TILE_THREADS) {
-        const int4* rp = reinterpret_cast<const int4*>(A.rec + (int64_t)t * TILE_CAP + j);
-        const int4 a = rp[0], b = rp[1];
-        const int64_t key = (int64_t)((uint64_t)(uint32_t)a.x | ((uint64_t)(uint32_t)a.y << 32));
-        const int lo = (int)((uint32_t)b.z & 0xffffu), hi = (int)((uint32_t)b.z >> 16);
-        bool hit = false;
-        const int pos = tile_find(s.sk, key, lo, hi, &hit);
-        s.rkey[j] = key;
-        s.rval[j] = __longlong_as_double((long long)((uint64_t)(uint32_t)a.z | ((uint64_t)(uint32_t)a.w << 32)));
-        s.rarr[j] = (uint32_t)b.x;
-        s.rslot[j] = b.y;
-        s.rpos[j] = (uint16_t)(pos | (hit ? 0x8000 : 0));
-        s.rnext[j] = (int16_t)atomicExch(&s.lhead[pos >> lgS], j);
+#pragma unroll
+    for (int i = 0; i < OPT; ++i) {
+        const int j = tid + i * TILE_THREADS;
+        if (j < nrec) {
+            const int4 a = ra[i], b = rb[i];
+            const int64_t key = (int64_t)((uint64_t)(uint32_t)a.x | ((uint64_t)(uint32_t)a.y << 32));
+            const int lo = (int)((uint32_t)b.z & 0xffffu), hi = (int)((uint32_t)b.z >> 16);
+            bool hit = false;
+            const int pos = tile_find(s.sk, key, lo, hi, &hit);
+            s.rkey[j] = key;
+            s.rval[j] = __longlong_as_double((long long)((uint64_t)(uint32_t)a.z | ((uint64_t)(uint32_t)a.w << 32)));
+            s.rarr[j] = (uint32_t)b.x;
+            s.rslot[j] = b.y;
+            s.rpos[j] = (uint16_t)(pos | (hit ? 0x8000 : 0));
+            s.rnext[j] = (int16_t)atomicExch(&s.lhead[pos >> lgS], j);
+        }
     }
     __syncthreads();
 
@@ -285,14 +299,9 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_CTAS_PER_SM) k_tile_merge(T
         const double v = s.rval[j];
         uint8_t st = 0;
         if (!dead) {
-            const unsigned bit = 1u << (pos & (S - 1));
             if (pp & 0x8000) {
-                if (v != 0.0) {
-                    s.sv[pos] = v;
-                    atomicOr(&s.ovw[l], bit);
-                } else {
-                    atomicOr(&s.del[l], bit);
-                }
+                if (v != 0.0) A.vals[tbase + pos] = v;   // in place; a re-laid leaf reads it back from there in phase E
+                else atomicOr(&s.del[l], 1u << (pos & (S - 1)));
             } else if (v != 0.0) {
                 st = 1;
                 atomicAdd(&s.nins[l], 1);
@@ -302,90 +311,115 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_CTAS_PER_SM) k_tile_merge(T
     }
     __syncthreads();
 
-    // ---- D: inserts.  A leaf whose post-batch count stays inside its own bounds (pma.jl:119-123, h = 0) is re-laid here:
-    //         merged rank = survivors up to the predecessor cell + inserts ordered before; the insert goes to its spread!
-    //         position at once.  Otherwise the leaf's inserts are handed, in order, to the density tree / window kernels. --------
+    // ---- D1: inserts of the leaves that are re-laid here (post-batch count inside the leaf's own bounds, pma.jl:119-123 with
+    //          h = 0): merged rank = survivors up to the predecessor cell + inserts ordered before ----------------------------
     for (int j = tid; j < nrec; j += TILE_THREADS) {
         if (!s.rstat[j]) continue;
         const int pp = s.rpos[j] & 0x7fff, l = pp >> lgS;
         const unsigned surv = s.live[l] & ~s.del[l];
         const int m = __popc(surv) + s.nins[l];
         if (m < mn0 || m > mx0) continue;
-        const int64_t key = s.rkey[j];
-        const int R = __popc(surv & mask_le(pp & (S - 1))) + tile_insert_rank(s, s.lhead[l], pp, key);
+        const int R = __popc(surv & mask_le(pp & (S - 1))) + tile_insert_rank(s, s.lhead[l], pp, s.rkey[j]);
+        s.rop[(l << lgS) + R] = (uint8_t)j;
         atomicOr(&s.insm[l], 1u << R);
-        const int64_t d = tbase + (l << lgS) + __ldg(A.destpos + m * 32 + R);
-        A.keys[d] = key;
-        A.vals[d] = s.rval[j];
-    }
-    for (int l = tid; l < NL; l += TILE_THREADS) {
-        const int ni = s.nins[l];
-        if (ni == 0) continue;
-        const int m = __popc(s.live[l] & ~s.del[l]) + ni;
-        if (m >= mn0 && m <= mx0) continue;
-        const int head = s.lhead[l];
-        const int64_t gb = (int64_t)atomicAdd((unsigned long long*)&A.status[ST_NINS], (unsigned long long)ni);
-        for (int j = head; j >= 0; j = s.rnext[j]) {
-            if (!s.rstat[j]) continue;
-            const int pp = s.rpos[j] & 0x7fff;
-            const int rk = tile_insert_rank(s, head, pp, s.rkey[j]);
-            A.ins_key[gb + rk] = s.rkey[j];
-            A.ins_val[gb + rk] = s.rval[j];
-            A.ins_pos[gb + rk] = tbase + pp;
-        }
-        const int64_t lg = (int64_t)t * NL + l;
-        A.inscnt[lg] = ni;
-        A.ins_first[lg] = (int32_t)gb;
     }
     __syncthreads();
 
-    // ---- E: cells.  Re-laid leaves: every survivor moves to the spread! position of its merged rank (the r-th rank not taken
-    //         by an insert), cells outside the new occupancy mask become gaps (pack! + spread!, moves.jl:94-172).  Other leaves:
-    //         blanked cells and overwritten values only. ----------------------------------------------------------------------
-#pragma unroll 1
-    for (int i = 0; i < RPW; ++i) {
-        const int row = i * WARPS + warp;
-        const int c = (row << 5) + lane;
-        const int l = row * G + grp;
-        const unsigned dl = s.del[l], ov = s.ovw[l];
+    // ---- D2: one thread per modified leaf.  Re-laid leaf (pack! + spread!, moves.jl:94-172): cell q is occupied iff the
+    //          spread! mask of m elements says so; rank r is an insert's or the next survivor's.  A leaf outside its bounds hands
+    //          its inserts, in order, to the density tree / window kernels; blanked cells are stored at once. -----------------
+    constexpr uint32_t CODE_GAP = 0xffffu, CODE_OP = 0x8000u;
+    for (int l = tid; l < NL; l += TILE_THREADS) {
         const int ni = s.nins[l];
-        if (!__any_sync(FULL, (dl | ov) != 0 || ni != 0)) continue;
-        const unsigned surv = s.live[l] & ~dl;
+        const unsigned dl = s.del[l];
+        if (ni == 0 && dl == 0) continue;
+        unsigned surv = s.live[l] & ~dl;
         const int cnt = __popc(surv);
         const int m = cnt + ni;
         const bool relay = ni > 0 && m >= mn0 && m <= mx0;
-        const int64_t lbase = tbase + (l << lgS);
+        const int64_t lg = (int64_t)t * NL + l;
+        const int lcell = l << lgS;
+        A.touched[lg] = 1;
         if (relay) {
-            const unsigned mask = L.leafmask[m];
-            if ((surv >> q) & 1u) {
-                const unsigned insm = s.insm[l];
-                const int srank = __popc(surv & ((1u << q) - 1u));
-                int R = srank;
-                while (true) {   // least fixed point of R = srank + #inserts at ranks <= R
-                    const int Rn = srank + __popc(insm & mask_le(R));
-                    if (Rn == R) break;
-                    R = Rn;
+            A.leafcnt[lg] = m;
+            const int base = atomicAdd(&s.nwork, S);
+            uint32_t* w = s.work + base + (base >> lgS);   // S + 1 entries per leaf: the threads of a warp write different banks
+            const unsigned mask = L.leafmask[m], insm = s.insm[l];
+            int r = 0;
+            for (int q = 0; q < S; ++q) {
+                uint32_t code = CODE_GAP;
+                if ((mask >> q) & 1u) {
+                    if ((insm >> r) & 1u) {
+                        code = CODE_OP | s.rop[lcell + r];
+                    } else {
+                        code = (uint32_t)(__ffs(surv) - 1);
+                        surv &= surv - 1;
+                    }
+                    ++r;
                 }
-                const int64_t d = lbase + __ldg(A.destpos + m * 32 + R);
-                const int64_t k = s.sk[c];
-                const double v = s.sv[c];
-                A.keys[d] = k;
-                A.vals[d] = v;
-                if (k == 0) A.sem[(int64_t)v - 1] = d;   // moves.jl:160-166
+                w[q] = ((uint32_t)(lcell + q) << 16) | code;
             }
-            if (!((mask >> q) & 1u)) {
-                A.keys[lbase + q] = GAP_KEY;
-                A.vals[lbase + q] = 0.0;
-            }
-        } else {
-            if ((dl >> q) & 1u) A.keys[lbase + q] = GAP_KEY;
-            else if ((ov >> q) & 1u) A.vals[lbase + q] = s.sv[c];
+            continue;
         }
-        if (q == 0 && (dl != 0 || ni != 0)) {
-            const int64_t lg = (int64_t)t * NL + l;
-            A.touched[lg] = 1;
-            if (relay) A.leafcnt[lg] = m;
-            else if (dl) A.leafcnt[lg] = cnt;
+        if (dl) {
+            A.leafcnt[lg] = cnt;
+            for (unsigned d = dl; d; d &= d - 1) A.keys[tbase + lcell + (__ffs(d) - 1)] = GAP_KEY;
+        }
+        if (ni) {
+            const int head = s.lhead[l];
+            const int64_t gb = (int64_t)atomicAdd((unsigned long long*)&A.status[ST_NINS], (unsigned long long)ni);
+            for (int j = head; j >= 0; j = s.rnext[j]) {
+                if (!s.rstat[j]) continue;
+                const int pp = s.rpos[j] & 0x7fff;
+                const int rk = tile_insert_rank(s, head, pp, s.rkey[j]);
+                A.ins_key[gb + rk] = s.rkey[j];
+                A.ins_val[gb + rk] = s.rval[j];
+                A.ins_pos[gb + rk] = tbase + pp;
+            }
+            A.inscnt[lg] = ni;
+            A.ins_first[lg] = (int32_t)gb;
+        }
+    }
+    __syncthreads();
+
+    // ---- E: the cells of the re-laid leaves, one thread each: fetch (survivor values from global memory, all loads of a
+    //         chunk in flight together), then store.  A leaf's cells sit in one warp, in one chunk. ---------------------------
+    const int nwork = s.nwork;
+    constexpr int EU = 4;
+    for (int w0 = 0; w0 < nwork; w0 += EU * TILE_THREADS) {
+        int64_t k[EU];
+        double v[EU];
+        int cell[EU];
+#pragma unroll
+        for (int u = 0; u < EU; ++u) {
+            const int w = w0 + u * TILE_THREADS + tid;
+            cell[u] = -1;
+            k[u] = GAP_KEY;
+            v[u] = 0.0;
+            if (w < nwork) {
+                const uint32_t e = s.work[w + (w >> lgS)];
+                const uint32_t code = e & 0xffffu;
+                const int c = (int)(e >> 16);
+                cell[u] = c;
+                if (code < 32u) {
+                    const int src = (c & ~(S - 1)) + (int)code;
+                    k[u] = s.sk[src];
+                    v[u] = A.vals[tbase + src];
+                } else if (code != CODE_GAP) {
+                    k[u] = s.rkey[code & 0xffu];
+                    v[u] = s.rval[code & 0xffu];
+                }
+            }
+        }
+        __syncwarp();   // every value of the warp's leaves is read before any of their cells is written
+#pragma unroll
+        for (int u = 0; u < EU; ++u) {
+            if (cell[u] >= 0) {
+                const int64_t p = tbase + cell[u];
+                A.keys[p] = k[u];
+                A.vals[p] = v[u];
+                if (k[u] == 0) A.sem[(int64_t)v[u] - 1] = p;   // moves.jl:160-166
+            }
         }
     }
 }
