@@ -212,13 +212,15 @@ static void phase2_launch(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t 
         ws.batch.ins_val.ensure((size_t)n + 1);
         ws.batch.ins_pos.ensure((size_t)n + 1);
         P.pma.ensure_destpos(st);
+        const int lgS = ilog2_i64(P.pma.g.segment_capacity);
+        void (*kern)(TileArgs, Levels) = lgS == 3 ? k_tile_merge<3> : lgS == 4 ? k_tile_merge<4> : k_tile_merge<5>;
         static std::mutex attr_mu;
-        static std::map<int, bool> attr_set;
+        static std::map<std::pair<int, int>, bool> attr_set;
         {
             std::lock_guard<std::mutex> lock(attr_mu);
-            bool& done = attr_set[current_device()];
+            bool& done = attr_set[std::make_pair(current_device(), lgS)];
             if (!done) {
-                DSA_CUDA(cudaFuncSetAttribute(k_tile_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
+                DSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
                 done = true;
             }
         }
@@ -228,7 +230,7 @@ static void phase2_launch(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t 
         T.ins_first = ws.batch.ins_first.p; T.ins_key = ws.batch.ins_key.p; T.ins_val = ws.batch.ins_val.p; T.ins_pos = ws.batch.ins_pos.p;
         T.status = ws.batch.status;
         const int64_t ntiles = P.pma.g.capacity >> TILE_LG;
-        DSA_LAUNCH("tile_merge", k_tile_merge, (unsigned)ntiles, TILE_THREADS, sizeof(TileSmem), st, T, P.pma.levels());
+        DSA_LAUNCH("tile_merge", kern, (unsigned)ntiles, TILE_THREADS, sizeof(TileSmem), st, T, P.pma.levels());
         P.pma.rebalance_launch(ws.batch, st);
         return;
     }

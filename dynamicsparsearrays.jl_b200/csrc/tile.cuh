@@ -70,12 +70,28 @@ __global__ void __launch_bounds__(256, 6) k_tile_assign(const int64_t* __restric
         const int64_t from = is_set ? ps + 1 : ps;    // inserts search (sem, end], deletes [sem, end]  (pcsr.jl:305-307)
         const int64_t to = pe - 1;
         int64_t t = ps >> TILE_LG, lo = from, hi = to;
-        if (t != (to >> TILE_LG)) {   // the span straddles a tile border: find the predecessor's tile in HBM
-            bool hit = false;
-            int64_t pos = gapped_find(keys, k, from, to, &hit);
-            if (pos < ps) pos = ps;
-            t = pos >> TILE_LG;
-            lo = hi = pos;
+        const int64_t t_last = to >> TILE_LG;
+        if (t != t_last) {
+            // The span straddles tile borders.  f(b) = key of the first stored cell in [b, end) is non-decreasing over the borders
+            // b, and the predecessor of k lies in the tile of the LAST border with f(b) <= k (or in the span's first tile): one
+            // probe — a short walk to the right of the border — per step of a binary search over the borders (one border for a
+            // span shorter than a tile), instead of the gapped search over the whole span in HBM.
+            int64_t blo = t + 1, bhi = t_last;   // border of tile u = u << TILE_LG
+            while (blo <= bhi) {
+                const int64_t u = (blo + bhi) >> 1;
+                int64_t p = u << TILE_LG;
+                int64_t kk = keys[p];
+                while (kk == GAP_KEY && p < to) kk = keys[++p];
+                if (kk != GAP_KEY && kk <= k) {
+                    t = u;
+                    blo = u + 1;
+                } else {
+                    bhi = u - 1;
+                }
+            }
+            const int64_t tb0 = t << TILE_LG;
+            lo = from > tb0 ? from : tb0;
+            hi = to < tb0 + TILE_CELLS - 1 ? to : tb0 + TILE_CELLS - 1;
         }
         const int64_t tb = t << TILE_LG;
         const int li = atomicAdd(&tcnt[t], 1);
@@ -214,13 +230,14 @@ __device__ __forceinline__ int tile_insert_rank(const TileSmem& s, int head, int
 // by one thread each.  Only the keys are staged (the searches read them); values are touched where something changes: an
 // overwrite stores its value in place, a re-laid leaf is written destination-driven (the r-th survivor, an insert, or a gap per
 // cell), so every cell has exactly one writer and a re-laid leaf goes back as full lines.
+template <int LGS>
 __global__ void __launch_bounds__(TILE_THREADS, TILE_CTAS_PER_SM) k_tile_merge(TileArgs A, Levels L) {
     extern __shared__ __align__(16) unsigned char tile_smem_raw[];
     TileSmem& s = *reinterpret_cast<TileSmem*>(tile_smem_raw);
     const int t = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t tbase = (int64_t)t << TILE_LG;
-    const int lgS = L.lgS, S = 1 << lgS, NL = TILE_CELLS >> lgS;
+    constexpr int lgS = LGS, S = 1 << lgS, NL = TILE_CELLS >> lgS;
     const int mn0 = (int)L.mn[0], mx0 = (int)L.mx[0];
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int ROWS = TILE_CELLS / 32, WARPS = TILE_THREADS / 32, RPW = ROWS / WARPS, OPT = TILE_CAP / TILE_THREADS;
@@ -257,8 +274,8 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_CTAS_PER_SM) k_tile_merge(T
     }
     __syncthreads();
     {   // live masks: a warp reads a row of 32 cells, the first 32/S lanes store the masks of its leaves
-        const int G = 32 >> lgS;
-        const unsigned gmask = S >= 32 ? 0xffffffffu : ((1u << S) - 1u);
+        constexpr int G = 32 >> lgS;
+        constexpr unsigned gmask = S >= 32 ? 0xffffffffu : ((1u << (S & 31)) - 1u);
 #pragma unroll
         for (int i = 0; i < RPW; ++i) {
             const int row = i * WARPS + warp;
@@ -346,6 +363,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_CTAS_PER_SM) k_tile_merge(T
             uint32_t* w = s.work + base + (base >> lgS);   // S + 1 entries per leaf: the threads of a warp write different banks
             const unsigned mask = L.leafmask[m], insm = s.insm[l];
             int r = 0;
+#pragma unroll
             for (int q = 0; q < S; ++q) {
                 uint32_t code = CODE_GAP;
                 if ((mask >> q) & 1u) {
