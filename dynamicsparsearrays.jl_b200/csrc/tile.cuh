@@ -178,9 +178,16 @@ struct TileSmem {
     int64_t sk[TILE_CELLS];           // the tile's keys (read-only after the load)
     int64_t rkey[TILE_CAP];
     double rval[TILE_CAP];
-    uint32_t rarr[TILE_CAP];
-    int32_t rslot[TILE_CAP];
-    uint32_t work[TILE_CELLS + TILE_MAX_LEAVES];   // phase E work list: (cell << 16) | what lands there; S + 1 entries per re-laid leaf
+    union {
+        struct {                      // phases B, C: arrival index and slot of every op (last writer wins)
+            uint32_t rarr[TILE_CAP];
+            int32_t rslot[TILE_CAP];
+        } op;
+        struct {                      // phases D2, E: what lands in each cell of a re-laid leaf; S + 1 entries per leaf
+            uint16_t code[TILE_CELLS + TILE_MAX_LEAVES];
+            uint8_t leaf[TILE_MAX_LEAVES];
+        } work;
+    } u;
     // per leaf
     uint32_t live[TILE_MAX_LEAVES];   // cells stored before the batch
     uint32_t del[TILE_MAX_LEAVES];    // cells blanked by the batch
@@ -192,7 +199,7 @@ struct TileSmem {
     int16_t rnext[TILE_CAP];          // next op of the same leaf (-1 = end)
     uint8_t rstat[TILE_CAP];          // 1 = live insert
     uint8_t rop[TILE_CELLS];          // per re-laid leaf: rop[leaf cell 0 + R] = the op that takes merged rank R
-    int nwork;                        // re-laid leaves so far * S
+    int nwork;                        // re-laid leaves so far
 };
 
 struct TileArgs {
@@ -247,6 +254,14 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_CTAS_PER_SM) k_tile_merge(T
     int nrec = A.tcnt[t];
     int4 ra[OPT], rb[OPT];
     {
+        // the tile that the CTA taking this one's place will work on: its keys and the head of its bucket are pulled into L2 now
+        const int tp = t + TILE_PREFETCH_DIST;
+        if (tp < (int)gridDim.x) {
+            const char* pk = reinterpret_cast<const char*>(A.keys + ((int64_t)tp << TILE_LG));
+            const char* pr = reinterpret_cast<const char*>(A.rec + (int64_t)tp * TILE_CAP);
+            if (tid < TILE_CELLS * 8 / 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pk + tid * 128));
+            else if (tid < TILE_CELLS * 8 / 128 + 24) asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + (tid - TILE_CELLS * 8 / 128) * 128));
+        }
         longlong2 kk[VPT];
         const longlong2* gk = reinterpret_cast<const longlong2*>(A.keys + tbase);
 #pragma unroll
@@ -296,8 +311,8 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_CTAS_PER_SM) k_tile_merge(T
             const int pos = tile_find(s.sk, key, lo, hi, &hit);
             s.rkey[j] = key;
             s.rval[j] = __longlong_as_double((long long)((uint64_t)(uint32_t)a.z | ((uint64_t)(uint32_t)a.w << 32)));
-            s.rarr[j] = (uint32_t)b.x;
-            s.rslot[j] = b.y;
+            s.u.op.rarr[j] = (uint32_t)b.x;
+            s.u.op.rslot[j] = b.y;
             s.rpos[j] = (uint16_t)(pos | (hit ? 0x8000 : 0));
             s.rnext[j] = (int16_t)atomicExch(&s.lhead[pos >> lgS], j);
         }
@@ -307,12 +322,12 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_CTAS_PER_SM) k_tile_merge(T
     // ---- C: last writer wins per key (arrival order); hits overwrite (writes.jl:16-19) or blank (writes.jl:65-68) -------
     for (int j = tid; j < nrec; j += TILE_THREADS) {
         const int64_t key = s.rkey[j];
-        const int32_t slot = s.rslot[j];
-        const uint32_t arr = s.rarr[j];
+        const int32_t slot = s.u.op.rslot[j];
+        const uint32_t arr = s.u.op.rarr[j];
         const int pp = s.rpos[j];
         const int pos = pp & 0x7fff, l = pos >> lgS;
         bool dead = false;
-        for (int o = s.lhead[l]; o >= 0; o = s.rnext[o]) dead |= (s.rkey[o] == key && s.rslot[o] == slot && s.rarr[o] > arr);
+        for (int o = s.lhead[l]; o >= 0; o = s.rnext[o]) dead |= (s.rkey[o] == key && s.u.op.rslot[o] == slot && s.u.op.rarr[o] > arr);
         const double v = s.rval[j];
         uint8_t st = 0;
         if (!dead) {
@@ -322,6 +337,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_CTAS_PER_SM) k_tile_merge(T
             } else if (v != 0.0) {
                 st = 1;
                 atomicAdd(&s.nins[l], 1);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(A.vals + tbase + (l << lgS)));   // phase E reads the leaf's values
             }
         }
         s.rstat[j] = st;
@@ -359,8 +375,9 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_CTAS_PER_SM) k_tile_merge(T
         A.touched[lg] = 1;
         if (relay) {
             A.leafcnt[lg] = m;
-            const int base = atomicAdd(&s.nwork, S);
-            uint32_t* w = s.work + base + (base >> lgS);   // S + 1 entries per leaf: the threads of a warp write different banks
+            const int slot = atomicAdd(&s.nwork, 1);
+            uint16_t* w = s.u.work.code + slot * (S + 1);   // S + 1 entries per leaf: the threads of a warp write different banks
+            s.u.work.leaf[slot] = (uint8_t)l;
             const unsigned mask = L.leafmask[m], insm = s.insm[l];
             int r = 0;
 #pragma unroll
@@ -375,7 +392,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_CTAS_PER_SM) k_tile_merge(T
                     }
                     ++r;
                 }
-                w[q] = ((uint32_t)(lcell + q) << 16) | code;
+                w[q] = (uint16_t)code;
             }
             continue;
         }
@@ -402,7 +419,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_CTAS_PER_SM) k_tile_merge(T
 
     // ---- E: the cells of the re-laid leaves, one thread each: fetch (survivor values from global memory, all loads of a
     //         chunk in flight together), then store.  A leaf's cells sit in one warp, in one chunk. ---------------------------
-    const int nwork = s.nwork;
+    const int nwork = s.nwork << lgS;
     constexpr int EU = 4;
     for (int w0 = 0; w0 < nwork; w0 += EU * TILE_THREADS) {
         int64_t k[EU];
@@ -415,14 +432,13 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_CTAS_PER_SM) k_tile_merge(T
             k[u] = GAP_KEY;
             v[u] = 0.0;
             if (w < nwork) {
-                const uint32_t e = s.work[w + (w >> lgS)];
-                const uint32_t code = e & 0xffffu;
-                const int c = (int)(e >> 16);
-                cell[u] = c;
+                const int slot = w >> lgS, q = w & (S - 1);
+                const uint32_t code = s.u.work.code[slot * (S + 1) + q];
+                const int lcell = (int)s.u.work.leaf[slot] << lgS;
+                cell[u] = lcell + q;
                 if (code < 32u) {
-                    const int src = (c & ~(S - 1)) + (int)code;
-                    k[u] = s.sk[src];
-                    v[u] = A.vals[tbase + src];
+                    k[u] = s.sk[lcell + (int)code];
+                    v[u] = A.vals[tbase + lcell + (int)code];
                 } else if (code != CODE_GAP) {
                     k[u] = s.rkey[code & 0xffu];
                     v[u] = s.rval[code & 0xffu];
