@@ -144,28 +144,48 @@ __global__ void __launch_bounds__(256, 6) k_tile_assign(const int64_t* __restric
     }
 }
 
-// the reference's gapped binary search (finds.jl:29-57) on the tile in shared memory: position of the hit or of the predecessor
-__device__ __forceinline__ int tile_find(const int64_t* sk, int64_t key, int lo, int hi, bool* hit) {
-    while (lo <= hi) {
-        const int mid = (lo + hi) >> 1;
-        int i = mid;
-        int64_t k = sk[i];
-        while (k == GAP_KEY && i > lo) {
-            --i;
-            k = sk[i];
-        }
-        if (k == GAP_KEY) {
-            lo = mid + 1;
-        } else if (k > key) {
-            hi = i - 1;
-        } else if (k < key) {
-            lo = mid + 1;
-        } else {
-            *hit = true;
-            return i;
-        }
-    }
+__device__ __forceinline__ unsigned mask_le_c(int x) { return x >= 31 ? 0xffffffffu : ((2u << x) - 1u); }
+
+// find (finds.jl:29-57) on the tile in shared memory: position of the hit or of the predecessor of `key` among the stored cells
+// of [lo, hi] (all of one partition), else the nearest stored cell to the left of lo (an insert's partition semaphore).
+// The reference's gapped binary search probes cells and walks over gaps; here the search first picks the LEAF — fpos[l] is the
+// first stored cell at or after the start of leaf l, and "that cell lies in the range and its key is <= key" is monotone in l —
+// then scans the leaf's stored cells (its live mask) from the right.  Same result (the answer is a property of the contents),
+// a third of the instructions, and no data-dependent walk inside the binary search.
+template <int LGS>
+__device__ __forceinline__ int tile_find(const int64_t* sk, const uint32_t* live, const uint16_t* fpos, int64_t key, int lo, int hi,
+                                         bool* hit) {
+    constexpr int S = 1 << LGS;
     *hit = false;
+    if (lo <= hi) {
+        int a = lo >> LGS, b = hi >> LGS;   // last leaf in (a, b] whose first stored cell is in range with a key <= key; else a
+        int best = a;
+        ++a;
+        while (a <= b) {
+            const int mid = (a + b) >> 1;
+            const int p = fpos[mid];
+            if (p <= hi && sk[p] <= key) {
+                best = mid;
+                a = mid + 1;
+            } else {
+                b = mid - 1;
+            }
+        }
+        const int c0 = best << LGS;
+        unsigned m = live[best];
+        if (lo > c0) m &= ~((1u << (lo - c0)) - 1u);
+        if (hi < c0 + S - 1) m &= mask_le_c(hi - c0);
+        while (m) {
+            const int q = 31 - __clz(m);
+            const int64_t k = sk[c0 + q];
+            if (k <= key) {
+                *hit = k == key;
+                return c0 + q;
+            }
+            m ^= 1u << q;
+        }
+        hi = lo - 1;
+    }
     int i = hi;
     while (i > 0 && sk[i] == GAP_KEY) --i;   // finds.jl:49-56 (the predecessor lies in this tile by construction)
     return i < 0 ? 0 : i;
@@ -194,6 +214,7 @@ struct TileSmem {
     uint32_t insm[TILE_MAX_LEAVES];   // merged ranks taken by the inserts (leaves re-laid here)
     int nins[TILE_MAX_LEAVES];        // inserts of the leaf
     int lhead[TILE_MAX_LEAVES];       // first op of the leaf's list (-1 = none)
+    uint16_t fpos[TILE_MAX_LEAVES];   // first stored cell at or after the start of the leaf (TILE_CELLS = none)
     // per op
     uint16_t rpos[TILE_CAP];          // tile-local position of the hit / predecessor; bit 15 = hit
     int16_t rnext[TILE_CAP];          // next op of the same leaf (-1 = end)
@@ -298,6 +319,17 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_CTAS_PER_SM) k_tile_merge(T
             if (lane < G) s.live[row * G + lane] = (b >> (lane << lgS)) & gmask;
         }
     }
+    __syncthreads();
+    for (int l = tid; l < NL; l += TILE_THREADS) {   // first stored cell at or after the leaf's start (an empty leaf: rare)
+        const unsigned m = s.live[l];
+        int p = (l << lgS) + __ffs(m) - 1;
+        if (m == 0) {
+            p = (l + 1) << lgS;
+            while (p < TILE_CELLS && s.sk[p] == GAP_KEY) ++p;
+        }
+        s.fpos[l] = (uint16_t)p;
+    }
+    __syncthreads();
 
     // ---- B: every op located in shared memory and pushed on the list of its leaf ---------------------------------------
 #pragma unroll
@@ -308,7 +340,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_CTAS_PER_SM) k_tile_merge(T
             const int64_t key = (int64_t)((uint64_t)(uint32_t)a.x | ((uint64_t)(uint32_t)a.y << 32));
             const int lo = (int)((uint32_t)b.z & 0xffffu), hi = (int)((uint32_t)b.z >> 16);
             bool hit = false;
-            const int pos = tile_find(s.sk, key, lo, hi, &hit);
+            const int pos = tile_find<LGS>(s.sk, s.live, s.fpos, key, lo, hi, &hit);
             s.rkey[j] = key;
             s.rval[j] = __longlong_as_double((long long)((uint64_t)(uint32_t)a.z | ((uint64_t)(uint32_t)a.w << 32)));
             s.u.op.rarr[j] = (uint32_t)b.x;
