@@ -67,9 +67,9 @@ static bool tile_eligible(Pcsr& P, const BatchCtx& c) {
         P.tile_penalty -= 1;
         return false;
     }
-    // below ~capacity/64 ops the random-access pipeline moves fewer bytes than one pass over the array; above TILE_CAP/2 ops
-    // per tile on average a bucket is likely to overflow
-    return c.n >= g.capacity / 64 && c.n <= ntiles * (TILE_CAP / 2);
+    // measured crossover at config 2's shape (profiles/tile_crossover_r02.log): the random-access pipeline wins below
+    // ~capacity/45 ops, one pass over the array above; beyond TILE_CAP/2 ops per tile on average a bucket is likely to overflow
+    return c.n >= g.capacity / 40 && c.n <= ntiles * (TILE_CAP / 2);
 }
 
 static void phase1_launch(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t st) {

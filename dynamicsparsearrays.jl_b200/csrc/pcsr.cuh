@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(256) k_scatter_x(const int64_t* __restrict__ x
 constexpr int TILE_LG = DSA_TILE_LG, TILE_CELLS = 1 << TILE_LG;   // 1024 cells = 16 KB of keys + values
 constexpr int TILE_CAP = TILE_CELLS / 4;                  // ops a tile's bucket holds
 constexpr int TILE_THREADS = TILE_CELLS / 8;              // a thread moves 4 x 16 bytes of keys and of values each way
-constexpr int TILE_CTAS_PER_SM = TILE_LG == 10 ? 11 : 5;
+constexpr int TILE_CTAS_PER_SM = TILE_LG == 9 ? 20 : TILE_LG == 10 ? 11 : 5;
 constexpr int TILE_PREFETCH_DIST = 148 * TILE_CTAS_PER_SM;   // tiles in flight on a B200: the L2 prefetch runs one wave ahead
 constexpr int TILE_MAX_LEAVES = TILE_CELLS / 8;           // segment capacity >= 8
 

@@ -232,7 +232,7 @@ int64_t dsa_cached_bytes(void);
 
 /* ---------------------------------------------------------------- tuning --------------- */
 /* How a batched setindex! of a matrix orientation (pcsr.jl:341-347 per op) is applied.  0: always the random-access pipeline
- * (per-partition buckets / radix sort, locate in HBM, leaf merge).  1 (default): batches of at least capacity/64 ops are
+ * (per-partition buckets / radix sort, locate in HBM, leaf merge).  1 (default): batches of at least capacity/40 ops are
  * tile-streamed (one pass over the array, every op located and every accepted leaf re-laid in shared memory); a batch that
  * creates columns or overflows a tile's bucket starts over on the random-access pipeline.  2: tile-streamed whenever the
  * structure allows it (tests).  Both pipelines leave the same layout, bit for bit.  Returns the previous mode. */
