@@ -78,10 +78,10 @@ static void phase1_launch(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t 
     if (c.tile) {
         // one block, one memset: [batch statistics][per-tile op counters]
         const int64_t ntiles = P.pma.g.capacity >> TILE_LG;
-        int32_t* blk = ws.bcnt.ensure((size_t)ntiles + 1 + 2 * CS_WORDS);
+        int32_t* blk = ws.bcnt.ensure((size_t)ntiles * TILE_CNT_STRIDE + 1 + 2 * CS_WORDS);
         int64_t* cs = (int64_t*)blk;
         TileRec* rec = ws.trec.ensure((size_t)ntiles * TILE_CAP);
-        DSA_CUDA(cudaMemsetAsync(blk, 0, ((size_t)ntiles + 1 + 2 * CS_WORDS) * 4, st));
+        DSA_CUDA(cudaMemsetAsync(blk, 0, ((size_t)ntiles * TILE_CNT_STRIDE + 1 + 2 * CS_WORDS) * 4, st));
         const int32_t* next_slot = P.nslots() == P.nlive() ? nullptr : P.d_next_slot.p;   // no tombstones: the next slot is s + 1
         DSA_LAUNCH("tile_assign", k_tile_assign, lookup_grid(c.n), 256, 0, st, c.partkeys, c.inkeys, c.vals, c.n, c.n_dev, P.d_live_keys.p,
                    P.d_live_slot.p, P.nlive(), P.keymap(), P.keymap_min, P.keymap_len, P.pma.keys.p, P.pma.g.capacity, P.d_sem.p, next_slot,
@@ -1043,10 +1043,7 @@ static void spmv_dense_dev(dsa_matrix_t* A, int trans, const double* d_x, int64_
     cudaStream_t st = A->sh.st;
     Pcsr& P = trans ? A->colmajor : A->rowmajor;
     DSA_CUDA(cudaMemsetAsync(d_y, 0, (size_t)ny * 8, st));
-    matrix_spmv_slots(A, trans, d_x, nullptr, nx);
-    const int64_t ns = P.nslots();
-    if (ns > 0)
-        DSA_LAUNCH("spmv_to_dense", k_spmv_to_dense, grid_for(ns, 256), 256, 0, st, A->ws.yslot.p, P.d_sem.p, P.d_slot_key.p, ns, d_y, ny);
+    P.spmv_dense(A->ws, d_x, nx, d_y, ny, st);
 }
 int dsa_matrix_spmv_dense(dsa_matrix_t* A, int trans, const double* x, int64_t nx, double* y, int64_t ny) {
     DSA_TRY

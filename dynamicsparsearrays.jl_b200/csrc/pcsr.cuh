@@ -549,6 +549,31 @@ __global__ void __launch_bounds__(256) k_spmv_fixup(double* __restrict__ yslot, 
 }
 
 
+// Dense-output epilogue in ONE kernel, driven by slot: the carry fix-up of k_spmv_fixup (same additions in the same order: the
+// partition that is open at the end of its chunk adds the carries of the following chunks up to and including the first one
+// with a head) and the scatter of y by partition key.  A slot is the last head of its chunk iff its span reaches the chunk's end.
+__global__ void __launch_bounds__(256) k_spmv_fix_to_dense(const double* __restrict__ yslot, const double* __restrict__ carry,
+                                                            const int32_t* __restrict__ chunk_last_slot, const int64_t* __restrict__ sem,
+                                                            const int32_t* __restrict__ next_slot, const int64_t* __restrict__ slot_key,
+                                                            int64_t nslots, int64_t cap, int64_t nchunks, int lg_chunk,
+                                                            double* __restrict__ y, int64_t ny) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nslots) return;
+    const int64_t ps = sem[s];
+    if (ps < 0) return;
+    const int64_t k = slot_key[s];
+    if (k < 1 || k > ny) return;
+    double a = yslot[s];
+    const int64_t c0 = ps >> lg_chunk;
+    if (span_end(sem, next_slot, (int32_t)s, cap) >= ((c0 + 1) << lg_chunk)) {
+        for (int64_t d = c0 + 1; d < nchunks; ++d) {
+            a = __dadd_rn(a, carry[d]);
+            if (chunk_last_slot[d] >= 0) break;
+        }
+    }
+    y[k - 1] = a;
+}
+
 // y by slot -> dense y indexed by partition key (1..ny)
 __global__ void __launch_bounds__(256) k_spmv_to_dense(const double* __restrict__ yslot, const int64_t* __restrict__ sem,
                                                         const int64_t* __restrict__ slot_key, int64_t nslots, double* __restrict__ y, int64_t ny) {
@@ -594,6 +619,10 @@ constexpr int TILE_THREADS = TILE_CELLS / 8;              // a thread moves 4 x 
 constexpr int TILE_CTAS_PER_SM = TILE_LG == 9 ? 20 : TILE_LG == 10 ? 11 : 5;
 constexpr int TILE_PREFETCH_DIST = 148 * TILE_CTAS_PER_SM;   // tiles in flight on a B200: the L2 prefetch runs one wave ahead
 constexpr int TILE_MAX_LEAVES = TILE_CELLS / 8;           // segment capacity >= 8
+#ifndef DSA_TILE_CNT_STRIDE
+#define DSA_TILE_CNT_STRIDE 8
+#endif
+constexpr int TILE_CNT_STRIDE = DSA_TILE_CNT_STRIDE;      // a tile's op counter has a 32-byte sector to itself: the L2 serialises atomics per sector
 
 struct __align__(16) TileRec {   // 32 B: one sector per op
     int64_t key;     // in-array key
@@ -765,7 +794,7 @@ struct Pcsr {
     // d_xkeys != nullptr: x = (d_xkeys, d_x)[nx] ascending, looked up by binary search (no dense buffer).
     template <int C>
     void spmv_launch_blocked(PcsrWorkspace& ws, const double* d_x, const uint8_t* d_xmask, int64_t nx, cudaStream_t st,
-                             const int64_t* d_xkeys = nullptr) {
+                             const int64_t* d_xkeys = nullptr, bool fixup = true) {
         const int64_t cap = pma.g.capacity;
         const int64_t nchunks = (cap + 32 * C - 1) / (32 * C);
         const int64_t ns = nslots();
@@ -786,13 +815,23 @@ struct Pcsr {
         } else {
             DSA_LAUNCH("spmv_blocked", (k_spmv_blocked<0, C>), gr, 256, 0, st, pma.keys.p, pma.vals.p, cap, d_x, d_xmask, d_xkeys, nx, yslot, ycnt,
                        carry, ccnt, clast, nchunks);
-            DSA_LAUNCH("spmv_fixup", k_spmv_fixup<false>, grid_for(nchunks, 256), 256, 0, st, yslot, ycnt, carry, ccnt, clast, nchunks);
+            if (fixup) DSA_LAUNCH("spmv_fixup", k_spmv_fixup<false>, grid_for(nchunks, 256), 256, 0, st, yslot, ycnt, carry, ccnt, clast, nchunks);
         }
     }
     // SpMV; results by slot in ws.yslot / ws.ycnt
+    static constexpr int SPMV_CELLS_PER_LANE = 4, SPMV_LG_CHUNK = 7;   // a warp's chunk = 32 lanes x 4 cells
     void spmv_slots(PcsrWorkspace& ws, const double* d_x, const uint8_t* d_xmask, int64_t nx, cudaStream_t st,
                     const int64_t* d_xkeys = nullptr) {
-        spmv_launch_blocked<4>(ws, d_x, d_xmask, nx, st, d_xkeys);
+        spmv_launch_blocked<SPMV_CELLS_PER_LANE>(ws, d_x, d_xmask, nx, st, d_xkeys);
+    }
+    // mat * dense x -> dense y (y zeroed by the caller): reduction kernel + one epilogue kernel (fix-up and scatter by key)
+    void spmv_dense(PcsrWorkspace& ws, const double* d_x, int64_t nx, double* d_y, int64_t ny, cudaStream_t st) {
+        spmv_launch_blocked<SPMV_CELLS_PER_LANE>(ws, d_x, nullptr, nx, st, nullptr, /*fixup=*/false);
+        const int64_t ns = nslots(), cap = pma.g.capacity;
+        const int64_t nchunks = (cap + (1 << SPMV_LG_CHUNK) - 1) >> SPMV_LG_CHUNK;
+        if (ns > 0)
+            DSA_LAUNCH("spmv_fix_to_dense", k_spmv_fix_to_dense, grid_for(ns, 256), 256, 0, st, ws.yslot.p, ws.carry.p, ws.chunk_last.p, d_sem.p,
+                       d_next_slot.p, d_slot_key.p, ns, cap, nchunks, SPMV_LG_CHUNK, d_y, ny);
     }
 
     void clone_from(const Pcsr& o, cudaStream_t st) {

@@ -354,6 +354,7 @@ __global__ void __launch_bounds__(256) k_insert_leaf_info(const int64_t* __restr
 //   k_select_pending  the queued leaves continue leaf -> root and mark the first window inside its density bounds.
 // ---------------------------------------------------------------------------------------------
 constexpr int TREE_LEAVES_PER_THREAD = 4, TREE_THREADS = 256, TREE_TILE = TREE_LEAVES_PER_THREAD * TREE_THREADS;   // 1024 leaves per CTA
+constexpr int TREE_UP_NODES = 2048;   // upper levels of the tree that the last CTA finishes in shared memory
 __global__ void __launch_bounds__(TREE_THREADS) k_tree_low(const int32_t* __restrict__ leafcnt, const int32_t* __restrict__ inscnt,
                                                             int32_t* __restrict__ post, Levels L, const uint8_t* __restrict__ touched,
                                                             uint8_t* __restrict__ mark, int64_t* __restrict__ status,
@@ -410,10 +411,31 @@ __global__ void __launch_bounds__(TREE_THREADS) k_tree_low(const int32_t* __rest
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    for (int k = 11; k <= L.H; ++k) {
+    int k = 11;
+    for (; k <= L.H && (L.nsegs >> (k - 1)) > TREE_UP_NODES; ++k) {   // huge arrays: one global round trip per level
         const int64_t nodes = L.nsegs >> k;
         for (int64_t i = threadIdx.x; i < nodes; i += TREE_THREADS)
             post[L.off[k] + i] = __ldcg(&post[L.off[k - 1] + 2 * i]) + __ldcg(&post[L.off[k - 1] + 2 * i + 1]);
+        __syncthreads();
+    }
+    if (k > L.H) return;
+    // the remaining levels hold at most TREE_UP_NODES nodes: one load into shared memory, then no more global round trips
+    // (10 levels at ~1 us each otherwise)
+    __shared__ int32_t up[2][TREE_UP_NODES];
+    int cur = 0;
+    {
+        const int n = (int)(L.nsegs >> (k - 1));
+        for (int i = threadIdx.x; i < n; i += TREE_THREADS) up[0][i] = __ldcg(&post[L.off[k - 1] + i]);
+    }
+    __syncthreads();
+    for (; k <= L.H; ++k) {
+        const int nodes = (int)(L.nsegs >> k);
+        for (int i = threadIdx.x; i < nodes; i += TREE_THREADS) {
+            const int32_t u = up[cur][2 * i] + up[cur][2 * i + 1];
+            up[cur ^ 1][i] = u;
+            post[L.off[k] + i] = u;
+        }
+        cur ^= 1;
         __syncthreads();
     }
 }
@@ -707,12 +729,13 @@ __global__ void __launch_bounds__(256) k_window_small(MergeArgs A, Levels L, uin
     const int64_t i = blockIdx.x;
     const int h = A.hi_h[i];
     const int64_t w = A.hi_w[i];
-    // outermost (no marked ancestor)?  then its leaves are covered by it: k_leaf_merge (launched after this kernel) skips them
-    if (threadIdx.x == 0) {
-        int mx = 1;
-        for (int g = h + 1; g <= L.H; ++g)
-            if (A.mark[L.off[g] + (w >> (g - h))]) { mx = 0; break; }
-        is_max = mx;
+    // outermost (no marked ancestor)?  then its leaves are covered by it: k_leaf_merge (launched after this kernel) skips them.
+    // One lane per ancestor level (the loads of a serial walk up the tree were most of this kernel's duration).
+    if (threadIdx.x < 32) {
+        const int g = h + 1 + (int)threadIdx.x;
+        const bool mk = g <= L.H && A.mark[L.off[g] + (w >> (g - h))] != 0;
+        const unsigned b = __ballot_sync(0xffffffffu, mk);
+        if (threadIdx.x == 0) is_max = b == 0;
     }
     __syncthreads();
     if (!is_max) return;

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256, 6) k_tile_assign(const int64_t* __restric
             hi = to < tb0 + TILE_CELLS - 1 ? to : tb0 + TILE_CELLS - 1;
         }
         const int64_t tb = t << TILE_LG;
-        const int li = atomicAdd(&tcnt[t], 1);
+        const int li = atomicAdd(&tcnt[t * TILE_CNT_STRIDE], 1);
         bmax = li + 1 > bmax ? li + 1 : bmax;
         if (li < TILE_CAP) {
             int4* out = reinterpret_cast<int4*>(rec + t * TILE_CAP + li);
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_CTAS_PER_SM) k_tile_merge(T
     constexpr int VPT = TILE_CELLS / 2 / TILE_THREADS;   // 16-byte key loads per thread
 
     // ---- A: the tile's keys and the tile's ops, all loads in flight together; live mask per leaf -----------------------
-    int nrec = A.tcnt[t];
+    int nrec = A.tcnt[(int64_t)t * TILE_CNT_STRIDE];
     int4 ra[OPT], rb[OPT];
     {
         // the tile that the CTA taking this one's place will work on: its keys and the head of its bucket are pulled into L2 now
