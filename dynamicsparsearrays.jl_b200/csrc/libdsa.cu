@@ -709,6 +709,7 @@ int dsa_vec_clone(const dsa_vec_t* v, dsa_vec_t** out) {
     DSA_CUDA(cudaMemcpyAsync(c->pma.keys.p, v->pma.keys.p, (size_t)v->pma.g.capacity * 8, cudaMemcpyDeviceToDevice, st));
     DSA_CUDA(cudaMemcpyAsync(c->pma.vals.p, v->pma.vals.p, (size_t)v->pma.g.capacity * 8, cudaMemcpyDeviceToDevice, st));
     DSA_CUDA(cudaMemcpyAsync(c->pma.leafcnt.p, v->pma.leafcnt.p, (size_t)v->pma.g.nb_segments * 4, cudaMemcpyDeviceToDevice, st));
+    c->pma.copy_destpos_from(v->pma, st);
     DSA_CUDA(cudaStreamSynchronize(st));
     *out = c.release();
     return DSA_OK;

@@ -1039,6 +1039,14 @@ struct PmaCore {
         }
         DSA_LAUNCH("layout_build", k_layout, grid_for(g.capacity, 256), 256, 0, st, keys.p, vals.p, g.capacity, n, d_k, d_v,
                    leafcnt.p, d_sem, lgS);
+        ensure_destpos(st);   // the segment capacity is fixed from here on (pma.jl:143-161 keep it): no upload inside a batch
+    }
+    // a copy inherits the table (device to device, no synchronisation)
+    void copy_destpos_from(const PmaCore& o, cudaStream_t st) {
+        if (o.destpos_S < 0) return;
+        destpos.ensure(33 * 32);
+        DSA_CUDA(cudaMemcpyAsync(destpos.p, o.destpos.p, 33 * 32, cudaMemcpyDeviceToDevice, st));
+        destpos_S = o.destpos_S;
     }
 
     // The batch tail shared by every mutation: ops are located (op_pos/op_flag), deletes/purges already counted in leafcnt

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list into per-kernel shares of one step.
-A step ends with k_spmv_to_dense; the last `--steps` complete steps are averaged.
+A step ends with the SpMV epilogue (k_spmv_fix_to_dense, k_spmv_to_dense before it); the last `--steps` complete steps are averaged.
 usage: python profiles/summarize_launches.py gpurun_out/launches.csv [--steps 2] > profiles/launches_rXX.md"""
 import collections
 import csv
@@ -18,7 +18,7 @@ for r in rows[hi + 1:]:
     if len(r) > vi:
         name = re.sub(r"\(.*", "", r[ki]).replace("dsa::", "").replace("void ", "")
         data.append((name, float(r[vi].replace(",", "")) / 1e3))
-ends = [i for i, (n, _) in enumerate(data) if n.startswith("k_spmv_to_dense")]
+ends = [i for i, (n, _) in enumerate(data) if n.startswith("k_spmv_to_dense") or n.startswith("k_spmv_fix_to_dense")]
 if len(ends) < nsteps + 1:
     nsteps = max(len(ends) - 1, 1)
 lo, hi_ = ends[-nsteps - 1] + 1, ends[-1] + 1
