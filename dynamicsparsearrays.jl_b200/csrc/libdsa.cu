@@ -62,14 +62,17 @@ static bool tile_eligible(Pcsr& P, const BatchCtx& c) {
     const Geometry& g = P.pma.g;
     if (g.capacity < TILE_CELLS || g.segment_capacity < 8 || g.segment_capacity > 32 || P.nslots() == 0) return false;
     const int64_t ntiles = g.capacity >> TILE_LG;
-    if (g_tile_mode >= 2) return c.n <= ntiles * TILE_CAP;
+    // a distributed batch only has an upper bound of its size on the host (W x the largest share): the size of the previous
+    // batch of this orientation is the better estimate
+    const int64_t n = (c.n_dev && P.last_batch_n > 0) ? std::min(c.n, P.last_batch_n) : c.n;
+    if (g_tile_mode >= 2) return n <= ntiles * TILE_CAP;
     if (P.tile_penalty > 0) {   // a recent batch overflowed a tile bucket or created columns: do not pay for the attempt again at once
         P.tile_penalty -= 1;
         return false;
     }
     // measured crossover at config 2's shape (profiles/tile_crossover_r02.log): the random-access pipeline wins below
     // ~capacity/45 ops, one pass over the array above; beyond TILE_CAP/2 ops per tile on average a bucket is likely to overflow
-    return c.n >= g.capacity / 40 && c.n <= ntiles * (TILE_CAP / 2);
+    return n >= g.capacity / 40 && n <= ntiles * (TILE_CAP / 2);
 }
 
 static void phase1_launch(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t st) {
@@ -115,6 +118,7 @@ static void phase1_read(PcsrWorkspace& ws, BatchCtx& c) {
 // A tile-streamed attempt is refused when the batch creates columns or overflows a tile's bucket: nothing has been modified
 // (k_tile_assign only reads the structure), the batch starts over on the general path.  Returns true if it must be relaunched.
 static bool tile_refused(Pcsr& P, BatchCtx& c) {
+    P.last_batch_n = c.n;   // exact by now (phase1_read)
     if (!c.tile) return false;
     if (c.bs.missing == 0 && c.bs.maxbucket <= TILE_CAP) return false;
     c.tile = false;

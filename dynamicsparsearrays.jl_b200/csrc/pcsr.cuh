@@ -671,6 +671,7 @@ struct Pcsr {
     std::vector<int32_t> next_slot_h;
     int64_t max_inkey = 0;      // upper bound of the in-array keys ever stored (sizes the dense x of SpMV)
     int tile_penalty = 0;       // batches to wait before the next tile-streamed attempt (after a refused one)
+    int64_t last_batch_n = 0;   // ops of the previous batch (the host only has an upper bound of a distributed batch's size)
 
     const int32_t* keymap() const { return keymap_len > 0 ? d_keymap.p : nullptr; }
     int64_t nslots() const { return (int64_t)slot_key.size(); }
