@@ -406,4 +406,8 @@ function SparseArrays.nnz(A::ShardedDynamicSparseMatrix)                        
     return out[3]
 end
 
+# How a batched setindex! is applied (include/dsa.h "tuning"): 0 = random-access pipeline only, 1 = dense batches are
+# tile-streamed (default), 2 = tile-streamed whenever possible.  Same layout either way; returns the previous mode.
+set_tile_mode!(mode::Integer) = ccall((:dsa_set_tile_mode, libdsa), Cint, (Cint,), mode)
+
 end # module
