@@ -28,7 +28,7 @@ constexpr int SMALL_CELLS = 2048;
 
 enum : uint8_t { FL_OVERWRITE = 1, FL_DELETE = 2, FL_INSERT = 4 };
 enum { ST_OVER = 0, ST_UNDER = 1, ST_NINS = 2, ST_ROOT = 3, ST_NHIGH = 4, ST_ANYBIG = 5, ST_NACT = 6, ST_ANYHIGH = 7, ST_TICKET = 8, ST_NPEND = 9,
-       ST_NBIG = 10, ST_MAXBIGH = 11, ST_WORDS = 16 };
+       ST_NBIG = 10, ST_MAXBIGH = 11, ST_MAXSMALLH = 12, ST_WORDS = 16 };
 
 __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;
@@ -461,6 +461,9 @@ __global__ void __launch_bounds__(256) k_select_pending(const int32_t* __restric
                     hi_h[slot] = h;
                     hi_w[slot] = l >> h;
                     status[ST_ANYHIGH] = 1;
+                    // sizes k_window_small's CTAs (the plain read keeps thousands of windows of one height off the atomic unit)
+                    if (h <= L.hsmall && (int64_t)h > *(volatile int64_t*)&status[ST_MAXSMALLH])
+                        atomicMax((long long*)&status[ST_MAXSMALLH], (long long)h);
                     if (h > L.hsmall) {   // too large for one CTA's shared memory: its own work list
                         status[ST_ANYBIG] = 1;
                         const unsigned long long bs = atomicAdd((unsigned long long*)&status[ST_NBIG], 1ull);
@@ -722,9 +725,12 @@ __global__ void __launch_bounds__(256) k_leaf_merge(MergeArgs A, Levels L) {
 // SMALL_CELLS cells are re-laid here: the merged, ranked items are scattered to their spread! offsets in shared memory, then the
 // window is written back coalesced (pack! + spread!, moves.jl:94-172, in one pass), with leaf counts and semaphore positions.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_window_small(MergeArgs A, Levels L, uint8_t* __restrict__ cover) {
-    __shared__ int64_t sk[SMALL_CELLS];
-    __shared__ double sv[SMALL_CELLS];
+// Shared memory (dynamic) and block size follow the LARGEST small window of the batch (`cells`): a batch whose windows are a few
+// leaves each runs 32 CTAs of 64 threads per SM instead of 7 of 256.
+__global__ void __launch_bounds__(256) k_window_small(MergeArgs A, Levels L, uint8_t* __restrict__ cover, int cells) {
+    extern __shared__ __align__(16) unsigned char window_smem[];
+    int64_t* sk = reinterpret_cast<int64_t*>(window_smem);
+    double* sv = reinterpret_cast<double*>(sk + cells);
     __shared__ int is_max;
     const int64_t i = blockIdx.x;
     const int h = A.hi_h[i];
@@ -1122,7 +1128,12 @@ struct PmaCore {
             const int64_t nhigh = hs[ST_NHIGH];
             // windows above leaf level: cover marks + the small ones re-laid through shared memory, one CTA each (before the leaf
             // merge, which skips covered leaves)
-            if (nhigh > 0) DSA_LAUNCH("window_small", k_window_small, (unsigned)nhigh, 256, 0, st, A, L, cover);
+            if (nhigh > 0) {
+                const int hmax = (int)std::min<int64_t>(std::max<int64_t>(hs[ST_MAXSMALLH], 1), L.hsmall);
+                const int cells = (int)(g.segment_capacity << hmax);
+                const int threads = std::min(256, std::max(64, cells / 2));
+                DSA_LAUNCH("window_small", k_window_small, (unsigned)nhigh, threads, (size_t)cells * 16, st, A, L, cover, cells);
+            }
             // leaves accepted at their own level (the common case), in place
             const int leaves_per_warp = 32 >> L.lgS;
             const int64_t nact = hs[ST_NACT];
