@@ -322,10 +322,9 @@ static void dist_spmv(dsa_dmatrix* D, int trans, const double* d_x, int64_t nx, 
     double* slice = yb + (size_t)d->rank * per;
     DSA_CUDA(cudaMemsetAsync(slice, 0, (size_t)per * 8, st));
     Pcsr& Pm = trans ? A->colmajor : A->rowmajor;
-    matrix_spmv_slots(A, trans, d_x, nullptr, nx);
-    const int64_t ns = Pm.nslots();
-    if (ns > 0 && hi > lo)   // epilogue: this rank's slice is written straight into the gather buffer
-        DSA_LAUNCH("spmv_to_dense", k_spmv_to_dense_range, grid_for(ns, 256), 256, 0, st, A->ws.yslot.p, Pm.d_sem.p, Pm.d_slot_key.p, ns, slice, lo, hi);
+    // the epilogue (carry fix-up + scatter by key) writes this rank's slice straight into the gather buffer
+    if (hi > lo) Pm.spmv_dense(A->ws, d_x, nx, slice, lo, hi, st);
+    else matrix_spmv_slots(A, trans, d_x, nullptr, nx);
     dist_all_gather(d, slice, yb, (size_t)per, ncclFloat64, st);
     if (ny <= 0) return;
     if (D->even[which]) {

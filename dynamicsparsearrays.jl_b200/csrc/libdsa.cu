@@ -78,6 +78,16 @@ static bool tile_eligible(Pcsr& P, const BatchCtx& c) {
 static void phase1_launch(Pcsr& P, PcsrWorkspace& ws, BatchCtx& c, cudaStream_t st) {
     int64_t* hcs = ws.h_cs.ensure(CS_WORDS);
     c.tile = tile_eligible(P, c);
+    if (c.tile) {   // the buckets are workspace (capacity x 8 bytes): without room for them the batch takes the general path
+        try {
+            ws.trec.ensure((size_t)(P.pma.g.capacity >> TILE_LG) * TILE_CAP);
+        } catch (const DsaError& e) {
+            if (e.code != DSA_ERR_OOM) throw;
+            c.tile = false;
+            c.no_tile = true;
+            P.tile_penalty = 64;
+        }
+    }
     if (c.tile) {
         // one block, one memset: [batch statistics][per-tile op counters]
         const int64_t ntiles = P.pma.g.capacity >> TILE_LG;
@@ -1048,7 +1058,7 @@ static void spmv_dense_dev(dsa_matrix_t* A, int trans, const double* d_x, int64_
     cudaStream_t st = A->sh.st;
     Pcsr& P = trans ? A->colmajor : A->rowmajor;
     DSA_CUDA(cudaMemsetAsync(d_y, 0, (size_t)ny * 8, st));
-    P.spmv_dense(A->ws, d_x, nx, d_y, ny, st);
+    P.spmv_dense(A->ws, d_x, nx, d_y, 1, ny + 1, st);
 }
 int dsa_matrix_spmv_dense(dsa_matrix_t* A, int trans, const double* x, int64_t nx, double* y, int64_t ny) {
     DSA_TRY
@@ -1123,29 +1133,15 @@ int dsa_matrix_set_batch_two_d(dsa_matrix_t* A, const int64_t* d_rows_c, const i
     return DSA_OK;
     DSA_CATCH
 }
-}  // extern "C"
-namespace dsa {
-__global__ void __launch_bounds__(256) k_spmv_to_dense_range(const double* __restrict__ yslot, const int64_t* __restrict__ sem,
-                                                              const int64_t* __restrict__ slot_key, int64_t nslots, double* __restrict__ y,
-                                                              int64_t key_lo, int64_t key_hi) {
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nslots || sem[s] < 0) return;
-    const int64_t k = slot_key[s];
-    if (k >= key_lo && k < key_hi) y[k - key_lo] = yslot[s];
-}
-}  // namespace dsa
-extern "C" {
 int dsa_matrix_spmv_dense_range_d(dsa_matrix_t* A, int trans, const double* d_x, int64_t nx, double* d_y, int64_t key_lo,
                                   int64_t key_hi) {
     DSA_TRY
     cudaStream_t st = A->sh.st;
     Pcsr& P = trans ? A->colmajor : A->rowmajor;
-    if (key_hi > key_lo) DSA_CUDA(cudaMemsetAsync(d_y, 0, (size_t)(key_hi - key_lo) * 8, st));
-    matrix_spmv_slots(A, trans, d_x, nullptr, nx);
-    const int64_t ns = P.nslots();
-    if (ns > 0)
-        DSA_LAUNCH("spmv_to_dense", k_spmv_to_dense_range, grid_for(ns, 256), 256, 0, st, A->ws.yslot.p, P.d_sem.p, P.d_slot_key.p, ns, d_y,
-                   key_lo, key_hi);
+    if (key_hi > key_lo) {
+        DSA_CUDA(cudaMemsetAsync(d_y, 0, (size_t)(key_hi - key_lo) * 8, st));
+        P.spmv_dense(A->ws, d_x, nx, d_y, key_lo, key_hi, st);
+    }
     return DSA_OK;
     DSA_CATCH
 }

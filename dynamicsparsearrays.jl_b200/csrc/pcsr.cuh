@@ -556,13 +556,13 @@ __global__ void __launch_bounds__(256) k_spmv_fix_to_dense(const double* __restr
                                                             const int32_t* __restrict__ chunk_last_slot, const int64_t* __restrict__ sem,
                                                             const int32_t* __restrict__ next_slot, const int64_t* __restrict__ slot_key,
                                                             int64_t nslots, int64_t cap, int64_t nchunks, int lg_chunk,
-                                                            double* __restrict__ y, int64_t ny) {
+                                                            double* __restrict__ y, int64_t key_lo, int64_t key_hi) {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nslots) return;
     const int64_t ps = sem[s];
     if (ps < 0) return;
     const int64_t k = slot_key[s];
-    if (k < 1 || k > ny) return;
+    if (k < key_lo || k >= key_hi) return;   // y holds the partition keys [key_lo, key_hi)
     double a = yslot[s];
     const int64_t c0 = ps >> lg_chunk;
     if (span_end(sem, next_slot, (int32_t)s, cap) >= ((c0 + 1) << lg_chunk)) {
@@ -571,17 +571,9 @@ __global__ void __launch_bounds__(256) k_spmv_fix_to_dense(const double* __restr
             if (chunk_last_slot[d] >= 0) break;
         }
     }
-    y[k - 1] = a;
+    y[k - key_lo] = a;
 }
 
-// y by slot -> dense y indexed by partition key (1..ny)
-__global__ void __launch_bounds__(256) k_spmv_to_dense(const double* __restrict__ yslot, const int64_t* __restrict__ sem,
-                                                        const int64_t* __restrict__ slot_key, int64_t nslots, double* __restrict__ y, int64_t ny) {
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nslots || sem[s] < 0) return;
-    const int64_t k = slot_key[s];
-    if (k >= 1 && k <= ny) y[k - 1] = yslot[s];
-}
 // touched partitions (at least one product) for the sparse output (operations.jl:11-12, sparsevec(::Dict, n))
 __global__ void __launch_bounds__(256) k_flag_touched(const int32_t* __restrict__ ycnt, const int64_t* __restrict__ sem, int64_t nslots,
                                                        int32_t* __restrict__ flag) {
@@ -825,14 +817,15 @@ struct Pcsr {
                     const int64_t* d_xkeys = nullptr) {
         spmv_launch_blocked<SPMV_CELLS_PER_LANE>(ws, d_x, d_xmask, nx, st, d_xkeys);
     }
-    // mat * dense x -> dense y (y zeroed by the caller): reduction kernel + one epilogue kernel (fix-up and scatter by key)
-    void spmv_dense(PcsrWorkspace& ws, const double* d_x, int64_t nx, double* d_y, int64_t ny, cudaStream_t st) {
+    // mat * dense x -> dense y over the partition keys [key_lo, key_hi) (y zeroed by the caller): reduction kernel + one
+    // epilogue kernel (fix-up and scatter by key)
+    void spmv_dense(PcsrWorkspace& ws, const double* d_x, int64_t nx, double* d_y, int64_t key_lo, int64_t key_hi, cudaStream_t st) {
         spmv_launch_blocked<SPMV_CELLS_PER_LANE>(ws, d_x, nullptr, nx, st, nullptr, /*fixup=*/false);
         const int64_t ns = nslots(), cap = pma.g.capacity;
         const int64_t nchunks = (cap + (1 << SPMV_LG_CHUNK) - 1) >> SPMV_LG_CHUNK;
         if (ns > 0)
             DSA_LAUNCH("spmv_fix_to_dense", k_spmv_fix_to_dense, grid_for(ns, 256), 256, 0, st, ws.yslot.p, ws.carry.p, ws.chunk_last.p, d_sem.p,
-                       d_next_slot.p, d_slot_key.p, ns, cap, nchunks, SPMV_LG_CHUNK, d_y, ny);
+                       d_next_slot.p, d_slot_key.p, ns, cap, nchunks, SPMV_LG_CHUNK, d_y, key_lo, key_hi);
     }
 
     void clone_from(const Pcsr& o, cudaStream_t st) {
