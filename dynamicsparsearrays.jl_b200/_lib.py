@@ -83,6 +83,12 @@ def check(code):
         raise _EXC.get(code, DsaError)(code, msg)
 
 
+def set_tile_mode(mode):
+    """How a batched setindex! is applied (include/dsa.h, "tuning"): 0 = random-access pipeline only, 1 = dense batches are
+    tile-streamed (default), 2 = tile-streamed whenever the structure allows it.  Same layout either way.  Returns the previous mode."""
+    return int(lib().dsa_set_tile_mode(C.c_int(int(mode))))
+
+
 def device_count():
     n = C.c_int()
     lib().dsa_device_count(C.byref(n))

@@ -13,9 +13,9 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture
 def tile_mode():
-    prev = D.lib().dsa_set_tile_mode(2)
-    yield lambda mode: D.lib().dsa_set_tile_mode(mode)
-    D.lib().dsa_set_tile_mode(prev)
+    prev = D.set_tile_mode(2)
+    yield D.set_tile_mode
+    D.set_tile_mode(prev)
 
 
 def _coo(rng, m, n, nnz):
