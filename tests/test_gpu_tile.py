@@ -161,3 +161,53 @@ def test_tile_streamed_hot_leaves_and_refusals(tile_mode):
         gt.set_batch(np.array([5, 0, 7]), np.array([1, 2, 3]), np.array([1.0, 2.0, 3.0]))
     after = gt.export(0)
     assert np.array_equal(before["tag"], after["tag"]) and np.array_equal(before["key"], after["key"])
+
+
+def test_tile_streamed_with_tombstones_and_empty_partitions(tile_mode):
+    """deleted columns / rows leave tombstones in the column map (the span of a partition then ends at the next LIVE semaphore),
+    a zero write to an absent column leaves an empty partition (semaphore only): batches over such a structure, tile-streamed and
+    through the random-access pipeline, against the oracle"""
+    rng = np.random.default_rng(321)
+    m, n = 3000, 2500
+    I, J, V = _coo(rng, m, n, 70_000)
+    mats = [D.dynamicsparse(I, J, V, m=m, n=n), D.dynamicsparse(I, J, V, m=m, n=n)]
+    pol, seq = O.Matrix(I, J, V, m=m, n=n), O.Matrix(I, J, V, m=m, n=n)
+    # empty partitions: zero writes to columns / rows that do not exist yet (pcsr.jl:341-347 creates the column)
+    r0, c0 = 7, 11   # an existing row and column that stay alive
+    ei, ej, ev = np.array([m + 5, r0, m + 9]), np.array([c0, n + 3, n + 8]), np.zeros(3)
+    for g in mats:
+        g.set_batch(ei, ej, ev)
+    pol.set_batch_policy(ei, ej, ev)
+    seq.set_many(ei, ej, ev)
+    dead_cols = [int(c) for c in rng.choice(np.setdiff1d(np.arange(1, n + 1), [c0]), 120, replace=False)]
+    dead_rows = [int(r) for r in rng.choice(np.setdiff1d(np.arange(1, m + 1), [r0]), 150, replace=False)]
+    for g in mats:
+        D.deletecolumn(g, dead_cols)
+        D.deleterow(g, dead_rows)
+    pol.delete_columns_policy(dead_cols)
+    pol.delete_rows_policy(dead_rows)
+    for c in dead_cols:
+        seq.deletecolumn(c)
+    for r in dead_rows:
+        seq.deleterow(r)
+    assert_matrix_equal(mats[0], pol)
+    assert_matrix_equal(mats[0], seq, layout=False)
+    live_c = np.setdiff1d(np.arange(1, n + 1), dead_cols)
+    live_r = np.setdiff1d(np.arange(1, m + 1), dead_rows)
+    for nb in (9000, 14_000, 6000):
+        I2, J2 = rng.choice(live_r, nb), rng.choice(live_c, nb)   # existing rows and columns only: no partition is created
+        V2 = np.where(rng.random(nb) < 0.35, 0.0, rng.integers(1, 50, nb).astype(float))
+        I2[:3], J2[:3] = [m + 5, r0, m + 9], [c0, n + 3, n + 8]     # writes into the empty partitions (third one: a delete)
+        V2[:3] = [4.0, 5.0, 0.0]
+        tile_mode(2)
+        mats[0].set_batch(I2, J2, V2)
+        tile_mode(0)
+        mats[1].set_batch(I2, J2, V2)
+        pol.set_batch_policy(I2, J2, V2)
+        seq.set_many(I2, J2, V2)
+        assert_matrix_equal(mats[0], pol)
+        assert_matrix_equal(mats[0], seq, layout=False)
+        _same_layout(mats[0], mats[1])
+    x = rng.random(n + 8)
+    y, yo = mats[0].mul_dense(x), seq.mul_dense(x, mats[0].size[0])
+    assert np.all(np.abs(y - yo) <= 1e-12 * np.maximum(np.abs(y), np.abs(yo)))
