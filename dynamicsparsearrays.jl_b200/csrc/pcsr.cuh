@@ -368,11 +368,38 @@ __global__ void __launch_bounds__(256) k_clear_sems(int64_t* __restrict__ sem, c
 // Per-partition order = ascending cells; association: sequential inside a lane, tree across lanes (within the 1e-12 bar,
 // exact for integer-valued data).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void ldg_stream4(const int64_t* p, int64_t& a, int64_t& b, int64_t& c, int64_t& d) {
-    asm volatile("ld.global.nc.L1::no_allocate.v4.s64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+// The big streams (the gapped arrays: 2 x 268 MB per matrix against 126 MB of L2) are loaded with an evict-first L2 policy so that
+// the small random-access tables (semaphore positions, column map, x, tile counters and buckets) stay resident between kernels.
+#ifndef DSA_L2_EVICT_FIRST
+#define DSA_L2_EVICT_FIRST 1
+#endif
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
 }
-__device__ __forceinline__ void ldg_stream4(const double* p, double& a, double& b, double& c, double& d) {
+__device__ __forceinline__ void ldg_stream4(const int64_t* p, int64_t& a, int64_t& b, int64_t& c, int64_t& d, uint64_t pol) {
+#if DSA_L2_EVICT_FIRST
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s64 {%0,%1,%2,%3}, [%4], %5;" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p), "l"(pol));
+#else
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+#endif
+}
+__device__ __forceinline__ void ldg_stream4(const double* p, double& a, double& b, double& c, double& d, uint64_t pol) {
+#if DSA_L2_EVICT_FIRST
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p), "l"(pol));
+#else
     asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+#endif
+}
+__device__ __forceinline__ longlong2 ldg_stream2(const longlong2* p, uint64_t pol) {
+    longlong2 r;
+#if DSA_L2_EVICT_FIRST
+    asm volatile("ld.global.L2::cache_hint.v2.s64 {%0,%1}, [%2], %3;" : "=l"(r.x), "=l"(r.y) : "l"(p), "l"(pol));
+#else
+    r = *p;
+#endif
+    return r;
 }
 
 // XMODE: 0 = dense x (x[key - 1], every entry stored); 1 = dense x + presence mask (a sparse x scattered into a dense buffer);
@@ -390,14 +417,15 @@ __global__ void __launch_bounds__(256) k_spmv_blocked(const int64_t* __restrict_
     const int lane = threadIdx.x & 31;
     if (chunk >= nchunks) return;
     const unsigned lt = lanemask_lt();
+    const uint64_t l2pol = l2_evict_first_policy();
     const int64_t p0 = chunk * (32 * C) + (int64_t)lane * C;
     int64_t k[C];
     double t[C];
 #pragma unroll
     for (int c = 0; c < C; c += 4) {
         if (p0 + c + 4 <= cap) {
-            ldg_stream4(keys + p0 + c, k[c], k[c + 1], k[c + 2], k[c + 3]);
-            ldg_stream4(vals + p0 + c, t[c], t[c + 1], t[c + 2], t[c + 3]);
+            ldg_stream4(keys + p0 + c, k[c], k[c + 1], k[c + 2], k[c + 3], l2pol);
+            ldg_stream4(vals + p0 + c, t[c], t[c + 1], t[c + 2], t[c + 3], l2pol);
         } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {

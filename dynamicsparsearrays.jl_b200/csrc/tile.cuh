@@ -283,10 +283,11 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_CTAS_PER_SM) k_tile_merge(T
             if (tid < TILE_CELLS * 8 / 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pk + tid * 128));
             else if (tid < TILE_CELLS * 8 / 128 + 24) asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + (tid - TILE_CELLS * 8 / 128) * 128));
         }
+        const uint64_t l2pol = l2_evict_first_policy();
         longlong2 kk[VPT];
         const longlong2* gk = reinterpret_cast<const longlong2*>(A.keys + tbase);
 #pragma unroll
-        for (int i = 0; i < VPT; ++i) kk[i] = gk[tid + i * TILE_THREADS];
+        for (int i = 0; i < VPT; ++i) kk[i] = ldg_stream2(gk + tid + i * TILE_THREADS, l2pol);
         if (nrec > TILE_CAP) nrec = TILE_CAP;
 #pragma unroll
         for (int i = 0; i < OPT; ++i) {
