@@ -318,8 +318,10 @@ void Pcsr::set_batch_d(PcsrWorkspace& ws, const int64_t* d_inkeys, const int64_t
 struct StreamHolder {
     cudaStream_t st = nullptr;
     bool owned = false;
-    void create() {
-        DSA_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    void create() {   // highest priority: the work a caller waits for (row-major phases, SpMV) goes ahead of the twin stream's
+        int least = 0, greatest = 0;
+        DSA_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        DSA_CUDA(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, greatest));
         owned = true;
     }
     void set(cudaStream_t s) {
@@ -365,7 +367,7 @@ struct dsa_matrix {
     } slot[2];
     cudaStream_t copy_st = nullptr;
     int staged_head = 0, staged_count = 0;
-    // the row-major twin's batch phases run on their own stream, forked from / joined to sh.st (DSA_TWO_STREAMS=0 disables)
+    // the column-major orientation's batch phases run on their own stream, forked from / joined to sh.st (DSA_TWO_STREAMS=0 disables)
     cudaStream_t twin_st = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     ~dsa_matrix() {
@@ -500,8 +502,8 @@ static void vec_set_batch_dev(dsa_vec* v, const int64_t* d_keys, const double* d
 }
 
 // ---- matrix helpers -----------------------------------------------------------------------------------------------
-// The two orientations go through the batch phases together so that they share each stream synchronisation.  A plain matrix
-// batch feeds both with the same triples; a shard of a distributed matrix feeds them different ones.
+// The two orientations go through the batch phases together so that they share the host decisions.  A plain matrix batch feeds
+// both with the same triples; a shard of a distributed matrix feeds them different ones.
 // nc_dev / nr_dev (nullable): device-side op counts; nc / nr are then upper bounds (distributed batches).
 static void matrix_set_batch_two(dsa_matrix* A, const int64_t* rows_c, const int64_t* cols_c, const double* vals_c, int64_t nc,
                                  const int64_t* rows_r, const int64_t* cols_r, const double* vals_r, int64_t nr,
@@ -511,38 +513,40 @@ static void matrix_set_batch_two(dsa_matrix* A, const int64_t* rows_c, const int
     BatchCtx cc, cr;
     cc.inkeys = rows_c; cc.partkeys = cols_c; cc.vals = vals_c; cc.n = nc; cc.n_dev = nc_dev;   // colmajor[row, col] = v  (matrix.jl:53-55)
     cr.inkeys = cols_r; cr.partkeys = rows_r; cr.vals = vals_r; cr.n = nr; cr.n_dev = nr_dev;   // rowmajor[col, row] = v  (matrix.jl:57-59)
-    // The two orientations are independent (own structure, own workspace) and most of their kernels are single-wave and
-    // latency-bound, so the twin's phases run on a second stream (st2) that forks from st here and joins it at the end:
-    // 0.764 -> 0.668 ms per config-2 step, layouts bit-identical (profiles/exp_r01_update_switches.log).
-    // DSA_TWO_STREAMS=0 puts everything back on one stream (st2 == st).
+    // The two orientations are independent (own structure, own workspace), so the column-major one runs on a second, low-priority
+    // stream (stc) that forks from st here; the row-major one stays on st and, being ahead, finishes first.
+    // DSA_TWO_STREAMS=0 puts everything back on one stream (stc == st).
     static const bool two_streams = [] {
         const char* e = getenv("DSA_TWO_STREAMS");
         return !e || atoi(e) != 0;
     }();
-    cudaStream_t st2 = st;
-    if (two_streams && nc > 0 && nr > 0) {
+    const bool use_two = two_streams && nc > 0 && nr > 0;
+    cudaStream_t stc = st;
+    if (use_two) {
         if (!A->twin_st) {
-            DSA_CUDA(cudaStreamCreateWithFlags(&A->twin_st, cudaStreamNonBlocking));
+            int least = 0, greatest = 0;
+            DSA_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+            DSA_CUDA(cudaStreamCreateWithPriority(&A->twin_st, cudaStreamNonBlocking, least));
             DSA_CUDA(cudaEventCreateWithFlags(&A->ev_fork, cudaEventDisableTiming));
             DSA_CUDA(cudaEventCreateWithFlags(&A->ev_join, cudaEventDisableTiming));
         }
-        st2 = A->twin_st;
+        stc = A->twin_st;
         DSA_CUDA(cudaEventRecord(A->ev_fork, st));        // everything queued on st so far (input copies) precedes the twin's work
-        DSA_CUDA(cudaStreamWaitEvent(st2, A->ev_fork, 0));
+        DSA_CUDA(cudaStreamWaitEvent(stc, A->ev_fork, 0));
     }
     try {
-        if (nc > 0) phase1_launch(A->colmajor, A->ws, cc, st);
-        if (nr > 0) phase1_launch(A->rowmajor, A->ws2, cr, st2);
+        if (nr > 0) phase1_launch(A->rowmajor, A->ws2, cr, st);
+        if (nc > 0) phase1_launch(A->colmajor, A->ws, cc, stc);
         DSA_CUDA(cudaStreamSynchronize(st));
-        if (st2 != st) DSA_CUDA(cudaStreamSynchronize(st2));
+        if (stc != st) DSA_CUDA(cudaStreamSynchronize(stc));
         if (nc > 0) { phase1_read(A->ws, cc); nc = cc.n; }
         if (nr > 0) { phase1_read(A->ws2, cr); nr = cr.n; }
         {   // a refused tile-streamed attempt starts over on the general path (nothing was modified)
             const bool rc = nc > 0 && tile_refused(A->colmajor, cc), rr = nr > 0 && tile_refused(A->rowmajor, cr);
-            if (rc) phase1_launch(A->colmajor, A->ws, cc, st);
-            if (rr) phase1_launch(A->rowmajor, A->ws2, cr, st2);
-            if (rc) DSA_CUDA(cudaStreamSynchronize(st));
-            if (rr) DSA_CUDA(cudaStreamSynchronize(st2));
+            if (rr) phase1_launch(A->rowmajor, A->ws2, cr, st);
+            if (rc) phase1_launch(A->colmajor, A->ws, cc, stc);
+            if (rr) DSA_CUDA(cudaStreamSynchronize(st));
+            if (rc) DSA_CUDA(cudaStreamSynchronize(stc));
             if (rc) phase1_read(A->ws, cc);
             if (rr) phase1_read(A->ws2, cr);
         }
@@ -551,20 +555,20 @@ static void matrix_set_batch_two(dsa_matrix* A, const int64_t* rows_c, const int
         // (both orientations are checked before either one creates a column)
         if (nc > 0) phase1_validate(A->colmajor, cc, "row and column keys");
         if (nr > 0) phase1_validate(A->rowmajor, cr, "row and column keys");
-        if (nc > 0) phase1_finish(A->colmajor, A->ws, cc, st);
-        if (nr > 0) phase1_finish(A->rowmajor, A->ws2, cr, st2);
-        if (nc > 0) phase2_launch(A->colmajor, A->ws, cc, st);
-        if (nr > 0) phase2_launch(A->rowmajor, A->ws2, cr, st2);
+        if (nr > 0) phase1_finish(A->rowmajor, A->ws2, cr, st);
+        if (nc > 0) phase1_finish(A->colmajor, A->ws, cc, stc);
+        if (nr > 0) phase2_launch(A->rowmajor, A->ws2, cr, st);
+        if (nc > 0) phase2_launch(A->colmajor, A->ws, cc, stc);
         DSA_CUDA(cudaStreamSynchronize(st));
-        if (st2 != st) DSA_CUDA(cudaStreamSynchronize(st2));
-        if (nc > 0) phase3(A->colmajor, A->ws, cc, st);
-        if (nr > 0) phase3(A->rowmajor, A->ws2, cr, st2);
-        if (st2 != st) {   // later work on st (SpMV, reads, the next batch) sees the twin's merges
-            DSA_CUDA(cudaEventRecord(A->ev_join, st2));
+        if (nr > 0) phase3(A->rowmajor, A->ws2, cr, st);     // the row-major orientation is not held back by the other one
+        if (stc != st) DSA_CUDA(cudaStreamSynchronize(stc));
+        if (nc > 0) phase3(A->colmajor, A->ws, cc, stc);
+        if (stc != st) {   // later work on st that needs the column-major orientation sees its merges
+            DSA_CUDA(cudaEventRecord(A->ev_join, stc));
             DSA_CUDA(cudaStreamWaitEvent(st, A->ev_join, 0));
         }
     } catch (...) {
-        if (st2 != st) cudaStreamSynchronize(st2);
+        if (stc != st) cudaStreamSynchronize(stc);
         throw;
     }
     // matrix.jl:44-47: dimensions grow on non-zero writes
