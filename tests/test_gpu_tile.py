@@ -18,6 +18,24 @@ def tile_mode():
     D.set_tile_mode(prev)
 
 
+def _kernels_of(fn):
+    """names of the kernels fn() launches (per-kernel event profile of the library)"""
+    import ctypes as C
+    L = D.lib()
+    L.dsa_prof_reset()
+    L.dsa_prof_enable(C.c_int(1))
+    try:
+        fn()
+    finally:
+        L.dsa_prof_enable(C.c_int(0))
+    L.dsa_prof_dump.restype = C.c_int64
+    need = L.dsa_prof_dump(None, C.c_int64(0))
+    buf = C.create_string_buffer(int(need) + 16)
+    L.dsa_prof_dump(buf, C.c_int64(len(buf)))
+    L.dsa_prof_reset()
+    return {ln.split(",")[0] for ln in buf.value.decode().strip().splitlines() if ln}
+
+
 def _coo(rng, m, n, nnz):
     return rng.integers(1, m + 1, nnz), rng.integers(1, n + 1, nnz), rng.random(nnz) + 0.5
 
@@ -211,3 +229,42 @@ def test_tile_streamed_with_tombstones_and_empty_partitions(tile_mode):
     x = rng.random(n + 8)
     y, yo = mats[0].mul_dense(x), seq.mul_dense(x, mats[0].size[0])
     assert np.all(np.abs(y - yo) <= 1e-12 * np.maximum(np.abs(y), np.abs(yo)))
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_tile_streamed_equals_random_access_pipeline_randomized(seed, tile_mode):
+    """many small random shapes and batch mixes: both pipelines must leave the same arrays (the random-access pipeline is the
+    one the other tests tie to the oracle); every 4th seed is also checked against the oracle"""
+    rng = np.random.default_rng(5000 + seed)
+    m, n = int(rng.integers(20, 4000)), int(rng.integers(20, 4000))
+    nnz0 = int(rng.integers(1500, 120_000))
+    I, J, V = _coo(rng, m, n, nnz0)
+    gt, gr = D.dynamicsparse(I, J, V, m=m, n=n), D.dynamicsparse(I, J, V, m=m, n=n)
+    pol = O.Matrix(I, J, V, m=m, n=n) if seed % 4 == 0 else None
+    known = (I, J)
+    cap = gt.info(0)["capacity"]
+    streamed = total = 0
+    for rnd in range(4):
+        nb = int(rng.integers(max(2, cap // 200), max(3, cap // 5)))
+        p_del, p_known, dup = rng.random() * 0.9, rng.random(), rng.random() * 0.2
+        I2, J2, V2 = _mixed_batch(rng, m, n, nb, known, p_del=p_del, p_known=p_known, dup=dup)
+        # only existing rows / columns, so that the tile-streamed attempt is not refused for creating a partition
+        ok = np.isin(I2, known[0]) & np.isin(J2, known[1])
+        I2, J2, V2 = I2[ok], J2[ok], V2[ok]
+        if len(I2) < 2:
+            continue
+        tile_mode(2)
+        names = _kernels_of(lambda: gt.set_batch(I2, J2, V2))
+        streamed += "tile_merge" in names
+        total += 1
+        tile_mode(0)
+        names0 = _kernels_of(lambda: gr.set_batch(I2, J2, V2))
+        assert "tile_merge" not in names0 and "tile_assign" not in names0
+        _same_layout(gt, gr)
+        for which in (0, 1):
+            assert gt.info(which) == gr.info(which)
+        if pol is not None:
+            pol.set_batch_policy(I2, J2, V2)
+            assert_matrix_equal(gt, pol)
+        known = (np.concatenate([known[0], I2]), np.concatenate([known[1], J2]))
+    assert total == 0 or streamed * 2 >= total, (streamed, total)   # the test is about the tile-streamed pipeline: it must have run
