@@ -840,7 +840,9 @@ struct Pcsr {
         }
     }
     // SpMV; results by slot in ws.yslot / ws.ycnt
-    static constexpr int SPMV_CELLS_PER_LANE = 4, SPMV_LG_CHUNK = 7;   // a warp's chunk = 32 lanes x 4 cells
+    // a warp's chunk = 32 lanes x 8 cells (two 256-bit loads of keys, two of values, 8 gathers of x in flight per lane):
+    // product call 71.5 -> 66.5 us at config 2 against 4 cells per lane; 16 cells per lane (114 registers): 83 us
+    static constexpr int SPMV_CELLS_PER_LANE = 8, SPMV_LG_CHUNK = 8;
     void spmv_slots(PcsrWorkspace& ws, const double* d_x, const uint8_t* d_xmask, int64_t nx, cudaStream_t st,
                     const int64_t* d_xkeys = nullptr) {
         spmv_launch_blocked<SPMV_CELLS_PER_LANE>(ws, d_x, d_xmask, nx, st, d_xkeys);

@@ -7,7 +7,6 @@ export PYTHONUNBUFFERED=1
 (timeout 500 python -m pytest tests -m gpu -q 2>&1 | tail -6) > gpurun_out/final_pytest.log; tail -2 gpurun_out/final_pytest.log
 timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/final_bench_n1.json 2> gpurun_out/final_bench_n1.err; echo "bench rc=$?"
 timeout 200 python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/final_bench_reference.json 2> /dev/null; echo "reference rc=$?"
-timeout 400 python profiles/bench_configs.py c1 c3 c5 > gpurun_out/final_configs.json 2> gpurun_out/final_configs.err; echo "configs rc=$?"
 # sanitizers on the final kernels: parity subset + the sharded worker on one rank (routing, push, unpack, device-side counts)
 (timeout 500 compute-sanitizer --tool memcheck --error-exitcode 99 --print-limit 20 python -m pytest tests/test_gpu_parity.py -q -m gpu -x \
     -k "vec_batches or matrix_batches or delete or spmv or build_layout or single_writes" 2>&1 | tail -12) > gpurun_out/final_memcheck.log
@@ -25,4 +24,4 @@ echo "memcheck sharded: $(tail -1 gpurun_out/final_memcheck_sharded.log)"
 (timeout 700 compute-sanitizer --tool racecheck --error-exitcode 99 --print-limit 20 python -m pytest tests/test_gpu_parity.py -q -m gpu -x \
     -k "matrix_batches or delete_columns or spmv_all or single_writes" 2>&1 | tail -8) > gpurun_out/final_racecheck.log
 echo "racecheck: $(tail -1 gpurun_out/final_racecheck.log)"
-bash profiles/capture_ncu.sh r02d > gpurun_out/final_capture.log 2>&1; tail -2 gpurun_out/final_capture.log
+bash profiles/capture_ncu.sh r02e > gpurun_out/final_capture.log 2>&1; tail -2 gpurun_out/final_capture.log
