@@ -6,14 +6,17 @@
 //
 //   k_tile_assign   one thread per op: column lookup (find(col_keys), pcsr.jl:342) + batch statistics, then the TILE that holds
 //                   the op's predecessor cell.  A partition span that lies inside one tile names the tile by itself (two loads of
-//                   the semaphore table); only spans that straddle a tile border run the gapped search (finds.jl:29-57) in HBM.
+//                   the semaphore table); a span that straddles tile borders is resolved by probing the first stored cell after
+//                   a border (binary search over the borders), not by the gapped search (finds.jl:29-57) over the span in HBM.
 //                   The op is dropped into its tile's bucket (fixed capacity: a batch that overflows one falls back).
-//   k_tile_merge    one CTA per tile with ops: the tile's cells are streamed into shared memory once; every op is located there
-//                   (same gapped binary search, on shared memory), hits overwrite / blank their cell (last writer wins by arrival),
-//                   misses are grouped per leaf, and every leaf whose post-batch count stays inside its own density bounds
-//                   (pma.jl:119-123 with h = 0) is re-laid at its spread! positions on the spot (pack! + spread!, moves.jl:94-172).
-//                   Leaves that fail their bounds hand their inserts, in order, to the density tree / window kernels of pma.cuh,
-//                   exactly as the random-access pipeline does.  Only modified leaves are written back.
+//   k_tile_merge    one CTA per tile with ops: the tile's KEYS are streamed into shared memory once; every op is located there
+//                   (the result of find — hit or predecessor — by a leaf-first search), hits overwrite their value in place or
+//                   set their leaf's delete bit (last writer wins by arrival), misses with a value are the leaf's inserts, and
+//                   every leaf whose post-batch count stays inside its own density bounds (pma.jl:119-123 with h = 0) is re-laid
+//                   at its spread! positions on the spot (pack! + spread!, moves.jl:94-172): one thread per leaf writes down what
+//                   lands in each cell, one thread per cell fetches and stores it.  Leaves that fail their bounds hand their
+//                   inserts, in order, to the density tree / window kernels of pma.cuh, exactly as the random-access pipeline
+//                   does.  Only modified leaves are written back.
 //
 // The result is the batch policy's layout, bit for bit: a leaf accepted at its own level and later covered by a
 // larger window is simply re-laid twice (the window kernel reads the merged leaf with no pending inserts).
