@@ -225,6 +225,8 @@ def workload_config(n_gpus):
             "rows": M_ROWS, "cols": N_COLS, "nnz": NNZ0, "batch": BATCH,
             "l2_policy": "inputs larger than L2 (2 x 268 MB gapped arrays per matrix vs 126 MB L2)", "seed": hex(SEED),
             "parallelism": f"column-range shards x{n_gpus}" if n_gpus > 1 else "single GPU",
+            # batches of >= capacity/40 ops are tile-streamed (one pass over each orientation's keys): config 2's are
+            "batch_pipeline": "tile-streamed (k_tile_assign + k_tile_merge) above capacity/40 ops per batch, random-access below",
             # kernel switches in effect (empty = the validated defaults)
             "switches": {k: os.environ[k] for k in sorted(os.environ) if k.startswith("DSA_")}}
 
