@@ -408,6 +408,9 @@ def main():
         if roofline["traffic"]:   # what the kernel physically moves (ncu DRAM bytes of the committed capture) over the live duration
             roofline["physical_gbs"] = roofline["traffic"] / (k["avg_us"] * 1e-6) / 1e9
             roofline["physical_frac"] = roofline["physical_gbs"] / peak
+        if name == "tile_merge":
+            roofline["note"] = ("one pass over the orientation's keys (8 B per cell, changed or not) replaces the random-access locate / "
+                                "apply / merge kernels for dense batches; the kernel is bound by instruction issue (DESIGN.md 6, 7)")
 
     # ---- e2e: host buffers through the host-pointer C-ABI calls ---------------------------------------------
     e2e = None
