@@ -155,3 +155,104 @@ def test_border_probes_find_the_tile_of_the_predecessor(tile_lg, lgS):
                     pos, hit = tile_find(cells[t << tile_lg:(t + 1) << tile_lg], lgS, key, lo, hi)
                     assert (t << tile_lg) + pos == ref
                     assert hit == (cells[ref] == key)
+
+
+# ----------------------------------------------------------------------------------------------------------------------------
+# the leaf re-lay of k_tile_merge (phases C, D1, D2, E) restated on the oracle's exported arrays, against the oracle's batch policy
+# ----------------------------------------------------------------------------------------------------------------------------
+def _tile_relay(e, parts, keys, vals, spread_dest, mn0, mx0):
+    """One orientation, one batch, the way csrc/tile.cuh applies it — for batches that create no partition and whose touched
+    leaves all stay inside their own bounds (otherwise None: those leaves go to the density tree / window kernels, which are
+    not restated here).  e = oracle export (tag, key, val, semaphores 1-based, col_keys, col_live)."""
+    tag, key, val = e["tag"].copy(), e["key"].copy(), e["val"].copy()
+    cap, S = len(tag), int(e["segment_capacity"])
+    sem = e["semaphores"].astype(np.int64) - 1
+    live_slots = [s for s in range(len(sem)) if e["col_live"][s]]
+    slot_of = {int(e["col_keys"][s]): s for s in live_slots}
+    order = sorted(live_slots, key=lambda s: sem[s])
+    span_end = {s: (sem[order[i + 1]] if i + 1 < len(order) else cap) for i, s in enumerate(order)}
+    # last writer wins per (partition, key), arrival order
+    last = {}
+    for arr, (p, k, v) in enumerate(zip(parts, keys, vals)):
+        if int(p) not in slot_of:
+            return None
+        last[(slot_of[int(p)], int(k))] = (arr, float(v))
+    per_leaf = {}
+    for (s, k), (arr, v) in last.items():
+        ps, pe = int(sem[s]), int(span_end[s])
+        idx = ps + np.flatnonzero(tag[ps:pe])          # stored cells of the span, the semaphore (key 0) first
+        j = int(np.searchsorted(key[idx], k, side="right")) - 1
+        pos = int(idx[j])
+        per_leaf.setdefault(pos // S, []).append((pos, key[pos] == k and pos != ps, k, v))
+    new_sem = sem.copy()
+    for leaf, ops in per_leaf.items():
+        c0 = leaf * S
+        dele = {pos for pos, hit, k, v in ops if hit and v == 0.0}
+        for pos, hit, k, v in ops:
+            if hit and v != 0.0:
+                val[pos] = v                                  # writes.jl:16-19
+        ins = sorted((pos, k, v) for pos, hit, k, v in ops if not hit and v != 0.0)   # by (predecessor cell, key)
+        surv = [q for q in range(S) if tag[c0 + q] and (c0 + q) not in dele]
+        m = len(surv) + len(ins)
+        if dele or ins:
+            if m < mn0 or m > mx0:
+                return None
+        if not ins:
+            for pos in dele:                                  # writes.jl:65-68
+                tag[pos] = 0
+            continue
+        # merged order: an insert goes after the survivors up to its predecessor cell and after the inserts ordered before it
+        items = [((q, 0, 0), int(key[c0 + q]), float(val[c0 + q])) for q in surv]
+        items += [((pos - c0, 1, k), int(k), float(v)) for pos, k, v in ins]
+        items.sort(key=lambda it: it[0])
+        tag[c0:c0 + S] = 0
+        for r, (_, k, v) in enumerate(items):                 # pack! + spread! (moves.jl:94-172)
+            d = c0 + spread_dest(S, m, r)
+            tag[d], key[d], val[d] = 1, k, v
+            if k == 0:
+                new_sem[int(v) - 1] = d                       # moves.jl:160-166
+    return tag, key, val, new_sem + 1
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_leaf_relay_of_the_tile_kernel_equals_the_batch_policy(seed):
+    import ctypes as C
+
+    import dsa_b200 as D
+    L = D.lib()
+    L.dsa_spread_dest.restype = C.c_int64
+    spread_dest = lambda c, m, r: int(L.dsa_spread_dest(C.c_int64(c), C.c_int64(m), C.c_int64(r)))
+    rng = np.random.default_rng(2000 + seed)
+    m, n = [(60, 50), (300, 40), (40, 400), (500, 500), (200, 900), (1000, 30)][seed]
+    nnz0 = int(rng.integers(2000, 9000))
+    I, J = rng.integers(1, m + 1, nnz0), rng.integers(1, n + 1, nnz0)
+    V = rng.integers(1, 100, nnz0).astype(float)
+    pol = O.Matrix(I, J, V, m=m, n=n)
+    checked = 0
+    for rnd in range(6):
+        nb = int(rng.integers(20, 300))
+        src = rng.integers(0, nnz0, nb)
+        I2 = np.where(rng.random(nb) < 0.5, I[src], rng.choice(I, nb))     # existing rows and columns only
+        J2 = np.where(rng.random(nb) < 0.5, J[src], rng.choice(J, nb))
+        V2 = np.where(rng.random(nb) < 0.4, 0.0, rng.integers(1, 100, nb).astype(float))
+        I2[:4], J2[:4] = I2[4:8], J2[4:8]                                   # repeated keys: last writer wins
+        before = [pol.export(w) for w in (0, 1)]
+        pol.set_batch_policy(I2, J2, V2)
+        for w in (0, 1):
+            e = before[w]
+            mn, mx = np.zeros(40, np.int64), np.zeros(40, np.int64)
+            assert L.dsa_level_bounds(C.c_int64(int(e["segment_capacity"])), C.c_int64(int(e["height"])),
+                                      mn.ctypes.data_as(C.c_void_p), mx.ctypes.data_as(C.c_void_p)) == 0
+            parts, keys = (J2, I2) if w == 0 else (I2, J2)                  # matrix.jl:53-59
+            got = _tile_relay(e, parts, keys, V2, spread_dest, int(mn[0]), int(mx[0]))
+            if got is None:
+                continue   # a leaf left its bounds: the density tree / window kernels take over (not restated here)
+            after = pol.export(w)
+            tag, key, val, sem = got
+            assert np.array_equal(tag, after["tag"]), (seed, rnd, w)
+            mk = tag.astype(bool)
+            assert np.array_equal(key[mk], after["key"][mk]) and np.array_equal(val[mk], after["val"][mk])
+            lv = after["col_live"].astype(bool)
+            assert np.array_equal(sem[lv], after["semaphores"][lv])
+            checked += 1
+    assert checked >= 3, "the batches are meant to stay inside the leaves' bounds most of the time"
